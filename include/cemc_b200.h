@@ -1,0 +1,185 @@
+/*
+ * cemc_b200.h -- C ABI of the B200-native cluster-expansion Metropolis hot path.
+ *
+ * Drop-in boundary for davidkleiven/CEMC's `CEUpdater` (reference paths are
+ * relative to /root/reference):
+ *
+ *   reference interface                                   replaced by
+ *   ----------------------------------------------------  -----------------------------
+ *   CEUpdater::init           cpp/src/ce_updater.cpp:32    cemc_create (+ cemc_tables)
+ *   CEUpdater::update_cf      cpp/src/ce_updater.cpp:313   cemc_trial_changes / cemc_replay / cemc_run_*
+ *   CEUpdater::calculate      cpp/src/ce_updater.cpp:471   cemc_trial_changes
+ *   CEUpdater::undo_changes   cpp/src/ce_updater.cpp:408   cemc_undo_changes
+ *   CEUpdater::clear_history  cpp/src/ce_updater.cpp:552   cemc_clear_history
+ *   CEUpdater::get_energy     cpp/src/ce_updater.cpp:236   cemc_get_energy
+ *   CEUpdater::get_cf         cpp/src/ce_updater.cpp:570   cemc_get_cf
+ *   CEUpdater::get_singlets   cpp/src/ce_updater.cpp:655   cemc_get_cf (+ singlet index list, host side)
+ *   CEUpdater::set_ecis       cpp/src/ce_updater.cpp:615   cemc_set_ecis
+ *   CEUpdater::set_symbols    cpp/src/ce_updater.cpp:606   cemc_set_occupancy
+ *   Cython binding            cemc/cpp_ext/ce_updater.pxd:9-43, pyce_updater.pyx:5-60
+ *
+ * The per-move Python loop of the reference samplers cannot feed a GPU one
+ * launch per move, so the loop bodies move under the boundary as well:
+ *
+ *   Montecarlo._mc_step/_accept        cemc/mcmc/montecarlo.py:910-1038     cemc_run_canonical
+ *   SGCMonteCarlo._get_trial_move      cemc/mcmc/sgc_montecarlo.py:62-76    cemc_run_sgc
+ *   SGCObserver.__call__               cemc/mcmc/mc_observers.py:222-270    accumulators (cemc_get_accumulators)
+ *   ParallelTempering._perform_exchange_move
+ *                                      cemc/mcmc/parallel_tempering.py:153  cemc_pt_exchange
+ *
+ * Conventions: every function returns 0 on success, non-zero on error;
+ * cemc_last_error() gives the message.  Host pointers unless the name says
+ * `_dev`.  All arrays are dense, row-major, replica-major ([R][...]).
+ * One handle = one CUDA device + one stream; calls are stream-ordered and
+ * the handle is not thread-safe.  No torch types appear in this ABI.
+ */
+#ifndef CEMC_B200_H
+#define CEMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEMC_MAX_CLUSTER_SIZE 4      /* cpp/src/cluster.cpp:131-171: sizes 2..4 */
+#define CEMC_POS_REF (-1)            /* fam_pos entry that denotes the changed site itself */
+
+enum cemc_eci_kind {
+  CEMC_ECI_EMPTY   = 0,              /* name starts with "c0": CF copied (ce_updater.cpp:357) */
+  CEMC_ECI_SINGLET = 1,              /* name starts with "c1" (ce_updater.cpp:366)           */
+  CEMC_ECI_CLUSTER = 2               /* n-body term          (ce_updater.cpp:373-404)        */
+};
+
+/* Flattened, read-only tables: what CEUpdater::init builds from the Python
+ * settings object (cluster_info, trans_matrix, basis_functions, ECIs).      */
+typedef struct cemc_tables {
+  int32_t n_sites;       /* N, including background sites                          */
+  int32_t n_species;     /* S: sorted(unique_elements U symbols present)           */
+  int32_t n_bf;          /* D = num_unique_elements - 1                            */
+  int32_t n_cols;        /* K: distinct translation-matrix columns used            */
+  int32_t n_eci;         /* number of ECIs == CFs, in lexicographic name order     */
+  int32_t n_symm;        /* translational symmetry groups                          */
+  int32_t n_fam;         /* (symmetry group, cluster family) tables                */
+  int32_t n_deco;        /* total rows of `deco`                                   */
+  const int32_t *trans;          /* [N][K]   T(site, col)                           */
+  const int32_t *symm_of_site;   /* [N]      symmetry group, -1 = background        */
+  const int32_t *symm_count;     /* [n_symm] N_g sites per group                    */
+  const double  *bf;             /* [D][S]   basis functions                        */
+  const double  *eci;            /* [n_eci]  initial ECIs (same for all replicas)   */
+  const int32_t *eci_kind;       /* [n_eci]  enum cemc_eci_kind                     */
+  const int32_t *eci_bf;         /* [n_eci]  singlets: decoration number            */
+  const int32_t *fam_size;       /* [n_fam]  n (2..4)                               */
+  const int32_t *fam_nsub;       /* [n_fam]  M sub-clusters                         */
+  const int32_t *fam_pos_off;    /* [n_fam+1] offsets into fam_pos                  */
+  const int32_t *fam_pos;        /* per family [M][n]: sorted position k holds the
+                                    changed site (CEMC_POS_REF) or column 0..K-1   */
+  const int32_t *term_fam;       /* [n_symm][n_eci] family id or -1                 */
+  const int32_t *term_count;     /* [n_symm][n_eci] cluster_symm_group_count[prefix]*/
+  const int32_t *term_deco_off;  /* [n_symm*n_eci + 1] range of rows in `deco`      */
+  const int8_t  *deco;           /* [n_deco][4] equivalent decorations, stored order */
+} cemc_tables;
+
+/* per-replica accumulator slots (doubles), see cemc_get_accumulators */
+enum cemc_acc_slot {
+  CEMC_ACC_COUNT     = 0,   /* number of sampled steps                              */
+  CEMC_ACC_E         = 1,   /* sum E/ref      (Averager, cemc/mcmc/averager.py:21)   */
+  CEMC_ACC_E2        = 2,   /* sum E*E/ref                                          */
+  CEMC_ACC_SINGLET0  = 3    /* then per singlet d: sum s, sum s*s, sum s*E          */
+};
+#define CEMC_ACC_STRIDE(n_singlets) (3 + 3 * (n_singlets))
+
+/* summation-order policy for the cluster spin products */
+enum cemc_order_mode {
+  CEMC_ORDER_REFERENCE = 0, /* reference operation order: bit-exact CF and E       */
+  CEMC_ORDER_TREE      = 1  /* lanes over sub-clusters + tree reduction; bit-exact
+                               only when all basis-function values are small
+                               integers (binary +-1), else ~1e-15 relative         */
+};
+
+typedef struct cemc_handle cemc_handle;
+
+const char *cemc_last_error(void);
+int  cemc_version(void);
+
+/* n_replicas chains on `device`; `stream` is a cudaStream_t or NULL (own stream).
+ * replica_offset = global index of local replica 0 (keys the Philox streams so
+ * that sharding over GPUs does not change any chain).                        */
+int cemc_create(const cemc_tables *tables, int n_replicas, int replica_offset,
+                int device, void *stream, cemc_handle **out);
+int cemc_destroy(cemc_handle *h);
+int cemc_set_stream(cemc_handle *h, void *stream);
+int cemc_synchronize(cemc_handle *h);
+int cemc_set_order_mode(cemc_handle *h, int mode);
+
+/* ---- state ---- */
+int cemc_set_occupancy(cemc_handle *h, const int8_t *occ /*[R][N]*/);
+int cemc_get_occupancy(cemc_handle *h, int8_t *occ /*[R][N]*/);
+int cemc_set_cf(cemc_handle *h, const double *cf /*[R][n_eci]*/);
+int cemc_get_cf(cemc_handle *h, double *cf /*[R][n_eci]*/);
+/* brute-force CFs from the definition, all replicas */
+int cemc_recompute_cf(cemc_handle *h);
+/* per_replica = 0: eci is [n_eci] broadcast; 1: [R][n_eci].  Energies are
+ * re-evaluated (montecarlo.py:203, sgc_montecarlo.py:260).                   */
+int cemc_set_ecis(cemc_handle *h, const double *eci, int per_replica);
+int cemc_get_ecis(cemc_handle *h, double *eci /*[R][n_eci]*/);
+int cemc_get_energy(cemc_handle *h, double *energy /*[R]*/);
+int cemc_set_kT(cemc_handle *h, const double *kT /*[R]*/);
+int cemc_get_kT(cemc_handle *h, double *kT /*[R]*/);
+int cemc_seed(cemc_handle *h, uint64_t seed);
+int cemc_get_counters(cemc_handle *h, uint64_t *steps /*[R]*/, uint64_t *accepted /*[R]*/);
+int cemc_reset_counters(cemc_handle *h);
+
+/* ---- the reference's per-call surface (one replica, trial semantics) ---- */
+/* CEUpdater::calculate: apply changes sequentially, keep them undoable.     */
+int cemc_trial_changes(cemc_handle *h, int replica, int n_changes,
+                       const int32_t *sites, const int8_t *old_species,
+                       const int8_t *new_species, double *energy_out);
+int cemc_undo_changes(cemc_handle *h, int replica);
+int cemc_clear_history(cemc_handle *h, int replica);
+
+/* ---- batched Metropolis ---- */
+/* Replay recorded proposals + uniforms.  sites[.][1] < 0
+ * marks a one-site (SGC) step.  accepted_out / e_after_out may be NULL.       */
+int cemc_replay(cemc_handle *h, int n_steps,
+                const int32_t *sites /*[R][n_steps][2]*/,
+                const int8_t *new_species /*[R][n_steps][2]*/,
+                const double *uniforms /*[R][n_steps]*/,
+                uint8_t *accepted_out /*[R][n_steps]*/,
+                double *e_after_out /*[R][n_steps]*/);
+/* n_steps Metropolis trial moves per replica with on-device Philox proposals. */
+int cemc_run_sgc(cemc_handle *h, int64_t n_steps);
+int cemc_run_canonical(cemc_handle *h, int64_t n_steps);
+/* optional trace of the last run (device proposals): enable before running   */
+int cemc_set_trace(cemc_handle *h, int64_t capacity_steps);
+int cemc_get_trace(cemc_handle *h, int64_t n_steps, int32_t *sites /*[R][n][2]*/,
+                   int8_t *new_species /*[R][n][2]*/, double *uniforms /*[R][n]*/,
+                   uint8_t *accepted /*[R][n]*/, double *e_after /*[R][n]*/);
+
+/* ---- observers (Averager / SGCObserver sums) ---- */
+int cemc_reset_accumulators(cemc_handle *h, const double *ref /*[R] or NULL (=1.0)*/);
+int cemc_get_accumulators(cemc_handle *h, double *acc /*[R][CEMC_ACC_STRIDE(D)]*/);
+
+/* ---- parallel tempering ---- */
+/* One exchange sweep over temperature slots.  slot_of_replica[g] for all
+ * n_total global replicas and the matching energies (device pointer, e.g. the
+ * output of an NCCL all-gather).  direction 0 = "up", 1 = "down".  Updates
+ * slot_of_replica_dev in place (identically on every rank) and the kT of the
+ * local replicas from kT_of_slot_dev.                                        */
+int cemc_pt_exchange(cemc_handle *h, int n_total, const double *energies_dev,
+                     int32_t *slot_of_replica_dev, const double *kT_of_slot_dev,
+                     int direction, uint64_t round, int32_t *n_accepted_dev);
+/* device pointer to the local energies [R] (input of the all-gather)        */
+int cemc_energy_dev(cemc_handle *h, double **ptr);
+
+/* ---- timing on the handle's stream (CUDA events) ---- */
+int cemc_timer_start(cemc_handle *h);
+int cemc_timer_stop(cemc_handle *h, float *ms);
+/* kernels launched by this handle since creation (bench gpu_launches)       */
+int cemc_launch_count(cemc_handle *h, uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEMC_B200_H */
