@@ -1,0 +1,117 @@
+"""ctypes binding of the C-ABI shared library (include/cemc_b200.h).
+
+The library is built in-tree (``__graft_entry__.build()`` / ``build_ext()``
+below) as ``cemc_b200/_cemc_b200.so``.  There is NO fallback: if the library
+is missing or no CUDA device is usable, the product raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from .tables import CemcTablesStruct
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_cemc_b200.so")
+SOURCES = [os.path.join(_HERE, "csrc", "cemc_b200.cu"),
+           os.path.join(_HERE, "csrc", "cemc_kernels.cuh"),
+           os.path.join(os.path.dirname(_HERE), "include", "cemc_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+              "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-fmad=false"]
+
+_lib = None
+
+
+class CemcError(RuntimeError):
+    pass
+
+
+def build_ext(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA extension for sm_100a (nvcc cross-compiles w/o GPU)."""
+    newest = max(os.path.getmtime(s) for s in SOURCES)
+    if not force and os.path.exists(LIB_PATH) and \
+            os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB_PATH, SOURCES[0]]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_u64p = C.POINTER(C.c_uint64)
+_i32p = C.POINTER(C.c_int32)
+_i8p = C.POINTER(C.c_int8)
+_u8p = C.POINTER(C.c_uint8)
+_f64p = C.POINTER(C.c_double)
+_H = C.c_void_p
+
+# name -> argtypes; every function returns int except the two noted below.
+SIGNATURES = {
+    "cemc_create": [C.POINTER(CemcTablesStruct), C.c_int, C.c_int, C.c_int,
+                    C.c_void_p, C.POINTER(_H)],
+    "cemc_destroy": [_H],
+    "cemc_set_stream": [_H, C.c_void_p],
+    "cemc_synchronize": [_H],
+    "cemc_set_order_mode": [_H, C.c_int],
+    "cemc_set_occupancy": [_H, _i8p],
+    "cemc_get_occupancy": [_H, _i8p],
+    "cemc_set_cf": [_H, _f64p],
+    "cemc_get_cf": [_H, _f64p],
+    "cemc_recompute_cf": [_H],
+    "cemc_set_ecis": [_H, _f64p, C.c_int],
+    "cemc_get_ecis": [_H, _f64p],
+    "cemc_get_energy": [_H, _f64p],
+    "cemc_set_kT": [_H, _f64p],
+    "cemc_get_kT": [_H, _f64p],
+    "cemc_seed": [_H, C.c_uint64],
+    "cemc_set_step": [_H, _u64p],
+    "cemc_set_sgc_species": [_H, C.c_int, _i8p],
+    "cemc_get_counters": [_H, _u64p, _u64p],
+    "cemc_reset_counters": [_H],
+    "cemc_trial_changes": [_H, C.c_int, C.c_int, _i32p, _i8p, _i8p, _f64p],
+    "cemc_undo_changes": [_H, C.c_int],
+    "cemc_clear_history": [_H, C.c_int],
+    "cemc_replay": [_H, C.c_int, _i32p, _i8p, _f64p, _u8p, _f64p],
+    "cemc_run_sgc": [_H, C.c_int64],
+    "cemc_run_canonical": [_H, C.c_int64],
+    "cemc_set_trace": [_H, C.c_int64],
+    "cemc_get_trace": [_H, C.c_int64, _i32p, _i8p, _f64p, _u8p, _f64p],
+    "cemc_reset_accumulators": [_H, _f64p],
+    "cemc_get_accumulators": [_H, _f64p],
+    "cemc_pt_exchange": [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                         C.c_int, C.c_uint64, C.c_void_p],
+    "cemc_energy_dev": [_H, C.POINTER(C.c_void_p)],
+    "cemc_timer_start": [_H],
+    "cemc_timer_stop": [_H, C.POINTER(C.c_float)],
+    "cemc_launch_count": [_H, _u64p],
+}
+
+
+def load():
+    """Load the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "cemc_b200: CUDA extension {} is missing -- run "
+            "`python -c 'import __graft_entry__ as g; g.build()'`; there is "
+            "no CPU fallback".format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.cemc_last_error.restype = C.c_char_p
+    lib.cemc_last_error.argtypes = []
+    lib.cemc_version.restype = C.c_int
+    lib.cemc_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise CemcError(load().cemc_last_error().decode("utf-8", "replace"))

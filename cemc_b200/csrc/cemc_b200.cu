@@ -1,0 +1,941 @@
+// cemc_b200.cu -- C ABI (include/cemc_b200.h) over the sm_100a kernels.
+//
+// Host side of the drop-in boundary: turns the flattened tables into the
+// device "cluster program", owns the per-replica device state, and launches
+// the kernels of cemc_kernels.cuh on the handle's stream.  No CPU fallback:
+// every entry point either runs on the GPU or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cemc_b200.h"
+#include "cemc_kernels.cuh"
+
+using namespace cemc;
+
+static thread_local std::string g_err;
+static int fail(const std::string &m, int code = 1) { g_err = m; return code; }
+
+#define CU(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e_ = (x);                                                          \
+    if (e_ != cudaSuccess)                                                         \
+      return fail(std::string(#x) + ": " + cudaGetErrorString(e_), 100);           \
+  } while (0)
+
+template <class T>
+static cudaError_t upload(T **dst, const T *src, size_t n) {
+  cudaError_t e = cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (n) e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+struct TrialEntry { int32_t site; int8_t old_sp; };
+
+struct cemc_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int R = 0, replica_offset = 0;
+  int acc_stride = 0;
+  int order_mode = CEMC_ORDER_REFERENCE;
+  uint64_t seed = 0;
+  uint64_t launches = 0;
+  int max_smem_optin = 0;
+  DeviceTables t{};
+  ReplicaState st{};
+  std::vector<void *> owned;            // device allocations to free
+  bool tracker_dirty = true;
+  // trial history (CFHistoryTracker semantics, cf_history_tracker.cpp)
+  std::vector<std::vector<TrialEntry>> trial_log;
+  double *cf_committed = nullptr;       // [R][n_eci]
+  double *e_committed = nullptr;        // [R]
+  // scratch
+  int32_t *d_sites = nullptr; int8_t *d_news = nullptr; double *d_u = nullptr;
+  uint8_t *d_acc = nullptr; double *d_e = nullptr; long long scratch_steps = 0;
+  long long trace_capacity = 0;
+  int32_t *tr_sites = nullptr; int8_t *tr_news = nullptr; double *tr_u = nullptr;
+  uint8_t *tr_acc = nullptr; double *tr_e = nullptr;
+  double *cf_partial = nullptr;         // [R][n_jobs]
+  int32_t *pt_scratch = nullptr; int pt_scratch_n = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // host copies needed by the API
+  std::vector<int32_t> symm_of_site;
+  std::vector<int8_t> allowed;
+  int n_jobs = 0;
+};
+
+// ---------------------------------------------------------------------------
+// small kernels
+
+// E = N * sum_i eci_i * cf_i, sequential (ce_updater.cpp:236-242, named_array.cpp:25-33)
+__global__ void energy_kernel(int R, int n_eci, int N, const double *eci, const double *cf,
+                              double *e_cur) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  double e = 0.0;
+  for (int i = 0; i < n_eci; i++)
+    e = __dadd_rn(e, __dmul_rn(eci[(size_t)r * n_eci + i], cf[(size_t)r * n_eci + i]));
+  e_cur[r] = __dmul_rn(e, (double)(unsigned)N);
+}
+
+__global__ void set_sites_kernel(int8_t *occ, int n, const int32_t *sites, const int8_t *vals) {
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int i = 0; i < n; i++) occ[sites[i]] = vals[i];
+}
+
+// SwapMoveIndexTracker.init_tracker (swap_move_index_tracker.py:22-36): per-species
+// site lists in ascending site order.  One CTA per replica, stable counting sort.
+__global__ void tracker_init_kernel(int N, int S, const int32_t *symm_of_site, const int8_t *occ,
+                                    int32_t *list, int32_t *loc, int32_t *off) {
+  const int r = blockIdx.x;
+  const int8_t *o = occ + (size_t)r * N;
+  int32_t *ls = list + (size_t)r * N, *lc = loc + (size_t)r * N, *of = off + (size_t)r * (S + 1);
+  __shared__ int cnt[129];
+  for (int i = threadIdx.x; i <= S; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  for (int a = threadIdx.x; a < N; a += blockDim.x)
+    if (symm_of_site[a] >= 0) atomicAdd(&cnt[o[a]], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int sp = 0; sp < S; sp++) { of[sp] = run; run += cnt[sp]; }
+    of[S] = run;
+  }
+  __syncthreads();
+  // one thread per species walks the sites in ascending order (deterministic)
+  for (int sp = threadIdx.x; sp < S; sp += blockDim.x) {
+    int k = 0;
+    const int base = of[sp];
+    for (int a = 0; a < N; a++)
+      if (symm_of_site[a] >= 0 && o[a] == sp) { ls[base + k] = a; lc[a] = k; k++; }
+  }
+  for (int a = threadIdx.x; a < N; a += blockDim.x)
+    if (symm_of_site[a] < 0) lc[a] = -1;
+}
+
+// Brute-force CF partial sums (definition in SURVEY.md 8c): one CTA per (job, replica).
+// jobs [0, n_tasks_total) are cluster tasks; the rest are singlet ECIs.
+__global__ void cf_partial_kernel(DeviceTables t, const int8_t *occ, double *partial, int n_jobs) {
+  const int job = blockIdx.x, r = blockIdx.y;
+  const int8_t *o = occ + (size_t)r * t.N;
+  double acc = 0.0;
+  if (job < t.n_tasks_total) {
+    int g = 0;
+    while (job >= t.task_base[g + 1]) g++;
+    const Task T = t.tasks[job];
+    const Fam F = t.fams[T.fam];
+    for (int a = threadIdx.x; a < t.N; a += blockDim.x) {
+      if (t.symm_of_site[a] != g) continue;
+      const int me = o[a];
+      double sp = 0.0;
+      for (int m = 0; m < F.M; m++) {
+        const uint32_t pp = t.pos[F.pos_off + m];
+        double tt = 1.0;
+        for (int k = 0; k < F.n; k++) {
+          const int p = (pp >> (8 * k)) & 0xff;
+          const int dk = (T.deco >> (8 * k)) & 0xff;
+          const int id = (p == t.K) ? me : (int)o[t.trans[(size_t)a * t.K + p]];
+          tt *= t.bf[dk * t.S + id];
+        }
+        sp += tt;
+      }
+      acc += sp;
+    }
+  } else {
+    const int d = job - t.n_tasks_total;   // basis function number
+    for (int a = threadIdx.x; a < t.N; a += blockDim.x)
+      if (t.symm_of_site[a] >= 0) acc += t.bf[d * t.S + o[a]];
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(size_t)r * n_jobs + job] = red[0];
+}
+
+__global__ void cf_final_kernel(DeviceTables t, const double *partial, int n_jobs, double *cf) {
+  const int r = blockIdx.x;
+  for (int i = threadIdx.x; i < t.n_eci; i += blockDim.x) {
+    double v = 0.0;
+    bool is_cluster = false, any = false;
+    for (int g = 0; g < t.n_symm; g++) {
+      const Fin f = t.fin[g * t.n_eci + i];
+      if (f.kind == 0) { v = 1.0; break; }
+      if (f.kind == 1) { v = partial[(size_t)r * n_jobs + t.n_tasks_total + f.d] / (double)t.N; break; }
+      is_cluster = true;
+      if (f.kind == 2 && f.t1 > f.t0) {
+        double sg = 0.0;
+        for (int q = f.t0; q < f.t1; q++) sg += partial[(size_t)r * n_jobs + t.task_base[g] + q];
+        v += sg / ((double)(f.t1 - f.t0) * f.div);
+        any = true;
+      }
+    }
+    if (is_cluster && !any) v = 0.0;
+    cf[(size_t)r * t.n_eci + i] = v;
+  }
+}
+
+// ParallelTempering._perform_exchange_move (parallel_tempering.py:153-175): the
+// slot<->replica map is permuted instead of copying configurations (:146-151).
+__global__ void pt_exchange_kernel(int n_total, const double *energies, int32_t *slot_of_replica,
+                                   const double *kT_of_slot, int direction, unsigned long long seed,
+                                   unsigned long long round, int32_t *rep_of_slot, double *kT_local,
+                                   int offset, int R, int32_t *n_accepted) {
+  __shared__ int s_acc;
+  if (threadIdx.x == 0) s_acc = 0;
+  for (int g = threadIdx.x; g < n_total; g += blockDim.x) rep_of_slot[slot_of_replica[g]] = g;
+  __syncthreads();
+  const int n_pairs = n_total / 2;
+  for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
+    const int i = direction == 0 ? 2 * p : n_total - 1 - 2 * p;
+    const int j = direction == 0 ? i + 1 : i - 1;
+    if (j < 0 || j >= n_total) continue;
+    const int r1 = rep_of_slot[i], r2 = rep_of_slot[j];
+    const double dE = __dsub_rn(energies[r1], energies[r2]);          // :139
+    const double b1 = __ddiv_rn(1.0, kT_of_slot[i]);                  // :140
+    const double b2 = __ddiv_rn(1.0, kT_of_slot[j]);                  // :141
+    const double pr = exp(__dmul_rn(__dsub_rn(b1, b2), dE));          // :143
+    uint32_t c0 = (uint32_t)round, c1 = (uint32_t)(round >> 32), c2 = (uint32_t)i, c3 = 2;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    if (u53(c0, c1) < pr) {                                           // :166
+      rep_of_slot[i] = r2; rep_of_slot[j] = r1;
+      atomicAdd(&s_acc, 1);
+    }
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < n_total; s += blockDim.x) slot_of_replica[rep_of_slot[s]] = s;
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += blockDim.x) kT_local[r] = kT_of_slot[slot_of_replica[offset + r]];
+  if (threadIdx.x == 0 && n_accepted) *n_accepted = s_acc;
+}
+
+// ---------------------------------------------------------------------------
+template <class T>
+static int dalloc(cemc_handle *h, T **p, size_t n, bool zero = true) {
+  CU(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+  h->owned.push_back(*p);
+  if (zero) CU(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  return 0;
+}
+
+template <class T>
+static int dupload(cemc_handle *h, const T **p, const std::vector<T> &v) {
+  T *d = nullptr;
+  CU(upload(&d, v.data(), v.size()));
+  h->owned.push_back(d);
+  *p = d;
+  return 0;
+}
+
+static int check_status(cemc_handle *h) {
+  std::vector<int32_t> stt(h->R);
+  CU(cudaMemcpyAsync(stt.data(), h->st.status, sizeof(int32_t) * h->R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < h->R; r++) {
+    if (stt[r]) {
+      CU(cudaMemsetAsync(h->st.status, 0, sizeof(int32_t) * h->R, h->stream));
+      char buf[160];
+      const char *why = stt[r] == 1 ? "Attempting to move a background atom!"
+                        : stt[r] == 2 ? "There is only one element in the given atoms object!"
+                                      : "proposal out of range";
+      snprintf(buf, sizeof buf, "replica %d: %s", r, why);
+      return fail(buf, 10 + stt[r]);
+    }
+  }
+  return 0;
+}
+
+extern "C" {
+
+const char *cemc_last_error(void) { return g_err.c_str(); }
+int cemc_version(void) { return 100; }
+
+int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int device, void *stream,
+                cemc_handle **out) {
+  if (!tb || !out) return fail("null argument");
+  if (n_replicas < 1) return fail("n_replicas must be >= 1");
+  const int N = tb->n_sites, S = tb->n_species, D = tb->n_bf, K = tb->n_cols, n_eci = tb->n_eci;
+  if (N < 1 || S < 1 || S > 127 || D < 1 || K < 1 || n_eci < 1 || tb->n_symm < 1)
+    return fail("invalid table sizes");
+  if (K > 254) return fail("more than 254 translation-matrix columns are not supported");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("no such CUDA device");
+  CU(cudaSetDevice(device));
+
+  // validate tables the way the reference's Python layer does
+  for (int f = 0; f < tb->n_fam; f++)
+    if (tb->fam_size[f] < 2 || tb->fam_size[f] > CEMC_MAX_CLUSTER_SIZE)
+      return fail("Only cluster sizes 2, 3 and 4 are supported!");          // cluster.cpp:168
+  for (size_t q = 0; q < (size_t)N * K; q++)
+    if (tb->trans[q] < 0 || tb->trans[q] >= N) return fail("translation matrix entry out of range");
+  {
+    std::vector<char> col_used(K, 0);
+    for (int f = 0; f < tb->n_fam; f++)
+      for (int q = tb->fam_pos_off[f]; q < tb->fam_pos_off[f + 1]; q++) {
+        const int p = tb->fam_pos[q];
+        if (p != CEMC_POS_REF && (p < 0 || p >= K)) return fail("fam_pos entry out of range");
+        if (p >= 0) col_used[p] = 1;
+      }
+    for (int s = 0; s < N; s++) {
+      if (tb->symm_of_site[s] < 0) continue;
+      for (int c = 0; c < K; c++)
+        if (col_used[c] && tb->trans[(size_t)s * K + c] == s)
+          return fail("The simulation cell is so small that the same site is present multiple "
+                      "times within one cluster. Increase the size of the simulation cell.");
+    }
+  }
+
+  cemc_handle *h = new cemc_handle();
+  h->device = device;
+  h->R = n_replicas;
+  h->replica_offset = replica_offset;
+  if (stream) h->stream = (cudaStream_t)stream;
+  else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  CU(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+
+  // ---- build the cluster program ------------------------------------------
+  DeviceTables &t = h->t;
+  t.N = N; t.S = S; t.D = D; t.K = K; t.KP = K + 1; t.n_eci = n_eci; t.n_symm = tb->n_symm;
+  t.n_fam = tb->n_fam;
+  std::vector<Fam> fams(tb->n_fam);
+  std::vector<uint32_t> pos;
+  for (int f = 0; f < tb->n_fam; f++) {
+    const int n = tb->fam_size[f], M = tb->fam_nsub[f];
+    if (M > 65535) return fail("too many sub-clusters in one family");
+    fams[f].n = (uint16_t)n; fams[f].M = (uint16_t)M; fams[f].pos_off = (uint32_t)pos.size();
+    const int32_t *src = tb->fam_pos + tb->fam_pos_off[f];
+    for (int m = 0; m < M; m++) {
+      uint32_t w = 0;
+      for (int k = 0; k < n; k++) {
+        const int p = src[m * n + k];
+        w |= (uint32_t)(p == CEMC_POS_REF ? K : p) << (8 * k);
+      }
+      pos.push_back(w);
+    }
+  }
+  std::vector<Task> tasks;
+  std::vector<int32_t> task_base(tb->n_symm + 1, 0);
+  std::vector<Fin> fin((size_t)tb->n_symm * n_eci);
+  std::vector<int32_t> singlet_idx;
+  int max_tasks = 0;
+  for (int g = 0; g < tb->n_symm; g++) {
+    task_base[g] = (int32_t)tasks.size();
+    for (int i = 0; i < n_eci; i++) {
+      Fin &f = fin[(size_t)g * n_eci + i];
+      f.kind = tb->eci_kind[i]; f.d = tb->eci_bf[i]; f.t0 = f.t1 = 0; f.scale = 0.0; f.div = 1.0;
+      if (f.kind == CEMC_ECI_SINGLET && (f.d < 0 || f.d >= D)) return fail("singlet decoration out of range");
+      if (f.kind != CEMC_ECI_CLUSTER) continue;
+      const int term = g * n_eci + i;
+      const int fam = tb->term_fam[term];
+      if (fam < 0) { f.kind = -1; continue; }
+      const int d0 = tb->term_deco_off[term], d1 = tb->term_deco_off[term + 1];
+      if (d1 <= d0) return fail("cluster ECI without decorations");
+      const int n = tb->fam_size[fam];
+      f.t0 = (int32_t)tasks.size() - task_base[g];
+      for (int e = d0; e < d1; e++) {
+        Task T; T.deco = 0; T.fam = (uint16_t)fam; T.eci = (uint16_t)i;
+        for (int k = 0; k < n; k++) {
+          const int dk = tb->deco[4 * e + k];
+          if (dk < 0 || dk >= D) return fail("decoration number out of range");
+          T.deco |= (uint32_t)dk << (8 * k);
+        }
+        tasks.push_back(T);
+      }
+      f.t1 = (int32_t)tasks.size() - task_base[g];
+      f.scale = (double)n / (double)(d1 - d0);                                   // :400
+      f.div = (double)(tb->term_count[term] * tb->symm_count[g]);                // :402
+    }
+    max_tasks = std::max(max_tasks, (int)tasks.size() - task_base[g]);
+  }
+  task_base[tb->n_symm] = (int32_t)tasks.size();
+  for (int i = 0; i < n_eci; i++)
+    if (tb->eci_kind[i] == CEMC_ECI_SINGLET) singlet_idx.push_back(i);
+  t.n_pos_words = (int)pos.size(); t.n_tasks_total = (int)tasks.size(); t.max_tasks = max_tasks;
+  t.n_singlets = (int)singlet_idx.size();
+  h->acc_stride = CEMC_ACC_STRIDE(t.n_singlets);
+  h->n_jobs = t.n_tasks_total + D;
+
+  std::vector<int32_t> trans(tb->trans, tb->trans + (size_t)N * K);
+  std::vector<int32_t> symm(tb->symm_of_site, tb->symm_of_site + N);
+  std::vector<double> bf(tb->bf, tb->bf + (size_t)D * S);
+  h->symm_of_site = symm;
+  std::vector<int32_t> active;
+  for (int s = 0; s < N; s++) if (symm[s] >= 0) active.push_back(s);
+  t.n_active = (int)active.size();
+  if (t.n_active == 0) return fail("no active sites");
+  h->allowed.resize(S);
+  for (int s = 0; s < S; s++) h->allowed[s] = (int8_t)s;
+  t.n_allowed = S;
+  int rc;
+  if ((rc = dupload(h, &t.trans, trans))) return rc;
+  if ((rc = dupload(h, &t.symm_of_site, symm))) return rc;
+  if ((rc = dupload(h, &t.bf, bf))) return rc;
+  if ((rc = dupload(h, &t.tasks, tasks))) return rc;
+  if ((rc = dupload(h, &t.task_base, task_base))) return rc;
+  if ((rc = dupload(h, &t.fams, fams))) return rc;
+  if ((rc = dupload(h, &t.pos, pos))) return rc;
+  if ((rc = dupload(h, &t.fin, fin))) return rc;
+  if ((rc = dupload(h, &t.singlet_idx, singlet_idx))) return rc;
+  if (t.n_active != N) { if ((rc = dupload(h, &t.active, active))) return rc; }
+  else t.active = nullptr;
+  {
+    int8_t *al = nullptr;
+    if ((rc = dalloc(h, &al, 128))) return rc;
+    CU(cudaMemcpy(al, h->allowed.data(), S, cudaMemcpyHostToDevice));
+    t.allowed = al;
+  }
+
+  // ---- per-replica state ---------------------------------------------------
+  const size_t R = (size_t)n_replicas;
+  ReplicaState &st = h->st;
+  if ((rc = dalloc(h, &st.occ, R * N))) return rc;
+  if ((rc = dalloc(h, &st.cf, R * n_eci))) return rc;
+  if ((rc = dalloc(h, &st.eci, R * n_eci))) return rc;
+  if ((rc = dalloc(h, &st.e_cur, R))) return rc;
+  if ((rc = dalloc(h, &st.kT, R))) return rc;
+  if ((rc = dalloc(h, &st.acc, R * h->acc_stride))) return rc;
+  if ((rc = dalloc(h, &st.ref, R))) return rc;
+  if ((rc = dalloc(h, &st.step, R))) return rc;
+  if ((rc = dalloc(h, &st.accepted, R))) return rc;
+  if ((rc = dalloc(h, &st.list, R * N))) return rc;
+  if ((rc = dalloc(h, &st.loc, R * N))) return rc;
+  if ((rc = dalloc(h, &st.off, R * (S + 1)))) return rc;
+  if ((rc = dalloc(h, &st.status, R))) return rc;
+  if ((rc = dalloc(h, &h->cf_committed, R * n_eci))) return rc;
+  if ((rc = dalloc(h, &h->e_committed, R))) return rc;
+  if ((rc = dalloc(h, &h->cf_partial, R * h->n_jobs))) return rc;
+  h->trial_log.resize(R);
+  {
+    std::vector<double> ones(R, 1.0), eci(R * n_eci);
+    for (size_t r = 0; r < R; r++) memcpy(&eci[r * n_eci], tb->eci, sizeof(double) * n_eci);
+    CU(cudaMemcpy(st.kT, ones.data(), sizeof(double) * R, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(st.ref, ones.data(), sizeof(double) * R, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(st.eci, eci.data(), sizeof(double) * R * n_eci, cudaMemcpyHostToDevice));
+  }
+  *out = h;
+  return 0;
+}
+
+int cemc_destroy(cemc_handle *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (void *p : h->owned) cudaFree(p);
+  void *extra[] = {h->d_sites, h->d_news, h->d_u, h->d_acc, h->d_e, h->tr_sites, h->tr_news,
+                   h->tr_u, h->tr_acc, h->tr_e, h->pt_scratch};
+  for (void *p : extra) if (p) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int cemc_set_stream(cemc_handle *h, void *stream) {
+  if (!h) return fail("null handle");
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+  if (stream) h->stream = (cudaStream_t)stream;
+  else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  return 0;
+}
+
+int cemc_synchronize(cemc_handle *h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_status(h);
+}
+
+int cemc_set_order_mode(cemc_handle *h, int mode) {
+  if (!h) return fail("null handle");
+  if (mode != CEMC_ORDER_REFERENCE && mode != CEMC_ORDER_TREE) return fail("unknown order mode");
+  h->order_mode = mode;
+  return 0;
+}
+
+static int refresh_energy(cemc_handle *h) {
+  energy_kernel<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->R, h->t.n_eci, h->t.N, h->st.eci,
+                                                           h->st.cf, h->st.e_cur);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static void drop_trials(cemc_handle *h) { for (auto &l : h->trial_log) l.clear(); }
+
+int cemc_set_occupancy(cemc_handle *h, const int8_t *occ) {
+  if (!h || !occ) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->R * h->t.N;
+  for (size_t q = 0; q < n; q++)
+    if (occ[q] < 0 || occ[q] >= h->t.S) return fail("occupancy value out of range");
+  CU(cudaMemcpyAsync(h->st.occ, occ, n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->tracker_dirty = true;
+  drop_trials(h);
+  return 0;
+}
+
+int cemc_get_occupancy(cemc_handle *h, int8_t *occ) {
+  if (!h || !occ) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(occ, h->st.occ, (size_t)h->R * h->t.N, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cemc_set_cf(cemc_handle *h, const double *cf) {
+  if (!h || !cf) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->st.cf, cf, sizeof(double) * h->R * h->t.n_eci, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  drop_trials(h);
+  return refresh_energy(h);
+}
+
+int cemc_get_cf(cemc_handle *h, double *cf) {
+  if (!h || !cf) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(cf, h->st.cf, sizeof(double) * h->R * h->t.n_eci, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cemc_recompute_cf(cemc_handle *h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  dim3 grid(h->n_jobs, h->R);
+  cf_partial_kernel<<<grid, 256, 0, h->stream>>>(h->t, h->st.occ, h->cf_partial, h->n_jobs);
+  cf_final_kernel<<<h->R, 64, 0, h->stream>>>(h->t, h->cf_partial, h->n_jobs, h->st.cf);
+  h->launches += 2;
+  CU(cudaGetLastError());
+  drop_trials(h);
+  return refresh_energy(h);
+}
+
+int cemc_set_ecis(cemc_handle *h, const double *eci, int per_replica) {
+  if (!h || !eci) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  const int n = h->t.n_eci;
+  std::vector<double> tmp;
+  const double *src = eci;
+  if (!per_replica) {
+    tmp.resize((size_t)h->R * n);
+    for (int r = 0; r < h->R; r++) memcpy(&tmp[(size_t)r * n], eci, sizeof(double) * n);
+    src = tmp.data();
+  }
+  CU(cudaMemcpyAsync(h->st.eci, src, sizeof(double) * h->R * n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return refresh_energy(h);
+}
+
+int cemc_get_ecis(cemc_handle *h, double *eci) {
+  if (!h || !eci) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(eci, h->st.eci, sizeof(double) * h->R * h->t.n_eci, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cemc_get_energy(cemc_handle *h, double *energy) {
+  if (!h || !energy) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(energy, h->st.e_cur, sizeof(double) * h->R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_status(h);
+}
+
+int cemc_set_kT(cemc_handle *h, const double *kT) {
+  if (!h || !kT) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  for (int r = 0; r < h->R; r++) if (!(kT[r] > 0.0)) return fail("kT must be positive");
+  CU(cudaMemcpyAsync(h->st.kT, kT, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cemc_get_kT(cemc_handle *h, double *kT) {
+  if (!h || !kT) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(kT, h->st.kT, sizeof(double) * h->R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cemc_seed(cemc_handle *h, uint64_t seed) {
+  if (!h) return fail("null handle");
+  h->seed = seed;
+  return 0;
+}
+
+int cemc_set_sgc_species(cemc_handle *h, int n_allowed, const int8_t *allowed) {
+  if (!h || !allowed) return fail("null argument");
+  if (n_allowed < 2 || n_allowed > h->t.S) return fail("At least 2 symbols have to be specified");
+  for (int i = 0; i < n_allowed; i++)
+    if (allowed[i] < 0 || allowed[i] >= h->t.S) return fail("species id out of range");
+  CU(cudaSetDevice(h->device));
+  h->allowed.assign(allowed, allowed + n_allowed);
+  CU(cudaMemcpyAsync((void *)h->t.allowed, allowed, n_allowed, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->t.n_allowed = n_allowed;
+  return 0;
+}
+
+int cemc_get_counters(cemc_handle *h, uint64_t *steps, uint64_t *accepted) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  if (steps) CU(cudaMemcpyAsync(steps, h->st.step, sizeof(uint64_t) * h->R, cudaMemcpyDeviceToHost, h->stream));
+  if (accepted) CU(cudaMemcpyAsync(accepted, h->st.accepted, sizeof(uint64_t) * h->R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cemc_reset_counters(cemc_handle *h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemsetAsync(h->st.accepted, 0, sizeof(uint64_t) * h->R, h->stream));
+  return 0;
+}
+
+int cemc_set_step(cemc_handle *h, const uint64_t *steps) {
+  if (!h || !steps) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->st.step, steps, sizeof(uint64_t) * h->R, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // extern "C"  (templates below need C++ linkage)
+
+// ---------------------------------------------------------------------------
+static int n_threads_for(const cemc_handle *h, int sites_changed) {
+  const int items = std::max({sites_changed * h->t.K, sites_changed * h->t.max_tasks, 32});
+  return std::min(256, (items + 31) / 32 * 32);
+}
+
+template <int MODE>
+static int launch_mc(cemc_handle *h, const RunArgs &a, int first_replica, int n_rep) {
+  const bool canonical = (MODE == MODE_CANONICAL);
+  const size_t sm_state = smem_bytes(h->t, h->acc_stride, canonical, true);
+  const bool in_smem = sm_state <= (size_t)h->max_smem_optin;
+  const size_t sm = in_smem ? sm_state : smem_bytes(h->t, h->acc_stride, canonical, false);
+  if (sm > (size_t)h->max_smem_optin) return fail("cluster program does not fit in shared memory");
+  const int nthr = n_threads_for(h, MODE == MODE_SGC ? 1 : 2);
+  ReplicaState st = h->st;
+  // offset the replica-major pointers when launching a sub-range (trial API)
+  if (first_replica) {
+    const size_t r0 = first_replica;
+    st.occ += r0 * h->t.N; st.cf += r0 * h->t.n_eci; st.eci += r0 * h->t.n_eci; st.e_cur += r0;
+    st.kT += r0; st.acc += r0 * h->acc_stride; st.ref += r0; st.step += r0; st.accepted += r0;
+    st.list += r0 * h->t.N; st.loc += r0 * h->t.N; st.off += r0 * (h->t.S + 1); st.status += r0;
+  }
+  if (in_smem) {
+    CU(cudaFuncSetAttribute(mc_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    mc_kernel<MODE, true><<<n_rep, nthr, sm, h->stream>>>(h->t, st, a, h->acc_stride);
+  } else {
+    CU(cudaFuncSetAttribute(mc_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    mc_kernel<MODE, false><<<n_rep, nthr, sm, h->stream>>>(h->t, st, a, h->acc_stride);
+  }
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int ensure_scratch(cemc_handle *h, long long n_steps) {
+  if (n_steps <= h->scratch_steps) return 0;
+  void *old[] = {h->d_sites, h->d_news, h->d_u, h->d_acc, h->d_e};
+  CU(cudaStreamSynchronize(h->stream));
+  for (void *p : old) if (p) cudaFree(p);
+  const size_t n = (size_t)h->R * n_steps;
+  CU(cudaMalloc((void **)&h->d_sites, n * 2 * sizeof(int32_t)));
+  CU(cudaMalloc((void **)&h->d_news, n * 2));
+  CU(cudaMalloc((void **)&h->d_u, n * sizeof(double)));
+  CU(cudaMalloc((void **)&h->d_acc, n));
+  CU(cudaMalloc((void **)&h->d_e, n * sizeof(double)));
+  h->scratch_steps = n_steps;
+  return 0;
+}
+
+extern "C" {
+
+int cemc_replay(cemc_handle *h, int n_steps, const int32_t *sites, const int8_t *news,
+                const double *uniforms, uint8_t *accepted_out, double *e_after_out) {
+  if (!h || !sites || !news || !uniforms) return fail("null argument");
+  if (n_steps <= 0) return 0;
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = ensure_scratch(h, n_steps))) return rc;
+  const size_t n = (size_t)h->R * n_steps;
+  CU(cudaMemcpyAsync(h->d_sites, sites, n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_news, news, n * 2, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_u, uniforms, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  RunArgs a{};
+  a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset;
+  a.observe = 1;
+  a.rp_sites = h->d_sites; a.rp_news = h->d_news; a.rp_u = h->d_u;
+  a.tr_acc = h->d_acc; a.tr_e = h->d_e; a.tr_capacity = n_steps;
+  drop_trials(h);
+  h->tracker_dirty = true;
+  if ((rc = launch_mc<MODE_REPLAY>(h, a, 0, h->R))) return rc;
+  if (accepted_out) CU(cudaMemcpyAsync(accepted_out, h->d_acc, n, cudaMemcpyDeviceToHost, h->stream));
+  if (e_after_out) CU(cudaMemcpyAsync(e_after_out, h->d_e, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_status(h);
+}
+
+static RunArgs run_args(cemc_handle *h, long long n_steps) {
+  RunArgs a{};
+  a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset;
+  a.observe = 1;
+  if (h->trace_capacity > 0) {
+    a.tr_sites = h->tr_sites; a.tr_news = h->tr_news; a.tr_u = h->tr_u; a.tr_acc = h->tr_acc;
+    a.tr_e = h->tr_e; a.tr_capacity = h->trace_capacity;
+  }
+  return a;
+}
+
+int cemc_run_sgc(cemc_handle *h, int64_t n_steps) {
+  if (!h) return fail("null handle");
+  if (n_steps <= 0) return 0;
+  CU(cudaSetDevice(h->device));
+  drop_trials(h);
+  h->tracker_dirty = true;
+  return launch_mc<MODE_SGC>(h, run_args(h, n_steps), 0, h->R);
+}
+
+int cemc_run_canonical(cemc_handle *h, int64_t n_steps) {
+  if (!h) return fail("null handle");
+  if (n_steps <= 0) return 0;
+  CU(cudaSetDevice(h->device));
+  drop_trials(h);
+  if (h->tracker_dirty) {
+    tracker_init_kernel<<<h->R, 128, 0, h->stream>>>(h->t.N, h->t.S, h->t.symm_of_site, h->st.occ,
+                                                     h->st.list, h->st.loc, h->st.off);
+    h->launches++;
+    CU(cudaGetLastError());
+    h->tracker_dirty = false;
+  }
+  return launch_mc<MODE_CANONICAL>(h, run_args(h, n_steps), 0, h->R);
+}
+
+int cemc_set_trace(cemc_handle *h, int64_t capacity) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  void *old[] = {h->tr_sites, h->tr_news, h->tr_u, h->tr_acc, h->tr_e};
+  for (void *p : old) if (p) cudaFree(p);
+  h->tr_sites = nullptr; h->tr_news = nullptr; h->tr_u = nullptr; h->tr_acc = nullptr; h->tr_e = nullptr;
+  h->trace_capacity = 0;
+  if (capacity <= 0) return 0;
+  const size_t n = (size_t)h->R * capacity;
+  CU(cudaMalloc((void **)&h->tr_sites, n * 2 * sizeof(int32_t)));
+  CU(cudaMalloc((void **)&h->tr_news, n * 2));
+  CU(cudaMalloc((void **)&h->tr_u, n * sizeof(double)));
+  CU(cudaMalloc((void **)&h->tr_acc, n));
+  CU(cudaMalloc((void **)&h->tr_e, n * sizeof(double)));
+  h->trace_capacity = capacity;
+  return 0;
+}
+
+int cemc_get_trace(cemc_handle *h, int64_t n_steps, int32_t *sites, int8_t *news, double *u,
+                   uint8_t *accepted, double *e_after) {
+  if (!h) return fail("null handle");
+  if (n_steps > h->trace_capacity) return fail("trace capacity exceeded");
+  CU(cudaSetDevice(h->device));
+  const size_t cap = (size_t)h->trace_capacity;
+  for (int r = 0; r < h->R; r++) {
+    const size_t so = (size_t)r * cap, d_o = (size_t)r * n_steps;
+    if (sites) CU(cudaMemcpyAsync(sites + 2 * d_o, h->tr_sites + 2 * so, n_steps * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (news) CU(cudaMemcpyAsync(news + 2 * d_o, h->tr_news + 2 * so, n_steps * 2, cudaMemcpyDeviceToHost, h->stream));
+    if (u) CU(cudaMemcpyAsync(u + d_o, h->tr_u + so, n_steps * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (accepted) CU(cudaMemcpyAsync(accepted + d_o, h->tr_acc + so, n_steps, cudaMemcpyDeviceToHost, h->stream));
+    if (e_after) CU(cudaMemcpyAsync(e_after + d_o, h->tr_e + so, n_steps * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---- the reference's per-call surface ---------------------------------------
+int cemc_trial_changes(cemc_handle *h, int replica, int n_changes, const int32_t *sites,
+                       const int8_t *old_species, const int8_t *new_species, double *energy_out) {
+  if (!h) return fail("null handle");
+  if (replica < 0 || replica >= h->R) return fail("replica out of range");
+  CU(cudaSetDevice(h->device));
+  const int n_eci = h->t.n_eci, N = h->t.N;
+  auto &log = h->trial_log[replica];
+  if (n_changes > 0) {
+    if (!sites || !new_species) return fail("null argument");
+    if (log.size() + (size_t)n_changes > 999)     // ring of 1000, cf_history_tracker.hpp:56
+      return fail("Can't store more trial changes than the history buffer holds");
+    // device occupancy is the truth; old_species (if given) must agree with it
+    std::vector<int8_t> cur(n_changes);
+    for (int i = 0; i < n_changes; i++) {
+      if (sites[i] < 0 || sites[i] >= N) return fail("site index out of range");
+      if (new_species[i] < 0 || new_species[i] >= h->t.S) return fail("species out of range");
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n_changes; i++) {
+      CU(cudaMemcpy(&cur[i], h->st.occ + (size_t)replica * N + sites[i], 1, cudaMemcpyDeviceToHost));
+      for (int j = 0; j < i; j++) if (sites[j] == sites[i]) cur[i] = new_species[j];
+      if (old_species && old_species[i] != cur[i])
+        return fail("The atom position tracker does not match the current state");
+    }
+    if (log.empty()) {
+      CU(cudaMemcpyAsync(h->cf_committed + (size_t)replica * n_eci, h->st.cf + (size_t)replica * n_eci,
+                         sizeof(double) * n_eci, cudaMemcpyDeviceToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->e_committed + replica, h->st.e_cur + replica, sizeof(double),
+                         cudaMemcpyDeviceToDevice, h->stream));
+    }
+    // each change is one forced-accept one-site step (ce_updater.cpp:845-852)
+    std::vector<int32_t> s2(2 * n_changes);
+    std::vector<int8_t> n2(2 * n_changes);
+    std::vector<double> uu(n_changes, 0.0);
+    for (int i = 0; i < n_changes; i++) {
+      s2[2 * i] = sites[i]; s2[2 * i + 1] = -1; n2[2 * i] = new_species[i]; n2[2 * i + 1] = 0;
+    }
+    int32_t *ds; int8_t *dn; double *du;
+    CU(cudaMalloc((void **)&ds, s2.size() * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&dn, n2.size()));
+    CU(cudaMalloc((void **)&du, uu.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(ds, s2.data(), s2.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dn, n2.data(), n2.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(du, uu.data(), uu.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    RunArgs a{};
+    a.n_steps = n_changes; a.seed = h->seed; a.force_accept = 1; a.observe = 0;
+    a.rp_sites = ds; a.rp_news = dn; a.rp_u = du;
+    int rc = launch_mc<MODE_REPLAY>(h, a, replica, 1);   // rp arrays hold this replica only
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(ds); cudaFree(dn); cudaFree(du);
+    if (rc) return rc;
+    if ((rc = check_status(h))) return rc;
+    for (int i = 0; i < n_changes; i++)
+      if (cur[i] != new_species[i]) log.push_back(TrialEntry{sites[i], cur[i]});
+    h->tracker_dirty = true;
+  }
+  if (energy_out) {
+    CU(cudaMemcpyAsync(energy_out, h->st.e_cur + replica, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int cemc_undo_changes(cemc_handle *h, int replica) {
+  if (!h) return fail("null handle");
+  if (replica < 0 || replica >= h->R) return fail("replica out of range");
+  CU(cudaSetDevice(h->device));
+  auto &log = h->trial_log[replica];
+  if (log.empty()) return 0;
+  const int n = (int)log.size(), n_eci = h->t.n_eci;
+  std::vector<int32_t> s(n);
+  std::vector<int8_t> v(n);
+  for (int i = 0; i < n; i++) { s[i] = log[n - 1 - i].site; v[i] = log[n - 1 - i].old_sp; }  // pop order
+  int32_t *ds; int8_t *dv;
+  CU(cudaMalloc((void **)&ds, n * sizeof(int32_t)));
+  CU(cudaMalloc((void **)&dv, n));
+  CU(cudaMemcpyAsync(ds, s.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(dv, v.data(), n, cudaMemcpyHostToDevice, h->stream));
+  set_sites_kernel<<<1, 32, 0, h->stream>>>(h->st.occ + (size_t)replica * h->t.N, n, ds, dv);
+  h->launches++;
+  CU(cudaMemcpyAsync(h->st.cf + (size_t)replica * n_eci, h->cf_committed + (size_t)replica * n_eci,
+                     sizeof(double) * n_eci, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->st.e_cur + replica, h->e_committed + replica, sizeof(double),
+                     cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(ds); cudaFree(dv);
+  log.clear();
+  h->tracker_dirty = true;
+  return 0;
+}
+
+int cemc_clear_history(cemc_handle *h, int replica) {
+  if (!h) return fail("null handle");
+  if (replica < 0 || replica >= h->R) return fail("replica out of range");
+  h->trial_log[replica].clear();
+  return 0;
+}
+
+// ---- observers -----------------------------------------------------------------
+int cemc_reset_accumulators(cemc_handle *h, const double *ref) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemsetAsync(h->st.acc, 0, sizeof(double) * h->R * h->acc_stride, h->stream));
+  if (ref) {
+    for (int r = 0; r < h->R; r++) if (ref[r] == 0.0) return fail("Averager reference value must be non-zero");
+    CU(cudaMemcpyAsync(h->st.ref, ref, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cemc_get_accumulators(cemc_handle *h, double *acc) {
+  if (!h || !acc) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(acc, h->st.acc, sizeof(double) * h->R * h->acc_stride, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_status(h);
+}
+
+// ---- parallel tempering -----------------------------------------------------------
+int cemc_pt_exchange(cemc_handle *h, int n_total, const double *energies_dev,
+                     int32_t *slot_of_replica_dev, const double *kT_of_slot_dev, int direction,
+                     uint64_t round, int32_t *n_accepted_dev) {
+  if (!h || !energies_dev || !slot_of_replica_dev || !kT_of_slot_dev) return fail("null argument");
+  if (h->replica_offset + h->R > n_total) return fail("local replicas exceed n_total");
+  CU(cudaSetDevice(h->device));
+  if (h->pt_scratch_n < n_total) {
+    if (h->pt_scratch) cudaFree(h->pt_scratch);
+    CU(cudaMalloc((void **)&h->pt_scratch, sizeof(int32_t) * n_total));
+    h->pt_scratch_n = n_total;
+  }
+  pt_exchange_kernel<<<1, 256, 0, h->stream>>>(n_total, energies_dev, slot_of_replica_dev, kT_of_slot_dev,
+                                               direction, h->seed, round, h->pt_scratch, h->st.kT,
+                                               h->replica_offset, h->R, n_accepted_dev);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int cemc_energy_dev(cemc_handle *h, double **ptr) {
+  if (!h || !ptr) return fail("null argument");
+  *ptr = h->st.e_cur;
+  return 0;
+}
+
+// ---- timing ------------------------------------------------------------------------
+int cemc_timer_start(cemc_handle *h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->ev0, h->stream));
+  return 0;
+}
+
+int cemc_timer_stop(cemc_handle *h, float *ms) {
+  if (!h || !ms) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaEventSynchronize(h->ev1));
+  CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return 0;
+}
+
+int cemc_launch_count(cemc_handle *h, uint64_t *n) {
+  if (!h || !n) return fail("null argument");
+  *n = h->launches;
+  return 0;
+}
+
+}  // extern "C"

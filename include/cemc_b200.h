@@ -128,6 +128,11 @@ int cemc_get_energy(cemc_handle *h, double *energy /*[R]*/);
 int cemc_set_kT(cemc_handle *h, const double *kT /*[R]*/);
 int cemc_get_kT(cemc_handle *h, double *kT /*[R]*/);
 int cemc_seed(cemc_handle *h, uint64_t seed);
+/* Philox counter = per-replica step index; set it to resume a recorded chain */
+int cemc_set_step(cemc_handle *h, const uint64_t *steps /*[R]*/);
+/* species ids the SGC sampler may insert (SGCMonteCarlo(symbols=...),
+ * sgc_montecarlo.py:38-43); default: all species                            */
+int cemc_set_sgc_species(cemc_handle *h, int n_allowed, const int8_t *allowed);
 int cemc_get_counters(cemc_handle *h, uint64_t *steps /*[R]*/, uint64_t *accepted /*[R]*/);
 int cemc_reset_counters(cemc_handle *h);
 

@@ -16,6 +16,7 @@ is provided by a stub module built from cemc_b200.synthetic.equivalent_deco.
 from __future__ import annotations
 
 import contextlib
+import ctypes
 import glob
 import math
 import os
@@ -91,9 +92,14 @@ class RefChain(object):
         # the reference stores `atoms` without INCREF and DECREFs it in its
         # destructor (ce_updater.cpp:34,22): hold one extra reference forever.
         _LEAK.append(self.atoms)
+        ctypes.pythonapi.Py_IncRef(ctypes.py_object(self.atoms))
         with _quiet():
             self.upd = mod.PyCEUpdater(self.atoms, settings, self.cf0, self.eci)
             self.upd.set_num_threads(int(num_threads))
+        # never run the reference's destructor (it would DECREF freed objects
+        # during interpreter shutdown): make the updater immortal.
+        ctypes.pythonapi.Py_IncRef(ctypes.py_object(self.upd))
+        _LEAK.append(self.upd)
         self.kT = float(kT)
         self.current_energy = self.upd.get_energy()  # montecarlo.py:753
         self.n_accepted = 0

@@ -1,0 +1,56 @@
+"""Quick throughput probe of the MC kernels on one GPU (not the bench)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from cemc_b200 import synthetic as syn
+from cemc_b200.tables import FlatTables
+from cemc_b200.updater import BatchedCEUpdater
+
+KB = 8.617330337217213e-05
+
+def setup(L, species, conc, R, kTs, mus=None):
+    st = syn.fcc_settings(L, species, ["nn", "2nn", "tri", "tet"])
+    eci = syn.synthetic_ecis(st)
+    syms = syn.random_symbols(st, conc, seed=1)
+    ft = FlatTables(st, eci, syms)
+    gpu = BatchedCEUpdater(ft, R)
+    occ = np.stack([ft.occupancy(syn.random_symbols(st, conc, seed=r)) for r in range(R)])
+    gpu.set_occupancy(occ)
+    gpu.recompute_cf()
+    gpu.set_kT(kTs)
+    if mus is not None:
+        e = np.tile(ft.eci, (R, 1))
+        e[:, ft.eci_index["c1_0"]] -= mus
+        gpu.set_ecis(e)
+    gpu.seed(1234)
+    return ft, gpu
+
+def timeit(gpu, fn, n, reps=3):
+    fn(n); gpu.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        gpu.timer_start(); fn(n); ms = gpu.timer_stop(); gpu.synchronize()
+        best = min(best, ms)
+    return best
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c2", "c3"]
+    if "c2" in which:
+        T = np.linspace(200, 1000, 16); mu = np.linspace(-1.1, -0.9, 16)
+        kTs = np.repeat(T * KB, 16); mus = np.tile(mu, 16)
+        ft, gpu = setup(10, ["Al", "Mg"], {"Al": 0.5, "Mg": 0.5}, 256, kTs, mus * 0.0)
+        for n in (20000, 100000):
+            ms = timeit(gpu, gpu.run_sgc, n)
+            print("C2 sgc binary L=10 R=256 n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
+                n, ms, 256 * n / ms / 1e3, ms * 1e6 / n))
+        st, acc = gpu.get_counters(); print("  accept rate", acc.sum() / st.sum())
+    if "c3" in which:
+        kTs = np.linspace(300, 900, 64) * KB
+        ft, gpu = setup(20, ["Al", "Mg", "Si"], {"Al": 0.8, "Mg": 0.1, "Si": 0.1}, 64, kTs)
+        for n in (20000, 100000):
+            ms = timeit(gpu, gpu.run_canonical, n)
+            print("C3 canonical ternary L=20 R=64 n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
+                n, ms, 64 * n / ms / 1e3, ms * 1e6 / n))
+        st, acc = gpu.get_counters(); print("  accept rate", acc.sum() / st.sum())
+        ms = timeit(gpu, gpu.run_sgc, 20000)
+        print("C3-lattice sgc ternary: %.1f M moves/s (%.0f ns/move/chain)" % (64 * 20000 / ms / 1e3, ms * 1e6 / 20000))

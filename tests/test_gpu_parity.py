@@ -1,0 +1,335 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on
+the same seeded inputs, and against the committed golden fixtures recorded
+from the reference's compiled C++ updater.  Bit-exact for accept sequences,
+occupations, energies and CFs (reference operation order, fp64)."""
+import numpy as np
+import pytest
+
+from cases import BINARY, GOLDEN, TERNARY, build, load_golden
+from cemc_b200.updater import BatchedCEUpdater, PyCEUpdater
+from cemc_b200 import synthetic as syn
+from oracle import ce_oracle
+from oracle.ce_oracle import OracleChain
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(ft, symbols_list, kTs, seed, offset=0, eci=None):
+    """R replicas on the GPU and R oracle chains with identical inputs."""
+    R = len(symbols_list)
+    occ = np.stack([ft.occupancy(s) for s in symbols_list])
+    chains = [OracleChain(ft, occ[r], kT=kTs[r], seed=seed, replica=offset + r,
+                          eci=None if eci is None else eci[r]) for r in range(R)]
+    gpu = BatchedCEUpdater(ft, R, replica_offset=offset)
+    gpu.set_occupancy(occ)
+    gpu.set_cf(np.stack([c.cf for c in chains]))
+    if eci is not None:
+        gpu.set_ecis(np.stack(eci))
+    gpu.set_kT(kTs)
+    gpu.seed(seed)
+    return gpu, chains
+
+
+def assert_state_equal(gpu, chains):
+    occ = gpu.get_occupancy()
+    cf = gpu.get_cf()
+    e = gpu.get_energy()
+    for r, c in enumerate(chains):
+        assert np.array_equal(occ[r], c.occ), "occupancy differs, replica %d" % r
+        assert np.array_equal(cf[r], c.cf), "CF differs, replica %d" % r
+        assert e[r] == c.e, "energy differs, replica %d" % r
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_replay_golden(cuda_device, name):
+    """Replay of trajectories recorded from the reference's own C++ CEUpdater."""
+    meta, st, ft, z = load_golden(name)
+    gpu = BatchedCEUpdater(ft, 1)
+    gpu.set_occupancy(ft.occupancy(meta["symbols0"])[None])
+    gpu.set_cf(z["cf0"][None])
+    gpu.set_kT([meta["kT"]])
+    assert gpu.get_energy()[0] == float(z["e0"])
+    acc, e_after = gpu.replay(z["sites"][None], z["news"][None], z["u"][None])
+    assert np.array_equal(acc[0], z["accepted"])
+    assert np.array_equal(e_after[0], z["e_after"])
+    assert np.array_equal(gpu.get_cf()[0], z["cf_final"])
+    assert np.array_equal(gpu.get_occupancy()[0], z["occ_final"])
+    steps, n_acc = gpu.get_counters()
+    assert steps[0] == len(z["u"]) and n_acc[0] == z["accepted"].sum()
+
+
+@pytest.mark.parametrize("case", [BINARY, TERNARY])
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+def test_device_proposals_match_oracle(cuda_device, case, mode):
+    """On-device Philox proposals + Metropolis == oracle chain, every step."""
+    st, eci, symbols, ft = build(**case)
+    R = 5
+    syms = [syn.random_symbols(st, case["conc"], seed=10 + r) for r in range(R)]
+    kTs = np.linspace(0.01, 0.09, R)
+    gpu, chains = make_pair(ft, syms, kTs, seed=777, offset=3)
+    n = 700
+    gpu.set_trace(n)
+    gpu.reset_accumulators()
+    (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+    gpu.synchronize()
+    sites, news, u, acc, e = gpu.get_trace(n)
+    for r, c in enumerate(chains):
+        tr = c.run_sgc(n, trace=True) if mode == "sgc" else c.run_canonical(n, trace=True)
+        assert np.array_equal(sites[r], tr[0])
+        assert np.array_equal(news[r], tr[1])
+        assert np.array_equal(u[r], tr[2])
+        assert np.array_equal(acc[r], tr[3])
+        assert np.array_equal(e[r], tr[4])
+    assert_state_equal(gpu, chains)
+    accs = gpu.get_accumulators()
+    steps, n_acc = gpu.get_counters()
+    for r, c in enumerate(chains):
+        assert np.array_equal(accs[r], c.acc)
+        assert steps[r] == n and n_acc[r] == c.n_accepted.value
+    assert 0.02 < acc.mean() < 0.98
+
+
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+def test_chunked_runs_equal_one_run(cuda_device, mode):
+    st, eci, symbols, ft = build(**TERNARY)
+    syms = [symbols, symbols]
+    gpu1, chains = make_pair(ft, syms, [0.05, 0.02], seed=5)
+    gpu2, _ = make_pair(ft, syms, [0.05, 0.02], seed=5)
+    run1 = gpu1.run_sgc if mode == "sgc" else gpu1.run_canonical
+    run2 = gpu2.run_sgc if mode == "sgc" else gpu2.run_canonical
+    run1(600)
+    for n in (1, 31, 32, 33, 203, 300):
+        run2(n)
+    gpu1.synchronize(); gpu2.synchronize()
+    assert np.array_equal(gpu1.get_occupancy(), gpu2.get_occupancy())
+    assert np.array_equal(gpu1.get_cf(), gpu2.get_cf())
+    assert np.array_equal(gpu1.get_energy(), gpu2.get_energy())
+    assert np.array_equal(gpu1.get_accumulators(), gpu2.get_accumulators())
+    for c in chains:
+        c.run_sgc(600) if mode == "sgc" else c.run_canonical(600)
+    assert_state_equal(gpu1, chains)
+
+
+def test_per_replica_ecis_chemical_potential(cuda_device):
+    """SGC sweep: mu folded into the singlet ECIs per replica
+    (sgc_montecarlo.py:239-261), Averager reference values per replica."""
+    st, eci, symbols, ft = build(**BINARY)
+    R = 4
+    mus = [-0.2, -0.05, 0.05, 0.2]
+    ecis = []
+    for mu in mus:
+        v = ft.eci.copy()
+        v[ft.eci_index["c1_0"]] -= mu
+        ecis.append(v)
+    gpu, chains = make_pair(ft, [symbols] * R, [0.03] * R, seed=21, eci=ecis)
+    refs = gpu.get_energy()
+    assert all(refs[r] == chains[r].e for r in range(R))
+    gpu.reset_accumulators(refs)
+    for r, c in enumerate(chains):
+        c.set_ref(refs[r])
+    gpu.run_sgc(500)
+    gpu.synchronize()
+    for c in chains:
+        c.run_sgc(500)
+    assert_state_equal(gpu, chains)
+    accs = gpu.get_accumulators()
+    for r, c in enumerate(chains):
+        assert np.array_equal(accs[r], c.acc)
+    # different mu -> different compositions
+    assert len({float(a[3]) for a in accs}) == R
+
+
+def test_replay_edge_cases(cuda_device):
+    """No-op changes (old == new, ce_updater.cpp:315), neighbouring swap
+    partners (A.2), the same site twice, and one-site + two-site steps mixed."""
+    st, eci, symbols, ft = build(**TERNARY)
+    occ = ft.occupancy(symbols)
+    nb = int(ft.trans[5, 0])           # a nearest neighbour of site 5
+    other = [s for s in range(ft.N) if occ[s] != occ[5] and s != nb][0]
+    sites = np.array([[5, -1], [5, nb], [5, other], [7, 7], [9, -1], [nb, 5], [11, 12]],
+                     dtype=np.int32)
+    news = np.array([[occ[5], 0], [occ[nb], occ[5]], [occ[other], occ[5]],
+                     [(occ[7] + 1) % 3, (occ[7] + 2) % 3], [(occ[9] + 1) % 3, 0],
+                     [occ[nb], occ[nb]], [occ[12], occ[11]]], dtype=np.int8)
+    u = np.array([0.5, 0.9, 0.1, 0.3, 0.99, 0.2, 0.6])
+    gpu, chains = make_pair(ft, [symbols], [0.05], seed=0)
+    acc, e = gpu.replay(sites[None], news[None], u[None])
+    acc_o, e_o = chains[0].replay(sites, news, u)
+    assert np.array_equal(acc[0], acc_o)
+    assert np.array_equal(e[0], e_o)
+    assert_state_equal(gpu, chains)
+    assert acc[0][0] == 1     # no-op step: E_new == E_cur, u <= exp(0)
+
+
+def test_replay_empty_and_errors(cuda_device):
+    from cemc_b200._lib import CemcError
+    st, eci, symbols, ft = build(**BINARY)
+    gpu, chains = make_pair(ft, [symbols], [0.05], seed=0)
+    acc, e = gpu.replay(np.zeros((1, 0, 2), np.int32), np.zeros((1, 0, 2), np.int8),
+                        np.zeros((1, 0)))
+    assert acc.shape == (1, 0)
+    with pytest.raises(CemcError):
+        gpu.replay(np.array([[[ft.N, -1]]], np.int32), np.zeros((1, 1, 2), np.int8),
+                   np.zeros((1, 1)))
+    with pytest.raises(CemcError):
+        gpu.set_occupancy(np.full((1, ft.N), 7, np.int8))
+    assert_state_equal(gpu, chains)   # failed calls left the state untouched
+
+
+def test_background_sites(cuda_device):
+    """Background atoms never move (ce_updater.cpp:330, :1015-1027)."""
+    from cemc_b200._lib import CemcError
+    from cemc_b200.tables import FlatTables
+    st = syn.fcc_settings(4, ["Al", "Mg"])
+    bkg = [0, 17]
+    st.background_indices = bkg
+    st.index_by_trans_symm = [[s for s in range(64) if s not in bkg]]
+    eci = syn.synthetic_ecis(st)
+    symbols = syn.random_symbols(st, {"Al": 0.5, "Mg": 0.5}, seed=2)
+    ft = FlatTables(st, eci, symbols)
+    gpu, chains = make_pair(ft, [symbols], [0.05], seed=8)
+    gpu.run_sgc(400)
+    gpu.synchronize()
+    chains[0].run_sgc(400)
+    assert_state_equal(gpu, chains)
+    occ0 = ft.occupancy(symbols)
+    assert np.array_equal(gpu.get_occupancy()[0][bkg], occ0[bkg])
+    with pytest.raises(CemcError, match="background"):
+        gpu.replay(np.array([[[0, -1]]], np.int32),
+                   np.array([[[1 - occ0[0], 0]]], np.int8), np.zeros((1, 1)))
+
+
+def test_recompute_cf_matches_definition(cuda_device):
+    st, eci, symbols, ft = build(**TERNARY)
+    gpu, chains = make_pair(ft, [symbols, symbols[::-1]], [0.05, 0.05], seed=1)
+    chains[1] = OracleChain(ft, ft.occupancy(symbols[::-1]), kT=0.05, seed=1, replica=1)
+    gpu.set_cf(np.zeros((2, ft.n_eci)))
+    gpu.recompute_cf()
+    cf = gpu.get_cf()
+    for r in range(2):
+        np.testing.assert_allclose(cf[r], chains[r].cf, rtol=0, atol=2e-14)
+    np.testing.assert_allclose(gpu.get_energy(), [c.e for c in chains], rtol=1e-12)
+
+
+def test_pyceupdater_drop_in(cuda_device):
+    """calculate / undo_changes / clear_history / get_cf / get_singlets /
+    set_ecis with the reference's call pattern (montecarlo.py:922,1015-1018)."""
+    st, eci, symbols, ft = build(**TERNARY)
+    oc = OracleChain(ft, ft.occupancy(symbols), kT=0.05)
+    cf0 = {n: float(v) for n, v in zip(ft.eci_names, oc.cf)}
+    atoms = syn.Atoms(symbols)
+    upd = PyCEUpdater(atoms, st, cf0, dict(eci))
+    assert upd.get_energy() == oc.e
+    e0 = oc.e
+    # a swap that is rejected, then one that is committed
+    a, b = 3, [s for s in range(ft.N) if symbols[s] != symbols[3]][0]
+    changes = [(a, symbols[a], symbols[b]), (b, symbols[b], symbols[a])]
+    e1 = upd.calculate(changes)
+    assert atoms[a].symbol == symbols[b] and atoms[b].symbol == symbols[a]
+    upd.undo_changes()
+    assert atoms[a].symbol == symbols[a] and atoms[b].symbol == symbols[b]
+    assert upd.get_energy() == e0
+    assert upd.get_cf() == cf0
+    e2 = upd.calculate(changes)
+    upd.clear_history()
+    assert e2 == e1
+    oc.update_cf(a, ft.species_id[symbols[b]])
+    oc.update_cf(b, ft.species_id[symbols[a]])
+    assert e2 == oc.e
+    assert np.array_equal(np.array([upd.get_cf()[n] for n in ft.eci_names]), oc.cf)
+    assert np.array_equal(upd.get_singlets(), oc.cf[ft.singlet_indices])
+    assert upd.get_symbols() == ft.symbols_of(oc.occ)
+    # chemical potential folded into an ECI (sgc_montecarlo.py:253-255)
+    new_eci = dict(eci)
+    new_eci["c1_0"] -= 0.37
+    upd.set_ecis(new_eci)
+    oc.set_ecis(ft.eci_vector(new_eci))
+    assert upd.get_energy() == oc.e
+    with pytest.raises(ValueError):
+        upd.set_ecis({"c0": 0.0})
+    # single flips through update_cf (CE.set_symbols path, ce_calculator.py:446)
+    for s in (1, 2, 40):
+        new = ft.species[(ft.species_id[atoms[s].symbol] + 1) % 3]
+        upd.update_cf((s, atoms[s].symbol, new))
+        oc.update_cf(s, ft.species_id[new])
+    upd.clear_history()
+    assert upd.get_energy() == oc.e
+
+
+def test_pt_exchange_matches_oracle(cuda_device):
+    import torch
+    st, eci, symbols, ft = build(**BINARY)
+    R = 8
+    kts = np.geomspace(0.08, 0.01, R)
+    syms = [syn.random_symbols(st, BINARY["conc"], seed=30 + r) for r in range(R)]
+    gpu, chains = make_pair(ft, syms, kts, seed=4242)
+    dev = torch.device("cuda:0")
+    slots = torch.arange(R, dtype=torch.int32, device=dev)
+    kt_slot = torch.tensor(kts, dtype=torch.float64, device=dev)
+    n_acc = torch.zeros(1, dtype=torch.int32, device=dev)
+    slots_o = np.arange(R, dtype=np.int32)
+    for rnd in range(6):
+        gpu.run_canonical(200)
+        gpu.synchronize()
+        for c in chains:
+            c.run_canonical(200)
+        torch.cuda.synchronize()
+        gpu.pt_exchange(R, gpu.energy_dev_ptr(), slots.data_ptr(), kt_slot.data_ptr(),
+                        rnd % 2, rnd, n_acc.data_ptr())
+        gpu.synchronize()
+        slots_o, n_o = ce_oracle.pt_exchange([c.e for c in chains], slots_o, kts,
+                                             rnd % 2, 4242, rnd)
+        assert np.array_equal(slots.cpu().numpy(), slots_o)
+        assert int(n_acc.item()) == n_o
+        for r, c in enumerate(chains):
+            c.kT = float(kts[slots_o[r]])
+        assert np.array_equal(gpu.get_kT(), np.array([c.kT for c in chains]))
+    assert_state_equal(gpu, chains)
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config sizes (10^3 binary SGC, 20^3 ternary canonical):
+    size-independent properties -- incremental CFs equal a from-scratch
+    recompute, canonical moves conserve composition, replaying the device's
+    own trace reproduces it, energies equal N * eci . cf."""
+    for L, species, conc, mode in [(10, ["Al", "Mg"], {"Al": 0.5, "Mg": 0.5}, "sgc"),
+                                   (20, ["Al", "Mg", "Si"],
+                                    {"Al": 0.8, "Mg": 0.1, "Si": 0.1}, "canonical")]:
+        st, eci, symbols, ft = build(L, species, ["nn", "2nn", "tri", "tet"], conc)
+        R = 4
+        occ0 = np.stack([ft.occupancy(symbols)] * R)
+        gpu = BatchedCEUpdater(ft, R)
+        gpu.set_occupancy(occ0)
+        gpu.recompute_cf()
+        cf0 = gpu.get_cf()
+        gpu.set_kT(np.linspace(0.02, 0.08, R))
+        gpu.seed(99)
+        n = 3000
+        gpu.set_trace(n)
+        (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+        gpu.synchronize()
+        cf_inc, e_inc, occ1 = gpu.get_cf(), gpu.get_energy(), gpu.get_occupancy()
+        tr = gpu.get_trace(n)
+        assert 0.01 < tr[3].mean() < 0.99
+        if mode == "canonical":
+            for r in range(R):
+                assert np.array_equal(np.bincount(occ1[r], minlength=3),
+                                      np.bincount(occ0[r], minlength=3))
+        np.testing.assert_array_equal(
+            e_inc, [ce_oracle.OracleChain(ft, occ1[r], cf=cf_inc[r]).e for r in range(R)])
+        gpu.recompute_cf()
+        np.testing.assert_allclose(gpu.get_cf(), cf_inc, rtol=0, atol=1e-12)
+        # replay of the recorded trace from the initial state: identical
+        gpu2 = BatchedCEUpdater(ft, R)
+        gpu2.set_occupancy(occ0)
+        gpu2.set_cf(cf0)
+        gpu2.set_kT(np.linspace(0.02, 0.08, R))
+        acc, e = gpu2.replay(tr[0], tr[1], tr[2])
+        assert np.array_equal(acc, tr[3]) and np.array_equal(e, tr[4])
+        assert np.array_equal(gpu2.get_occupancy(), occ1)
+        assert np.array_equal(gpu2.get_cf(), cf_inc)
+        # and the oracle agrees on one replica end to end
+        oc = OracleChain(ft, occ0[1], cf=cf0[1], kT=np.linspace(0.02, 0.08, R)[1])
+        acc_o, e_o = oc.replay(tr[0][1], tr[1][1], tr[2][1])
+        assert np.array_equal(acc_o, tr[3][1]) and np.array_equal(e_o, tr[4][1])
+        assert np.array_equal(oc.cf, cf_inc[1])
