@@ -55,6 +55,7 @@ SIGNATURES = {
     "cemc_set_stream": [_H, C.c_void_p],
     "cemc_synchronize": [_H],
     "cemc_set_order_mode": [_H, C.c_int],
+    "cemc_set_block_threads": [_H, C.c_int],
     "cemc_set_occupancy": [_H, _i8p],
     "cemc_get_occupancy": [_H, _i8p],
     "cemc_set_cf": [_H, _f64p],

@@ -69,6 +69,8 @@ struct cemc_handle {
   std::vector<int32_t> symm_of_site;
   std::vector<int8_t> allowed;
   int n_jobs = 0;
+  bool integer_bf = false;
+  int block_threads = 0;              // 0 = auto
 };
 
 // ---------------------------------------------------------------------------
@@ -121,28 +123,33 @@ __global__ void tracker_init_kernel(int N, int S, const int32_t *symm_of_site, c
 }
 
 // Brute-force CF partial sums (definition in SURVEY.md 8c): one CTA per (job, replica).
-// jobs [0, n_tasks_total) are cluster tasks; the rest are singlet ECIs.
+// jobs [0, n_tasks_total) are cluster tasks; the rest are the D singlet basis functions.
 __global__ void cf_partial_kernel(DeviceTables t, const int8_t *occ, double *partial, int n_jobs) {
   const int job = blockIdx.x, r = blockIdx.y;
   const int8_t *o = occ + (size_t)r * t.N;
+  const int RB = t.D * t.KP;
   double acc = 0.0;
   if (job < t.n_tasks_total) {
     int g = 0;
     while (job >= t.task_base[g + 1]) g++;
-    const Task T = t.tasks[job];
-    const Fam F = t.fams[T.fam];
+    // items of this task are contiguous: find the first one through its slot
+    const int2 ts = t.task_sum[job];
+    int q0 = t.item_base[g];
+    while (t.item_slot[q0] != ts.x) q0++;
     for (int a = threadIdx.x; a < t.N; a += blockDim.x) {
       if (t.symm_of_site[a] != g) continue;
       const int me = o[a];
       double sp = 0.0;
-      for (int m = 0; m < F.M; m++) {
-        const uint32_t pp = t.pos[F.pos_off + m];
+      for (int m = 0; m < ts.y; m++) {
+        const unsigned long long w = t.items[q0 + m];
         double tt = 1.0;
-        for (int k = 0; k < F.n; k++) {
-          const int p = (pp >> (8 * k)) & 0xff;
-          const int dk = (T.deco >> (8 * k)) & 0xff;
-          const int id = (p == t.K) ? me : (int)o[t.trans[(size_t)a * t.K + p]];
-          tt *= t.bf[dk * t.S + id];
+        for (int k = 0; k < 4; k++) {
+          const int idx = (int)((w >> (CEMC_ITEM_BITS * k)) & CEMC_ITEM_MASK);
+          if (idx == t.K) continue;                       // unused position
+          double f;
+          if (idx >= RB) f = t.bf[(idx - RB) * t.S + me];
+          else { const int d = idx / t.KP, c = idx % t.KP; f = t.bf[d * t.S + o[t.trans[(size_t)a * t.K + c]]]; }
+          tt *= f;
         }
         sp += tt;
       }
@@ -169,14 +176,15 @@ __global__ void cf_final_kernel(DeviceTables t, const double *partial, int n_job
     double v = 0.0;
     bool is_cluster = false, any = false;
     for (int g = 0; g < t.n_symm; g++) {
-      const Fin f = t.fin[g * t.n_eci + i];
-      if (f.kind == 0) { v = 1.0; break; }
-      if (f.kind == 1) { v = partial[(size_t)r * n_jobs + t.n_tasks_total + f.d] / (double)t.N; break; }
+      const int4 f = t.fin_i[g * t.n_eci + i];
+      const double2 fd = t.fin_d[g * t.n_eci + i];
+      if (f.x == 0) { v = 1.0; break; }
+      if (f.x == 1) { v = partial[(size_t)r * n_jobs + t.n_tasks_total + f.y] / (double)t.N; break; }
       is_cluster = true;
-      if (f.kind == 2 && f.t1 > f.t0) {
+      if (f.x == 2 && f.w > f.z) {
         double sg = 0.0;
-        for (int q = f.t0; q < f.t1; q++) sg += partial[(size_t)r * n_jobs + t.task_base[g] + q];
-        v += sg / ((double)(f.t1 - f.t0) * f.div);
+        for (int q = f.z; q < f.w; q++) sg += partial[(size_t)r * n_jobs + t.task_base[g] + q];
+        v += sg / ((double)(f.w - f.z) * fd.y);
         any = true;
       }
     }
@@ -234,6 +242,17 @@ static int dupload(cemc_handle *h, const T **p, const std::vector<T> &v) {
   CU(upload(&d, v.data(), v.size()));
   h->owned.push_back(d);
   *p = d;
+  return 0;
+}
+
+static int upload_allowed(cemc_handle *h) {
+  int8_t al[128], ap[128];
+  memset(al, 0, sizeof al);
+  memset(ap, -1, sizeof ap);
+  for (size_t i = 0; i < h->allowed.size(); i++) { al[i] = h->allowed[i]; ap[h->allowed[i]] = (int8_t)i; }
+  CU(cudaMemcpy((void *)h->t.allowed, al, 128, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy((void *)h->t.allowed_pos, ap, 128, cudaMemcpyHostToDevice));
+  h->t.n_allowed = (int)h->allowed.size();
   return 0;
 }
 
@@ -308,65 +327,87 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
 
   // ---- build the cluster program ------------------------------------------
   DeviceTables &t = h->t;
-  t.N = N; t.S = S; t.D = D; t.K = K; t.KP = K + 1; t.n_eci = n_eci; t.n_symm = tb->n_symm;
-  t.n_fam = tb->n_fam;
-  std::vector<Fam> fams(tb->n_fam);
-  std::vector<uint32_t> pos;
-  for (int f = 0; f < tb->n_fam; f++) {
-    const int n = tb->fam_size[f], M = tb->fam_nsub[f];
-    if (M > 65535) return fail("too many sub-clusters in one family");
-    fams[f].n = (uint16_t)n; fams[f].M = (uint16_t)M; fams[f].pos_off = (uint32_t)pos.size();
-    const int32_t *src = tb->fam_pos + tb->fam_pos_off[f];
-    for (int m = 0; m < M; m++) {
-      uint32_t w = 0;
-      for (int k = 0; k < n; k++) {
-        const int p = src[m * n + k];
-        w |= (uint32_t)(p == CEMC_POS_REF ? K : p) << (8 * k);
-      }
-      pos.push_back(w);
-    }
-  }
-  std::vector<Task> tasks;
-  std::vector<int32_t> task_base(tb->n_symm + 1, 0);
-  std::vector<Fin> fin((size_t)tb->n_symm * n_eci);
+  t.N = N; t.S = S; t.D = D; t.K = K; t.KP = K + 1; t.VS = D * (K + 1) + 2 * D;
+  t.n_eci = n_eci; t.n_symm = tb->n_symm;
+  if (t.VS > (int)CEMC_ITEM_MASK) return fail("too many (basis function, column) pairs for the item encoding");
+  const int RB = D * t.KP;
+  std::vector<unsigned long long> items;
+  std::vector<uint16_t> item_slot;
+  std::vector<int32_t> item_base(tb->n_symm + 1, 0), task_base(tb->n_symm + 1, 0);
+  std::vector<int2> task_sum;
+  std::vector<int4> fin_i((size_t)tb->n_symm * n_eci);
+  std::vector<double2> fin_d((size_t)tb->n_symm * n_eci);
   std::vector<int32_t> singlet_idx;
-  int max_tasks = 0;
+  int max_tasks = 0, max_items = 0, max_slots = 0;
   for (int g = 0; g < tb->n_symm; g++) {
-    task_base[g] = (int32_t)tasks.size();
+    task_base[g] = (int32_t)task_sum.size();
+    item_base[g] = (int32_t)items.size();
+    int slot = 0;
     for (int i = 0; i < n_eci; i++) {
-      Fin &f = fin[(size_t)g * n_eci + i];
-      f.kind = tb->eci_kind[i]; f.d = tb->eci_bf[i]; f.t0 = f.t1 = 0; f.scale = 0.0; f.div = 1.0;
-      if (f.kind == CEMC_ECI_SINGLET && (f.d < 0 || f.d >= D)) return fail("singlet decoration out of range");
-      if (f.kind != CEMC_ECI_CLUSTER) continue;
+      int4 &f = fin_i[(size_t)g * n_eci + i];
+      double2 &fd = fin_d[(size_t)g * n_eci + i];
+      f.x = tb->eci_kind[i]; f.y = tb->eci_bf[i]; f.z = f.w = 0; fd.x = 0.0; fd.y = 1.0;
+      if (f.x == CEMC_ECI_SINGLET && (f.y < 0 || f.y >= D)) return fail("singlet decoration out of range");
+      if (f.x != CEMC_ECI_CLUSTER) continue;
       const int term = g * n_eci + i;
       const int fam = tb->term_fam[term];
-      if (fam < 0) { f.kind = -1; continue; }
+      if (fam < 0) { f.x = -1; continue; }
+      if (fam >= tb->n_fam) return fail("family id out of range");
       const int d0 = tb->term_deco_off[term], d1 = tb->term_deco_off[term + 1];
       if (d1 <= d0) return fail("cluster ECI without decorations");
-      const int n = tb->fam_size[fam];
-      f.t0 = (int32_t)tasks.size() - task_base[g];
+      const int n = tb->fam_size[fam], M = tb->fam_nsub[fam];
+      const int32_t *pos = tb->fam_pos + tb->fam_pos_off[fam];
+      f.z = (int32_t)task_sum.size() - task_base[g];
       for (int e = d0; e < d1; e++) {
-        Task T; T.deco = 0; T.fam = (uint16_t)fam; T.eci = (uint16_t)i;
-        for (int k = 0; k < n; k++) {
-          const int dk = tb->deco[4 * e + k];
-          if (dk < 0 || dk >= D) return fail("decoration number out of range");
-          T.deco |= (uint32_t)dk << (8 * k);
+        const int tk = (int)task_sum.size() - task_base[g];
+        while (slot % 16 != tk % 16) slot++;        // bank-conflict-free sums (P2b)
+        task_sum.push_back(make_int2(slot, M));
+        for (int m = 0; m < M; m++) {
+          unsigned long long w = 0;
+          int kref = -1;
+          for (int k = 0; k < 4; k++) {
+            int idx = K;                              // constant 1.0
+            if (k < n) {
+              const int dk = tb->deco[4 * e + k];
+              if (dk < 0 || dk >= D) return fail("decoration number out of range");
+              const int p = pos[m * n + k];
+              if (p == CEMC_POS_REF) {
+                if (kref >= 0) return fail("a sub-cluster lists the changed site twice");
+                kref = k; idx = RB + dk;
+              } else idx = dk * t.KP + p;
+            }
+            w |= (unsigned long long)idx << (CEMC_ITEM_BITS * k);
+          }
+          if (kref < 0) return fail("a sub-cluster does not contain the changed site (bad `order`)");
+          w |= (unsigned long long)kref << 48;
+          items.push_back(w);
+          if (slot > 65535) return fail("cluster program too large (product slots)");
+          item_slot.push_back((uint16_t)slot++);
         }
-        tasks.push_back(T);
       }
-      f.t1 = (int32_t)tasks.size() - task_base[g];
-      f.scale = (double)n / (double)(d1 - d0);                                   // :400
-      f.div = (double)(tb->term_count[term] * tb->symm_count[g]);                // :402
+      f.w = (int32_t)task_sum.size() - task_base[g];
+      fd.x = (double)n / (double)(d1 - d0);                                      // :400
+      fd.y = (double)(tb->term_count[term] * tb->symm_count[g]);                 // :402
     }
-    max_tasks = std::max(max_tasks, (int)tasks.size() - task_base[g]);
+    max_tasks = std::max(max_tasks, (int)task_sum.size() - task_base[g]);
+    max_items = std::max(max_items, (int)items.size() - item_base[g]);
+    max_slots = std::max(max_slots, slot);
   }
-  task_base[tb->n_symm] = (int32_t)tasks.size();
+  task_base[tb->n_symm] = (int32_t)task_sum.size();
+  item_base[tb->n_symm] = (int32_t)items.size();
   for (int i = 0; i < n_eci; i++)
     if (tb->eci_kind[i] == CEMC_ECI_SINGLET) singlet_idx.push_back(i);
-  t.n_pos_words = (int)pos.size(); t.n_tasks_total = (int)tasks.size(); t.max_tasks = max_tasks;
+  t.n_items_total = (int)items.size(); t.n_tasks_total = (int)task_sum.size();
+  t.max_tasks = max_tasks; t.max_items = max_items; t.max_slots = max_slots;
   t.n_singlets = (int)singlet_idx.size();
   h->acc_stride = CEMC_ACC_STRIDE(t.n_singlets);
   h->n_jobs = t.n_tasks_total + D;
+  // order-free summation is bit-exact when every product is a small integer
+  h->integer_bf = true;
+  for (int q = 0; q < D * S; q++) {
+    const double v = tb->bf[q];
+    if (v != std::floor(v) || std::fabs(v) > 1024.0) h->integer_bf = false;
+  }
 
   std::vector<int32_t> trans(tb->trans, tb->trans + (size_t)N * K);
   std::vector<int32_t> symm(tb->symm_of_site, tb->symm_of_site + N);
@@ -383,19 +424,23 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   if ((rc = dupload(h, &t.trans, trans))) return rc;
   if ((rc = dupload(h, &t.symm_of_site, symm))) return rc;
   if ((rc = dupload(h, &t.bf, bf))) return rc;
-  if ((rc = dupload(h, &t.tasks, tasks))) return rc;
+  if ((rc = dupload(h, &t.items, items))) return rc;
+  if ((rc = dupload(h, &t.item_slot, item_slot))) return rc;
+  if ((rc = dupload(h, &t.item_base, item_base))) return rc;
   if ((rc = dupload(h, &t.task_base, task_base))) return rc;
-  if ((rc = dupload(h, &t.fams, fams))) return rc;
-  if ((rc = dupload(h, &t.pos, pos))) return rc;
-  if ((rc = dupload(h, &t.fin, fin))) return rc;
+  if ((rc = dupload(h, &t.task_sum, task_sum))) return rc;
+  if ((rc = dupload(h, &t.fin_i, fin_i))) return rc;
+  if ((rc = dupload(h, &t.fin_d, fin_d))) return rc;
   if ((rc = dupload(h, &t.singlet_idx, singlet_idx))) return rc;
   if (t.n_active != N) { if ((rc = dupload(h, &t.active, active))) return rc; }
   else t.active = nullptr;
+  t.uniform_group = (tb->n_symm == 1 && t.n_active == N) ? 1 : 0;
   {
-    int8_t *al = nullptr;
+    int8_t *al = nullptr, *ap = nullptr;
     if ((rc = dalloc(h, &al, 128))) return rc;
-    CU(cudaMemcpy(al, h->allowed.data(), S, cudaMemcpyHostToDevice));
-    t.allowed = al;
+    if ((rc = dalloc(h, &ap, 128))) return rc;
+    t.allowed = al; t.allowed_pos = ap;
+    if ((rc = upload_allowed(h))) return rc;
   }
 
   // ---- per-replica state ---------------------------------------------------
@@ -576,6 +621,13 @@ int cemc_get_kT(cemc_handle *h, double *kT) {
   return 0;
 }
 
+int cemc_set_block_threads(cemc_handle *h, int n) {
+  if (!h) return fail("null handle");
+  if (n != 0 && (n < 32 || n > 256 || n % 32)) return fail("block threads must be 0 (auto) or a multiple of 32 in [32, 256]");
+  h->block_threads = n;
+  return 0;
+}
+
 int cemc_seed(cemc_handle *h, uint64_t seed) {
   if (!h) return fail("null handle");
   h->seed = seed;
@@ -588,11 +640,11 @@ int cemc_set_sgc_species(cemc_handle *h, int n_allowed, const int8_t *allowed) {
   for (int i = 0; i < n_allowed; i++)
     if (allowed[i] < 0 || allowed[i] >= h->t.S) return fail("species id out of range");
   CU(cudaSetDevice(h->device));
-  h->allowed.assign(allowed, allowed + n_allowed);
-  CU(cudaMemcpyAsync((void *)h->t.allowed, allowed, n_allowed, cudaMemcpyHostToDevice, h->stream));
+  for (int i = 0; i < n_allowed; i++)
+    for (int j = 0; j < i; j++) if (allowed[i] == allowed[j]) return fail("duplicate species");
   CU(cudaStreamSynchronize(h->stream));
-  h->t.n_allowed = n_allowed;
-  return 0;
+  h->allowed.assign(allowed, allowed + n_allowed);
+  return upload_allowed(h);
 }
 
 int cemc_get_counters(cemc_handle *h, uint64_t *steps, uint64_t *accepted) {
@@ -623,8 +675,19 @@ int cemc_set_step(cemc_handle *h, const uint64_t *steps) {
 
 // ---------------------------------------------------------------------------
 static int n_threads_for(const cemc_handle *h, int sites_changed) {
-  const int items = std::max({sites_changed * h->t.K, sites_changed * h->t.max_tasks, 32});
+  if (h->block_threads > 0) return h->block_threads;
+  // one pass over the products of a move, but never fewer threads than gather columns
+  const int items = std::max({sites_changed * h->t.KP, sites_changed * h->t.max_items, 32});
   return std::min(256, (items + 31) / 32 * 32);
+}
+
+template <int MODE, bool kSmem, bool kTree>
+static int launch_one(cemc_handle *h, const ReplicaState &st, const RunArgs &a, int n_rep, int nthr, size_t sm) {
+  CU(cudaFuncSetAttribute(mc_kernel<MODE, kSmem, kTree>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  mc_kernel<MODE, kSmem, kTree><<<n_rep, nthr, sm, h->stream>>>(h->t, st, a, h->acc_stride);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
 }
 
 template <int MODE>
@@ -635,24 +698,19 @@ static int launch_mc(cemc_handle *h, const RunArgs &a, int first_replica, int n_
   const size_t sm = in_smem ? sm_state : smem_bytes(h->t, h->acc_stride, canonical, false);
   if (sm > (size_t)h->max_smem_optin) return fail("cluster program does not fit in shared memory");
   const int nthr = n_threads_for(h, MODE == MODE_SGC ? 1 : 2);
+  // TREE sums are used when asked for, or when they are provably bit-identical
+  const bool tree = (h->order_mode == CEMC_ORDER_TREE) || h->integer_bf;
   ReplicaState st = h->st;
-  // offset the replica-major pointers when launching a sub-range (trial API)
-  if (first_replica) {
+  if (first_replica) {      // sub-range launch (trial API): offset the replica-major pointers
     const size_t r0 = first_replica;
     st.occ += r0 * h->t.N; st.cf += r0 * h->t.n_eci; st.eci += r0 * h->t.n_eci; st.e_cur += r0;
     st.kT += r0; st.acc += r0 * h->acc_stride; st.ref += r0; st.step += r0; st.accepted += r0;
     st.list += r0 * h->t.N; st.loc += r0 * h->t.N; st.off += r0 * (h->t.S + 1); st.status += r0;
   }
-  if (in_smem) {
-    CU(cudaFuncSetAttribute(mc_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    mc_kernel<MODE, true><<<n_rep, nthr, sm, h->stream>>>(h->t, st, a, h->acc_stride);
-  } else {
-    CU(cudaFuncSetAttribute(mc_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    mc_kernel<MODE, false><<<n_rep, nthr, sm, h->stream>>>(h->t, st, a, h->acc_stride);
-  }
-  h->launches++;
-  CU(cudaGetLastError());
-  return 0;
+  if (in_smem) return tree ? launch_one<MODE, true, true>(h, st, a, n_rep, nthr, sm)
+                           : launch_one<MODE, true, false>(h, st, a, n_rep, nthr, sm);
+  return tree ? launch_one<MODE, false, true>(h, st, a, n_rep, nthr, sm)
+              : launch_one<MODE, false, false>(h, st, a, n_rep, nthr, sm);
 }
 
 static int ensure_scratch(cemc_handle *h, long long n_steps) {

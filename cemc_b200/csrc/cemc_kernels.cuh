@@ -3,10 +3,21 @@
 // One CTA per replica (independent Markov chain).  Per-replica state lives in
 // shared memory for the whole launch: int8 occupations, the running
 // correlation-function (CF) vector, the per-species site lists of the
-// canonical sampler.  The read-only cluster "program" (families, decorations,
-// per-ECI normalisation) is staged once per CTA; the translation matrix stays
-// in global memory and is read through the read-only path (L1/L2 resident,
+// canonical sampler.  The read-only cluster "program" (items, tasks, per-ECI
+// normalisation) is staged once per CTA; the translation matrix stays in
+// global memory and is read through the read-only path (L1/L2 resident,
 // shared by all replicas).
+//
+// Work decomposition of one trial move (c = 1 or 2 changed sites):
+//   P1 gather   one thread per (site, translation column): T row -> neighbour
+//               occupation -> basis-function values V[d][col] in shared memory
+//   P2a items   one thread per (site, ECI, decoration, sub-cluster): the
+//               left-to-right product of spin_product_one_atom for the old
+//               and the new species of the changed site
+//   P2b sums    one thread per (site, ECI, decoration): sum over sub-clusters
+//               in the reference's order (or 4-way interleaved in TREE mode)
+//   P3  warp 0  per-ECI normalisation, CF increment, sequential energy dot,
+//               Metropolis test, commit, observers
 //
 // Arithmetic follows the reference's operation order exactly (SURVEY.md
 // Appendix A; /root/reference/cpp/src/ce_updater.cpp:244-285, :313-406,
@@ -21,41 +32,32 @@ namespace cemc {
 
 enum Mode : int { MODE_REPLAY = 0, MODE_SGC = 1, MODE_CANONICAL = 2 };
 
-struct Task {            // one (ECI, equivalent decoration) spin-product sum
-  uint32_t deco;         // 4 x u8 decoration numbers
-  uint16_t fam;          // family id
-  uint16_t eci;          // ECI index
-};
-struct Fam {
-  uint16_t n;            // cluster size 2..4
-  uint16_t M;            // sub-clusters
-  uint32_t pos_off;      // first packed position word
-};
-struct Fin {             // per (symmetry group, ECI)
-  int32_t kind;          // cemc_eci_kind, or -1: cluster not in this group (copy)
-  int32_t d;             // singlet decoration number
-  int32_t t0, t1;        // task range (relative to the group's first task)
-  double scale;          // (double)n / |E|            ce_updater.cpp:400
-  double div;            // (double)(count * N_g)      ce_updater.cpp:402
-};
+// item word: 4 x 12-bit indices into V (sorted cluster positions 0..3; unused
+// positions point at the constant 1.0), bits 48-49 = position of the changed site.
+#define CEMC_ITEM_BITS 12
+#define CEMC_ITEM_MASK 0xfffu
 
 struct DeviceTables {    // device pointers, shared by all replicas
-  int N, S, D, K, KP, n_eci, n_symm, n_fam, n_pos_words, n_tasks_total, max_tasks;
+  int N, S, D, K, KP, VS, n_eci, n_symm, n_singlets;
+  int n_items_total, n_tasks_total, max_tasks, max_items, max_slots;
   const int32_t *trans;        // [N][K]
   const int32_t *symm_of_site; // [N]
   const double *bf;            // [D][S]
-  const Task *tasks;           // [n_tasks_total]
+  const unsigned long long *items;  // [n_items_total]
+  const uint16_t *item_slot;   // [n_items_total] product slot (padded, per group)
+  const int32_t *item_base;    // [n_symm+1]
   const int32_t *task_base;    // [n_symm+1]
-  const Fam *fams;             // [n_fam]
-  const uint32_t *pos;         // packed positions, one word per sub-cluster
-  const Fin *fin;              // [n_symm][n_eci]
+  const int2 *task_sum;        // [n_tasks_total] {first slot, M}
+  const int4 *fin_i;           // [n_symm][n_eci] {kind, d, t0, t1}; kind -1 = copy
+  const double2 *fin_d;        // [n_symm][n_eci] {scale (:400), div (:402)}
   const int32_t *singlet_idx;  // [n_singlets]
-  int n_singlets;
+  int uniform_group;           // 1: one symmetry group, no background sites
   // SGC proposal support
   int n_active;                // non-background sites
   const int32_t *active;       // [n_active] or nullptr when n_active == N
   int n_allowed;
-  const int8_t *allowed;       // [n_allowed]
+  const int8_t *allowed;       // [128] species ids the sampler may insert
+  const int8_t *allowed_pos;   // [128] position of a species in `allowed`, -1 if absent
 };
 
 struct ReplicaState {    // device pointers, replica-major
@@ -107,136 +109,96 @@ __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32
 }
 
 __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
-  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
 struct Smem {            // carved from dynamic shared memory
-  double *cf, *cfn, *eci, *prod, *A, *diff, *bf, *acc;
-  Fin *fin;
-  Task *tasks;
-  Fam *fams;
-  uint32_t *pos;
-  int32_t *task_base, *singlet_idx, *off, *present;
-  uint32_t *rng;         // [32][8]
+  double *cf, *cfn, *eci, *prod, *V, *PO, *PN, *diff, *bf, *acc;
+  double2 *fin_d;
+  unsigned long long *items;
+  int4 *fin_i;
+  int2 *task_sum;
+  int32_t *item_base, *task_base, *singlet_idx, *off, *present;
+  uint4 *rng;            // [32][2]: 8 Philox words per move
+  uint16_t *item_slot;
+  int8_t *allowed, *allowed_pos;
   int32_t *list;         // or global
   int8_t *occ;           // or global
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline size_t at_least_1(int x) { return x > 0 ? (size_t)x : 1; }
 
-// Shared-memory footprint; state_in_smem selects occ/list residency.
-inline size_t smem_bytes(const DeviceTables &t, int acc_stride, bool canonical,
-                         bool state_in_smem) {
-  size_t b = 0;
-  b += sizeof(double) * (size_t)t.n_eci * 4;               // cf cfn eci prod
-  b += sizeof(double) * (size_t)2 * t.D * t.KP;            // A
-  b += sizeof(double) * (size_t)2 * (t.max_tasks > 0 ? t.max_tasks : 1);  // diff
-  b += sizeof(double) * (size_t)t.D * t.S;                 // bf
-  b += sizeof(double) * (size_t)acc_stride;                // acc
-  b += sizeof(Fin) * (size_t)t.n_symm * t.n_eci;
-  b = align_up(b, 8);
-  b += sizeof(Task) * (size_t)(t.n_tasks_total > 0 ? t.n_tasks_total : 1);
-  b += sizeof(Fam) * (size_t)(t.n_fam > 0 ? t.n_fam : 1);
-  b += sizeof(uint32_t) * (size_t)(t.n_pos_words > 0 ? t.n_pos_words : 1);
-  b += sizeof(int32_t) * (size_t)(t.n_symm + 1);
-  b += sizeof(int32_t) * (size_t)(t.n_singlets > 0 ? t.n_singlets : 1);
-  b += sizeof(int32_t) * (size_t)(t.S + 1) * 2;            // off, present
-  b += sizeof(uint32_t) * 32 * 8;                          // rng ring
-  b = align_up(b, 16) + 16;
-  if (state_in_smem) {
-    if (canonical) b += sizeof(int32_t) * (size_t)t.N;
-    b += align_up((size_t)t.N, 16);
-  }
-  return align_up(b, 16);
-}
-
+// Walks the layout; with base == nullptr only the size is computed.
 template <bool kStateSmem>
-__device__ __forceinline__ Smem carve(unsigned char *base, const DeviceTables &t, int acc_stride,
-                                      bool canonical, int8_t *g_occ, int32_t *g_list) {
-  Smem s;
-  double *d = reinterpret_cast<double *>(base);
-  s.cf = d; d += t.n_eci;
-  s.cfn = d; d += t.n_eci;
-  s.eci = d; d += t.n_eci;
-  s.prod = d; d += t.n_eci;
-  s.A = d; d += 2 * t.D * t.KP;
-  s.diff = d; d += 2 * (t.max_tasks > 0 ? t.max_tasks : 1);
-  s.bf = d; d += t.D * t.S;
-  s.acc = d; d += acc_stride;
-  s.fin = reinterpret_cast<Fin *>(d);
-  unsigned char *p = reinterpret_cast<unsigned char *>(s.fin + (size_t)t.n_symm * t.n_eci);
-  p = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<size_t>(p), 8));
-  s.tasks = reinterpret_cast<Task *>(p); p += sizeof(Task) * (t.n_tasks_total > 0 ? t.n_tasks_total : 1);
-  s.fams = reinterpret_cast<Fam *>(p); p += sizeof(Fam) * (t.n_fam > 0 ? t.n_fam : 1);
-  s.pos = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * (t.n_pos_words > 0 ? t.n_pos_words : 1);
-  s.task_base = reinterpret_cast<int32_t *>(p); p += sizeof(int32_t) * (t.n_symm + 1);
-  s.singlet_idx = reinterpret_cast<int32_t *>(p); p += sizeof(int32_t) * (t.n_singlets > 0 ? t.n_singlets : 1);
-  s.off = reinterpret_cast<int32_t *>(p); p += sizeof(int32_t) * (t.S + 1);
-  s.present = reinterpret_cast<int32_t *>(p); p += sizeof(int32_t) * (t.S + 1);
-  s.rng = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * 32 * 8;
-  p = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<size_t>(p), 16));
+__host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, const DeviceTables &t,
+                                              int acc_stride, bool canonical, int8_t *g_occ,
+                                              int32_t *g_list) {
+  size_t o = 0;
+#define CEMC_TAKE(field, type, count)                                   \
+  do {                                                                  \
+    o = align_up(o, sizeof(type) < 16 ? sizeof(type) : 16);             \
+    if (s) s->field = reinterpret_cast<type *>(base + o);               \
+    o += sizeof(type) * at_least_1((int)(count));                       \
+  } while (0)
+  CEMC_TAKE(fin_d, double2, t.n_symm * t.n_eci);
+  CEMC_TAKE(cf, double, t.n_eci);
+  CEMC_TAKE(cfn, double, t.n_eci);
+  CEMC_TAKE(eci, double, t.n_eci);
+  CEMC_TAKE(prod, double, t.n_eci);
+  CEMC_TAKE(V, double, 2 * t.VS);
+  CEMC_TAKE(PO, double, 2 * t.max_slots);
+  CEMC_TAKE(PN, double, 2 * t.max_slots);
+  CEMC_TAKE(diff, double, 2 * t.max_tasks);
+  CEMC_TAKE(bf, double, t.D * t.S);
+  CEMC_TAKE(acc, double, acc_stride);
+  CEMC_TAKE(items, unsigned long long, t.n_items_total);
+  CEMC_TAKE(fin_i, int4, t.n_symm * t.n_eci);
+  CEMC_TAKE(task_sum, int2, t.n_tasks_total);
+  CEMC_TAKE(item_base, int32_t, t.n_symm + 1);
+  CEMC_TAKE(task_base, int32_t, t.n_symm + 1);
+  CEMC_TAKE(singlet_idx, int32_t, t.n_singlets);
+  CEMC_TAKE(off, int32_t, t.S + 1);
+  CEMC_TAKE(present, int32_t, t.S + 1);
+  CEMC_TAKE(rng, uint4, 32 * 2);
+  CEMC_TAKE(item_slot, uint16_t, t.n_items_total);
+  CEMC_TAKE(allowed, int8_t, 128);
+  CEMC_TAKE(allowed_pos, int8_t, 128);
   if (kStateSmem) {
-    if (canonical) { s.list = reinterpret_cast<int32_t *>(p); p += sizeof(int32_t) * (size_t)t.N; }
-    else s.list = g_list;
-    s.occ = reinterpret_cast<int8_t *>(p);
-  } else {
-    s.list = g_list;
-    s.occ = g_occ;
+    if (canonical) CEMC_TAKE(list, int32_t, t.N);
+    else if (s) s->list = g_list;
+    o = align_up(o, 16);
+    if (s) s->occ = reinterpret_cast<int8_t *>(base + o);
+    o += align_up((size_t)t.N, 16);
+  } else if (s) {
+    s->list = g_list;
+    s->occ = g_occ;
   }
-  return s;
+#undef CEMC_TAKE
+  return align_up(o, 16);
 }
 
-// One (ECI, decoration) task: sp_new - sp_ref of ce_updater.cpp:395-397 with
-// spin_product_one_atom (:244-285) evaluated for old and new in one pass.
-template <int N_>
-__device__ __forceinline__ double task_diff(const uint32_t *__restrict__ pos, int M,
-                                            const double *__restrict__ A, int KP, int K,
-                                            uint32_t deco, const double *__restrict__ bf, int S,
-                                            int old_id, int new_id) {
-  int aoff[N_];
-  double rO[N_], rN[N_];
-#pragma unroll
-  for (int k = 0; k < N_; k++) {
-    const int dk = (deco >> (8 * k)) & 0xff;
-    aoff[k] = dk * KP;
-    rO[k] = bf[dk * S + old_id];
-    rN[k] = bf[dk * S + new_id];
-  }
-  double spO = 0.0, spN = 0.0;
-#pragma unroll 4
-  for (int m = 0; m < M; m++) {
-    const uint32_t pp = pos[m];
-    double tO = 0.0, tN = 0.0;
-#pragma unroll
-    for (int k = 0; k < N_; k++) {
-      const int p = (pp >> (8 * k)) & 0xff;
-      const double f = A[aoff[k] + p];
-      const bool isref = (p == K);
-      const double fO = isref ? rO[k] : f;
-      const double fN = isref ? rN[k] : f;
-      if (k == 0) { tO = fO; tN = fN; }        // 1.0 * f == f exactly (:255,:275)
-      else { tO = __dmul_rn(tO, fO); tN = __dmul_rn(tN, fN); }
-    }
-    spO = __dadd_rn(spO, tO);                  // :282
-    spN = __dadd_rn(spN, tN);
-  }
-  return __dsub_rn(spN, spO);                  // :397
+inline size_t smem_bytes(const DeviceTables &t, int acc_stride, bool canonical, bool state_in_smem) {
+  return state_in_smem ? smem_layout<true>(nullptr, nullptr, t, acc_stride, canonical, nullptr, nullptr)
+                       : smem_layout<false>(nullptr, nullptr, t, acc_stride, canonical, nullptr, nullptr);
 }
 
-template <int MODE, bool kStateSmem>
+template <int MODE, bool kStateSmem, bool kTree>
 __global__ void __launch_bounds__(256)
 mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int r = blockIdx.x;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int N = t.N, K = t.K, KP = t.KP, S = t.S, D = t.D, n_eci = t.n_eci;
+  const int N = t.N, K = t.K, KP = t.KP, S = t.S, D = t.D, VS = t.VS, n_eci = t.n_eci;
+  const int RB = D * KP;                       // first "changed site" slot of V
   constexpr bool kCanon = (MODE == MODE_CANONICAL);
 
   int8_t *g_occ = st.occ + (size_t)r * N;
   int32_t *g_list = st.list ? st.list + (size_t)r * N : nullptr;
   int32_t *g_loc = st.loc ? st.loc + (size_t)r * N : nullptr;
-  Smem s = carve<kStateSmem>(smem_raw, t, acc_stride, kCanon, g_occ, g_list);
+  Smem s;
+  smem_layout<kStateSmem>(&s, smem_raw, t, acc_stride, kCanon, g_occ, g_list);
 
   // ---- stage per-replica state and the cluster program -------------------
   for (int i = tid; i < n_eci; i += nthr) {
@@ -245,19 +207,18 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   }
   for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
   for (int i = tid; i < acc_stride; i += nthr) s.acc[i] = st.acc[(size_t)r * acc_stride + i];
-  for (int i = tid; i < t.n_symm * n_eci; i += nthr) s.fin[i] = t.fin[i];
-  for (int i = tid; i < t.n_tasks_total; i += nthr) s.tasks[i] = t.tasks[i];
-  for (int i = tid; i < t.n_fam; i += nthr) s.fams[i] = t.fams[i];
-  for (int i = tid; i < t.n_pos_words; i += nthr) s.pos[i] = t.pos[i];
-  for (int i = tid; i <= t.n_symm; i += nthr) s.task_base[i] = t.task_base[i];
+  for (int i = tid; i < t.n_symm * n_eci; i += nthr) { s.fin_i[i] = t.fin_i[i]; s.fin_d[i] = t.fin_d[i]; }
+  for (int i = tid; i < t.n_items_total; i += nthr) { s.items[i] = t.items[i]; s.item_slot[i] = t.item_slot[i]; }
+  for (int i = tid; i < t.n_tasks_total; i += nthr) s.task_sum[i] = t.task_sum[i];
+  for (int i = tid; i <= t.n_symm; i += nthr) { s.item_base[i] = t.item_base[i]; s.task_base[i] = t.task_base[i]; }
   for (int i = tid; i < t.n_singlets; i += nthr) s.singlet_idx[i] = t.singlet_idx[i];
-  for (int i = tid; i < 2 * D * KP; i += nthr) s.A[i] = 1.0;   // column K stays 1.0
+  for (int i = tid; i < 128; i += nthr) { s.allowed[i] = t.allowed[i]; s.allowed_pos[i] = t.allowed_pos[i]; }
+  for (int i = tid; i < 2 * VS; i += nthr) s.V[i] = 1.0;       // V[K] is the constant 1.0
   if (kStateSmem) {
-    // 16-byte vectorised copy of the int8 occupations
-    const int nvec = N / 16;
-    const int4 *src = reinterpret_cast<const int4 *>(g_occ);
-    int4 *dst = reinterpret_cast<int4 *>(s.occ);
+    const int nvec = N / 16;                   // 16-byte vectorised copy of the int8 occupations
     if ((reinterpret_cast<size_t>(g_occ) & 15) == 0) {
+      const int4 *src = reinterpret_cast<const int4 *>(g_occ);
+      int4 *dst = reinterpret_cast<int4 *>(s.occ);
       for (int i = tid; i < nvec; i += nthr) dst[i] = src[i];
       for (int i = nvec * 16 + tid; i < N; i += nthr) s.occ[i] = g_occ[i];
     } else {
@@ -290,13 +251,14 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   const double kT = st.kT[r];
   const double ref = st.ref[r];
   const double dN = (double)(unsigned)N;
-  unsigned long long step0 = st.step[r];
+  const unsigned long long step0 = st.step[r];
   unsigned long long n_acc = 0;
   const uint32_t rep_global = a.replica_offset + (uint32_t)r;
+  const int n_allowed = t.n_allowed;
   int err = 0;
 
   for (long long it = 0; it < a.n_steps; it++) {
-    // ---- P0: proposal ------------------------------------------------------
+    // ---- P0: proposal (every thread, redundantly) --------------------------
     int site0, site1 = -1, new0, new1 = 0, slot0 = 0, slot1 = 0;
     double u;
     if (MODE == MODE_REPLAY) {
@@ -307,13 +269,12 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
       if (site0 < 0 || site0 >= N || site1 >= N || new0 < 0 || new0 >= S ||
           (site1 >= 0 && (new1 < 0 || new1 >= S))) { err = 3; break; }
     } else {
-      if ((it & 31) == 0) {
-        __syncthreads();                       // everyone done with the old ring
+      if ((it & 31) == 0) {                    // refill the Philox ring: 32 moves per call
         if (warp == 0) {
           const unsigned long long stp = step0 + (unsigned long long)it + lane;
           uint32_t c0 = (uint32_t)stp, c1 = (uint32_t)(stp >> 32), c2 = rep_global, c3 = 0;
           philox4x32_10(c0, c1, c2, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-          uint32_t *w = s.rng + lane * 8;
+          uint32_t *w = reinterpret_cast<uint32_t *>(s.rng + lane * 2);
           w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
           if (kCanon) {
             c0 = (uint32_t)stp; c1 = (uint32_t)(stp >> 32); c2 = rep_global; c3 = 1;
@@ -323,91 +284,139 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
         }
         __syncthreads();
       }
-      const uint32_t *w = s.rng + (it & 31) * 8;
+      const uint4 w = s.rng[(it & 31) * 2];
       if (MODE == MODE_SGC) {
-        // sgc_montecarlo.py:69-75: site uniform, new species uniform among others
-        const uint32_t ia = __umulhi(w[0], (uint32_t)t.n_active);
+        // sgc_montecarlo.py:69-75: site uniform, new species uniform among the others
+        const uint32_t ia = __umulhi(w.x, (uint32_t)t.n_active);
         site0 = t.active ? t.active[ia] : (int)ia;
-        const int old = s.occ[site0];
-        int p = -1;
-        for (int q = 0; q < t.n_allowed; q++) if (t.allowed[q] == old) p = q;
+        const int p = s.allowed_pos[s.occ[site0]];
         int rr;
-        if (p >= 0) { rr = (int)__umulhi(w[1], (uint32_t)(t.n_allowed - 1)); rr += (rr >= p); }
-        else rr = (int)__umulhi(w[1], (uint32_t)t.n_allowed);
-        new0 = t.allowed[rr];
-        u = u53(w[2], w[3]);
+        if (p >= 0) { rr = (int)__umulhi(w.y, (uint32_t)(n_allowed - 1)); rr += (rr >= p); }
+        else rr = (int)__umulhi(w.y, (uint32_t)n_allowed);
+        new0 = s.allowed[rr];
+        u = u53(w.z, w.w);
       } else {
         // montecarlo.py:899-907: species pair uniform (a != b), site uniform per species
-        const int ia = (int)__umulhi(w[0], (uint32_t)n_present);
-        int ib = (int)__umulhi(w[1], (uint32_t)(n_present - 1)); ib += (ib >= ia);
+        const uint4 w2 = s.rng[(it & 31) * 2 + 1];
+        const int ia = (int)__umulhi(w.x, (uint32_t)n_present);
+        int ib = (int)__umulhi(w.y, (uint32_t)(n_present - 1)); ib += (ib >= ia);
         const int sa = s.present[ia], sb = s.present[ib];
-        slot0 = s.off[sa] + (int)__umulhi(w[2], (uint32_t)(s.off[sa + 1] - s.off[sa]));
-        slot1 = s.off[sb] + (int)__umulhi(w[3], (uint32_t)(s.off[sb + 1] - s.off[sb]));
+        slot0 = s.off[sa] + (int)__umulhi(w.z, (uint32_t)(s.off[sa + 1] - s.off[sa]));
+        slot1 = s.off[sb] + (int)__umulhi(w.w, (uint32_t)(s.off[sb + 1] - s.off[sb]));
         site0 = s.list[slot0]; site1 = s.list[slot1];
         new0 = sb; new1 = sa;
-        u = u53(w[4], w[5]);
+        u = u53(w2.x, w2.y);
       }
     }
     const int old0 = s.occ[site0];
     const int old1 = site1 >= 0 ? (site1 == site0 ? new0 : (int)s.occ[site1]) : 0;
     const bool ch0 = (old0 != new0);                       // ce_updater.cpp:315
     const bool ch1 = (site1 >= 0) && (old1 != new1);
-    const int g0 = t.symm_of_site[site0];
-    const int g1 = site1 >= 0 ? t.symm_of_site[site1] : 0;
-    if ((ch0 && g0 < 0) || (ch1 && g1 < 0)) { err = 1; break; }   // :330 background atom
+    int g0 = 0, g1 = 0;
+    if (!t.uniform_group) {
+      g0 = t.symm_of_site[site0];
+      g1 = site1 >= 0 ? t.symm_of_site[site1] : 0;
+      if ((ch0 && g0 < 0) || (ch1 && g1 < 0)) { err = 1; break; }   // :330 background atom
+    }
 
     // ---- P1: gather neighbour occupations -> basis-function values ---------
-    for (int q = tid; q < 2 * K; q += nthr) {
-      const int j = q >= K, c = j ? q - K : q;
-      if (j ? ch1 : ch0) {
+    for (int q = tid; q < 2 * KP; q += nthr) {
+      const int j = q >= KP, c = j ? q - KP : q;
+      if (!(j ? ch1 : ch0)) continue;
+      double *Vj = s.V + j * VS;
+      if (c < K) {
         const int sj = j ? site1 : site0;
-        const int nb = __ldg(&t.trans[(size_t)sj * K + c]);       // :264
+        const int nb = __ldg(&t.trans[(size_t)sj * K + c]);         // :264
         int v = s.occ[nb];
         if (j && nb == site0) v = new0;        // change 1 sees change 0 applied (:845-852)
-        double *Aj = s.A + (size_t)j * D * KP;
-        for (int d = 0; d < D; d++) Aj[d * KP + c] = s.bf[d * S + v];
-      }
-    }
-    __syncthreads();
-
-    // ---- P2: spin-product sums, one thread per (changed site, task) --------
-    {
-      const int nt0 = ch0 ? (s.task_base[g0 + 1] - s.task_base[g0]) : 0;
-      const int nt1 = ch1 ? (s.task_base[g1 + 1] - s.task_base[g1]) : 0;
-      for (int q = tid; q < nt0 + nt1; q += nthr) {
-        const int j = q >= nt0, tk = j ? q - nt0 : q;
-        const int g = j ? g1 : g0;
-        const Task T = s.tasks[s.task_base[g] + tk];
-        const Fam F = s.fams[T.fam];
-        const double *Aj = s.A + (size_t)j * D * KP;
+        for (int d = 0; d < D; d++) Vj[d * KP + c] = s.bf[d * S + v];
+      } else {                                 // the changed site: old and new (:273-276)
         const int oid = j ? old1 : old0, nid = j ? new1 : new0;
-        double dv;
-        if (F.n == 2) dv = task_diff<2>(s.pos + F.pos_off, F.M, Aj, KP, K, T.deco, s.bf, S, oid, nid);
-        else if (F.n == 3) dv = task_diff<3>(s.pos + F.pos_off, F.M, Aj, KP, K, T.deco, s.bf, S, oid, nid);
-        else dv = task_diff<4>(s.pos + F.pos_off, F.M, Aj, KP, K, T.deco, s.bf, S, oid, nid);
-        s.diff[j * t.max_tasks + tk] = dv;
+        for (int d = 0; d < D; d++) {
+          Vj[RB + d] = s.bf[d * S + oid];
+          Vj[RB + D + d] = s.bf[d * S + nid];
+        }
       }
     }
     __syncthreads();
 
-    // ---- P3/P4 (warp 0): per-ECI increments, energy, Metropolis, commit ----
+    // ---- P2a: one product per (site, task, sub-cluster), old and new -------
+    const int ib0 = s.item_base[g0], ib1 = s.item_base[g1];
+    const int ni0 = ch0 ? (s.item_base[g0 + 1] - ib0) : 0;
+    const int ni1 = ch1 ? (s.item_base[g1 + 1] - ib1) : 0;
+    for (int q = tid; q < ni0 + ni1; q += nthr) {
+      const int j = q >= ni0;
+      const int qi = j ? ib1 + (q - ni0) : ib0 + q;
+      const unsigned long long w = s.items[qi];
+      const int slot = s.item_slot[qi] + j * t.max_slots;
+      const double *Vj = s.V + j * VS;
+      const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+      const int i0 = lo & CEMC_ITEM_MASK, i1 = (lo >> 12) & CEMC_ITEM_MASK;
+      const int i2 = (uint32_t)(w >> 24) & CEMC_ITEM_MASK, i3 = (hi >> 4) & CEMC_ITEM_MASK;
+      const int kref = (hi >> 16) & 3;
+      const double f0 = Vj[i0], f1 = Vj[i1], f2 = Vj[i2], f3 = Vj[i3];
+      const int iref = kref == 0 ? i0 : kref == 1 ? i1 : kref == 2 ? i2 : i3;
+      const double fr = Vj[iref + D];
+      // left-to-right product (:271-281); 1.0 * f == f and f * 1.0 == f exactly
+      const double tO = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), f2), f3);
+      const double tN = __dmul_rn(__dmul_rn(__dmul_rn(kref == 0 ? fr : f0, kref == 1 ? fr : f1),
+                                            kref == 2 ? fr : f2), kref == 3 ? fr : f3);
+      s.PO[slot] = tO;
+      s.PN[slot] = tN;
+    }
+    __syncthreads();
+
+    // ---- P2b: sum over sub-clusters per (site, task) ------------------------
+    const int tb0 = s.task_base[g0], tb1 = s.task_base[g1];
+    const int nt0 = ch0 ? (s.task_base[g0 + 1] - tb0) : 0;
+    const int nt1 = ch1 ? (s.task_base[g1 + 1] - tb1) : 0;
+    for (int q = tid; q < nt0 + nt1; q += nthr) {
+      const int j = q >= nt0;
+      const int tk = j ? q - nt0 : q;
+      const int2 ts = s.task_sum[(j ? tb1 : tb0) + tk];
+      const double *po = s.PO + ts.x + j * t.max_slots;
+      const double *pn = s.PN + ts.x + j * t.max_slots;
+      double dv;
+      if (!kTree) {
+        double spO = 0.0, spN = 0.0;                         // :246, :282
+#pragma unroll 4
+        for (int m = 0; m < ts.y; m++) { spO = __dadd_rn(spO, po[m]); spN = __dadd_rn(spN, pn[m]); }
+        dv = __dsub_rn(spN, spO);                            // :397
+      } else {
+        // order-free variant: exact whenever every product is an integer
+        double o0 = 0.0, o1 = 0.0, n0 = 0.0, n1 = 0.0;
+        int m = 0;
+        for (; m + 1 < ts.y; m += 2) {
+          o0 = __dadd_rn(o0, po[m]); o1 = __dadd_rn(o1, po[m + 1]);
+          n0 = __dadd_rn(n0, pn[m]); n1 = __dadd_rn(n1, pn[m + 1]);
+        }
+        if (m < ts.y) { o0 = __dadd_rn(o0, po[m]); n0 = __dadd_rn(n0, pn[m]); }
+        dv = __dsub_rn(__dadd_rn(n0, n1), __dadd_rn(o0, o1));
+      }
+      s.diff[j * t.max_tasks + tk] = dv;
+    }
+    __syncthreads();
+
+    // ---- P3 (warp 0): per-ECI increments, energy, Metropolis, commit --------
     if (warp == 0) {
       for (int i = lane; i < n_eci; i += 32) {
         double c = s.cf[i];
 #pragma unroll
         for (int j = 0; j < 2; j++) {
           if (!(j ? ch1 : ch0)) continue;
-          const Fin f = s.fin[(j ? g1 : g0) * n_eci + i];
+          const int fi = (j ? g1 : g0) * n_eci + i;
+          const int4 f = s.fin_i[fi];
           const int oid = j ? old1 : old0, nid = j ? new1 : new0;
-          if (f.kind == 1) {                                    // :366-371
-            const double dl = __ddiv_rn(__dsub_rn(s.bf[f.d * S + nid], s.bf[f.d * S + oid]), dN);
+          if (f.x == 1) {                                       // :366-371
+            const double dl = __ddiv_rn(__dsub_rn(s.bf[f.y * S + nid], s.bf[f.y * S + oid]), dN);
             c = __dadd_rn(c, dl);
-          } else if (f.kind == 2) {
+          } else if (f.x == 2) {
+            const double2 fd = s.fin_d[fi];
             double delta = 0.0;
             const double *df = s.diff + j * t.max_tasks;
-            for (int q = f.t0; q < f.t1; q++) delta = __dadd_rn(delta, df[q]);   // :397
-            delta = __dmul_rn(delta, f.scale);                  // :400
-            delta = __ddiv_rn(delta, f.div);                    // :402
+            for (int q = f.z; q < f.w; q++) delta = __dadd_rn(delta, df[q]);     // :397
+            delta = __dmul_rn(delta, fd.x);                     // :400
+            delta = __ddiv_rn(delta, fd.y);                     // :402
             c = __dadd_rn(c, delta);                            // :404
           }                                                     // else: copied (:360,:382)
         }
@@ -432,11 +441,6 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
           if (kCanon) {                        // swap_move_index_tracker.py:39-59
             s.list[slot0] = site1; s.list[slot1] = site0;
             g_loc[site1] = slot0 - s.off[new1]; g_loc[site0] = slot1 - s.off[new0];
-          } else if (MODE == MODE_REPLAY && g_list != nullptr && site1 >= 0 && ch0 && ch1) {
-            const int l1 = g_loc[site0], l2 = g_loc[site1];
-            const int32_t *off = st.off + (size_t)r * (S + 1);
-            s.list[off[old0] + l1] = site1; g_loc[site1] = l1;
-            s.list[off[old1] + l2] = site0; g_loc[site0] = l2;
           }
         }
       }

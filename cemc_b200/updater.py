@@ -127,6 +127,9 @@ class BatchedCEUpdater(object):
     def set_order_mode(self, mode: int):
         _lib.check(self.lib.cemc_set_order_mode(self._h, int(mode)))
 
+    def set_block_threads(self, n: int):
+        _lib.check(self.lib.cemc_set_block_threads(self._h, int(n)))
+
     def get_counters(self):
         steps = np.zeros(self.R, dtype=np.uint64)
         acc = np.zeros(self.R, dtype=np.uint64)

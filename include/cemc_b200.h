@@ -112,6 +112,8 @@ int cemc_destroy(cemc_handle *h);
 int cemc_set_stream(cemc_handle *h, void *stream);
 int cemc_synchronize(cemc_handle *h);
 int cemc_set_order_mode(cemc_handle *h, int mode);
+/* threads per CTA (= per replica): 0 = auto, else a multiple of 32 in [32,256] */
+int cemc_set_block_threads(cemc_handle *h, int n);
 
 /* ---- state ---- */
 int cemc_set_occupancy(cemc_handle *h, const int8_t *occ /*[R][N]*/);

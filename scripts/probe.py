@@ -34,23 +34,28 @@ def timeit(gpu, fn, n, reps=3):
     return best
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c2", "c3"]
+    which = [a for a in sys.argv[1:] if not a.startswith("t=")] or ["c2", "c3"]
+    threads = [int(a[2:]) for a in sys.argv[1:] if a.startswith("t=")] or [0]
     if "c2" in which:
         T = np.linspace(200, 1000, 16); mu = np.linspace(-1.1, -0.9, 16)
         kTs = np.repeat(T * KB, 16); mus = np.tile(mu, 16)
         ft, gpu = setup(10, ["Al", "Mg"], {"Al": 0.5, "Mg": 0.5}, 256, kTs, mus * 0.0)
-        for n in (20000, 100000):
+        for th in threads:
+            gpu.set_block_threads(th)
+            n = 50000
             ms = timeit(gpu, gpu.run_sgc, n)
-            print("C2 sgc binary L=10 R=256 n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
-                n, ms, 256 * n / ms / 1e3, ms * 1e6 / n))
+            print("C2 sgc binary L=10 R=256 threads=%d n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
+                th, n, ms, 256 * n / ms / 1e3, ms * 1e6 / n))
         st, acc = gpu.get_counters(); print("  accept rate", acc.sum() / st.sum())
     if "c3" in which:
         kTs = np.linspace(300, 900, 64) * KB
         ft, gpu = setup(20, ["Al", "Mg", "Si"], {"Al": 0.8, "Mg": 0.1, "Si": 0.1}, 64, kTs)
-        for n in (20000, 100000):
+        for th in threads:
+            gpu.set_block_threads(th)
+            n = 50000
             ms = timeit(gpu, gpu.run_canonical, n)
-            print("C3 canonical ternary L=20 R=64 n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
-                n, ms, 64 * n / ms / 1e3, ms * 1e6 / n))
+            print("C3 canonical ternary L=20 R=64 threads=%d n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
+                th, n, ms, 64 * n / ms / 1e3, ms * 1e6 / n))
+            ms = timeit(gpu, gpu.run_sgc, n)
+            print("C3-lattice sgc ternary threads=%d: %.1f M moves/s (%.0f ns/move/chain)" % (th, 64 * n / ms / 1e3, ms * 1e6 / n))
         st, acc = gpu.get_counters(); print("  accept rate", acc.sum() / st.sum())
-        ms = timeit(gpu, gpu.run_sgc, 20000)
-        print("C3-lattice sgc ternary: %.1f M moves/s (%.0f ns/move/chain)" % (64 * 20000 / ms / 1e3, ms * 1e6 / 20000))

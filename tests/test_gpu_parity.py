@@ -333,3 +333,40 @@ def test_full_size_properties(cuda_device):
         acc_o, e_o = oc.replay(tr[0][1], tr[1][1], tr[2][1])
         assert np.array_equal(acc_o, tr[3][1]) and np.array_equal(e_o, tr[4][1])
         assert np.array_equal(oc.cf, cf_inc[1])
+
+
+def test_tree_order_mode_ternary(cuda_device):
+    """CEMC_ORDER_TREE on a non-integer basis: decisions identical, energies
+    and CFs within 1e-10 relative of the reference-order oracle."""
+    from cemc_b200.updater import ORDER_TREE
+    st, eci, symbols, ft = build(**TERNARY)
+    gpu, chains = make_pair(ft, [symbols] * 3, [0.02, 0.05, 0.09], seed=31)
+    gpu.set_order_mode(ORDER_TREE)
+    n = 2000
+    gpu.set_trace(n)
+    gpu.run_canonical(n)
+    gpu.synchronize()
+    tr = gpu.get_trace(n)
+    for r, c in enumerate(chains):
+        o = c.run_canonical(n, trace=True)
+        assert np.array_equal(tr[3][r], o[3])
+        np.testing.assert_allclose(tr[4][r], o[4], rtol=1e-10, atol=1e-12)
+    cf = gpu.get_cf()
+    occ = gpu.get_occupancy()
+    for r, c in enumerate(chains):
+        assert np.array_equal(occ[r], c.occ)
+        np.testing.assert_allclose(cf[r], c.cf, rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128, 256])
+def test_block_size_invariance(cuda_device, threads):
+    st, eci, symbols, ft = build(**TERNARY)
+    gpu, chains = make_pair(ft, [symbols] * 2, [0.03, 0.06], seed=77)
+    gpu.set_block_threads(threads)
+    gpu.run_canonical(300)
+    gpu.run_sgc(300)
+    gpu.synchronize()
+    for c in chains:
+        c.run_canonical(300)
+        c.run_sgc(300)
+    assert_state_equal(gpu, chains)
