@@ -13,7 +13,7 @@ import subprocess
 from .tables import CemcTablesStruct
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_cemc_b200.so")
+LIB_PATH = os.environ.get("CEMC_B200_LIB") or os.path.join(_HERE, "_cemc_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "cemc_b200.cu"),
            os.path.join(_HERE, "csrc", "cemc_kernels.cuh"),
            os.path.join(os.path.dirname(_HERE), "include", "cemc_b200.h")]
@@ -56,6 +56,9 @@ SIGNATURES = {
     "cemc_synchronize": [_H],
     "cemc_set_order_mode": [_H, C.c_int],
     "cemc_set_block_threads": [_H, C.c_int],
+    "cemc_set_generic_path": [_H, C.c_int],
+    "cemc_debug_phase_cycles": [_H, _u64p],
+    "cemc_selftest_division": [_H, C.c_uint64, C.c_int, C.c_int, _u64p],
     "cemc_set_occupancy": [_H, _i8p],
     "cemc_get_occupancy": [_H, _i8p],
     "cemc_set_cf": [_H, _f64p],

@@ -71,6 +71,7 @@ struct cemc_handle {
   int n_jobs = 0;
   bool integer_bf = false;
   int block_threads = 0;              // 0 = auto
+  bool force_generic = false;         // testing: disable the register-resident P3
 };
 
 // ---------------------------------------------------------------------------
@@ -253,6 +254,8 @@ static int upload_allowed(cemc_handle *h) {
   CU(cudaMemcpy((void *)h->t.allowed, al, 128, cudaMemcpyHostToDevice));
   CU(cudaMemcpy((void *)h->t.allowed_pos, ap, 128, cudaMemcpyHostToDevice));
   h->t.n_allowed = (int)h->allowed.size();
+  h->t.allowed_identity = ((int)h->allowed.size() == h->t.S) ? 1 : 0;
+  for (size_t i = 0; i < h->allowed.size(); i++) if (h->allowed[i] != (int8_t)i) h->t.allowed_identity = 0;
   return 0;
 }
 
@@ -380,8 +383,9 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
           }
           if (kref < 0) return fail("a sub-cluster does not contain the changed site (bad `order`)");
           w |= (unsigned long long)kref << 48;
+          if (slot >= (1 << 14)) return fail("cluster program too large (product slots)");
+          w |= (unsigned long long)slot << 50;
           items.push_back(w);
-          if (slot > 65535) return fail("cluster program too large (product slots)");
           item_slot.push_back((uint16_t)slot++);
         }
       }
@@ -435,6 +439,7 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   if (t.n_active != N) { if ((rc = dupload(h, &t.active, active))) return rc; }
   else t.active = nullptr;
   t.uniform_group = (tb->n_symm == 1 && t.n_active == N) ? 1 : 0;
+  t.prefetch_rows = ((size_t)32 * 2 * K * sizeof(int32_t) <= 24 * 1024) ? 1 : 0;
   {
     int8_t *al = nullptr, *ap = nullptr;
     if ((rc = dalloc(h, &al, 128))) return rc;
@@ -621,6 +626,50 @@ int cemc_get_kT(cemc_handle *h, double *kT) {
   return 0;
 }
 
+int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8) {
+  if (!h || !out8) return fail("null argument");
+#ifdef CEMC_PHASE_TIMING
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpyFromSymbol(out8, g_phase_cycles, 8 * sizeof(uint64_t)));
+  return 0;
+#else
+  return fail("library built without -DCEMC_PHASE_TIMING");
+#endif
+}
+
+int cemc_set_generic_path(cemc_handle *h, int on) {
+  if (!h) return fail("null handle");
+  h->force_generic = on != 0;
+  return 0;
+}
+
+int cemc_selftest_division(cemc_handle *h, uint64_t seed, int n_blocks, int iters, uint64_t *mismatches) {
+  if (!h || !mismatches) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  // denominators the kernels really use: count * N_g of every term, N, and some kT values
+  std::vector<double> dens;
+  std::vector<double2> fd((size_t)h->t.n_symm * h->t.n_eci);
+  CU(cudaMemcpy(fd.data(), h->t.fin_d, fd.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+  for (auto &f : fd) dens.push_back(f.y);
+  dens.push_back((double)h->t.N);
+  for (int k = 1; k <= 16; k++) dens.push_back(8.617330337217213e-05 * 100.0 * k);
+  double *d_dens; unsigned long long *d_bad;
+  CU(cudaMalloc((void **)&d_dens, dens.size() * sizeof(double)));
+  CU(cudaMalloc((void **)&d_bad, sizeof(unsigned long long)));
+  CU(cudaMemcpy(d_dens, dens.data(), dens.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+  exact_div_selftest_kernel<<<n_blocks, 256, 0, h->stream>>>(seed, iters, d_dens, (int)dens.size(), d_bad);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  unsigned long long bad = 0;
+  CU(cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+  cudaFree(d_dens); cudaFree(d_bad);
+  *mismatches = bad;
+  return 0;
+}
+
 int cemc_set_block_threads(cemc_handle *h, int n) {
   if (!h) return fail("null handle");
   if (n != 0 && (n < 32 || n > 256 || n % 32)) return fail("block threads must be 0 (auto) or a multiple of 32 in [32, 256]");
@@ -681,13 +730,21 @@ static int n_threads_for(const cemc_handle *h, int sites_changed) {
   return std::min(256, (items + 31) / 32 * 32);
 }
 
-template <int MODE, bool kSmem, bool kTree>
+template <int MODE, bool kSmem, bool kTree, bool kFast>
 static int launch_one(cemc_handle *h, const ReplicaState &st, const RunArgs &a, int n_rep, int nthr, size_t sm) {
-  CU(cudaFuncSetAttribute(mc_kernel<MODE, kSmem, kTree>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  mc_kernel<MODE, kSmem, kTree><<<n_rep, nthr, sm, h->stream>>>(h->t, st, a, h->acc_stride);
+  CU(cudaFuncSetAttribute(mc_kernel<MODE, kSmem, kTree, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  mc_kernel<MODE, kSmem, kTree, kFast><<<n_rep, nthr, sm, h->stream>>>(h->t, st, a, h->acc_stride);
   h->launches++;
   CU(cudaGetLastError());
   return 0;
+}
+
+template <int MODE, bool kSmem, bool kTree>
+static int launch_fast(cemc_handle *h, const ReplicaState &st, const RunArgs &a, int n_rep, int nthr, size_t sm) {
+  // register-resident CF vector: one lane of warp 0 per ECI
+  const bool fast = h->t.n_eci <= 32 && h->t.uniform_group && !h->force_generic;
+  return fast ? launch_one<MODE, kSmem, kTree, true>(h, st, a, n_rep, nthr, sm)
+              : launch_one<MODE, kSmem, kTree, false>(h, st, a, n_rep, nthr, sm);
 }
 
 template <int MODE>
@@ -707,10 +764,10 @@ static int launch_mc(cemc_handle *h, const RunArgs &a, int first_replica, int n_
     st.kT += r0; st.acc += r0 * h->acc_stride; st.ref += r0; st.step += r0; st.accepted += r0;
     st.list += r0 * h->t.N; st.loc += r0 * h->t.N; st.off += r0 * (h->t.S + 1); st.status += r0;
   }
-  if (in_smem) return tree ? launch_one<MODE, true, true>(h, st, a, n_rep, nthr, sm)
-                           : launch_one<MODE, true, false>(h, st, a, n_rep, nthr, sm);
-  return tree ? launch_one<MODE, false, true>(h, st, a, n_rep, nthr, sm)
-              : launch_one<MODE, false, false>(h, st, a, n_rep, nthr, sm);
+  if (in_smem) return tree ? launch_fast<MODE, true, true>(h, st, a, n_rep, nthr, sm)
+                           : launch_fast<MODE, true, false>(h, st, a, n_rep, nthr, sm);
+  return tree ? launch_fast<MODE, false, true>(h, st, a, n_rep, nthr, sm)
+              : launch_fast<MODE, false, false>(h, st, a, n_rep, nthr, sm);
 }
 
 static int ensure_scratch(cemc_handle *h, long long n_steps) {

@@ -130,6 +130,15 @@ class BatchedCEUpdater(object):
     def set_block_threads(self, n: int):
         _lib.check(self.lib.cemc_set_block_threads(self._h, int(n)))
 
+    def set_generic_path(self, on: bool):
+        _lib.check(self.lib.cemc_set_generic_path(self._h, int(bool(on))))
+
+    def selftest_division(self, seed=1, n_blocks=296, iters=2000) -> int:
+        bad = C.c_uint64(0)
+        _lib.check(self.lib.cemc_selftest_division(
+            self._h, C.c_uint64(seed), int(n_blocks), int(iters), C.byref(bad)))
+        return bad.value
+
     def get_counters(self):
         steps = np.zeros(self.R, dtype=np.uint64)
         acc = np.zeros(self.R, dtype=np.uint64)

@@ -112,6 +112,15 @@ int cemc_destroy(cemc_handle *h);
 int cemc_set_stream(cemc_handle *h, void *stream);
 int cemc_synchronize(cemc_handle *h);
 int cemc_set_order_mode(cemc_handle *h, int mode);
+/* testing hooks: force the generic (shared-memory CF) kernel path; compare the
+ * FMA-based exact division used by the kernels with IEEE division on
+ * n_blocks*256*iters random operand pairs                                    */
+int cemc_set_generic_path(cemc_handle *h, int on);
+/* debug builds (-DCEMC_PHASE_TIMING) only: clock64() cycles warp 0 of replica 0
+ * spent per kernel phase in the last launch                                   */
+int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8);
+int cemc_selftest_division(cemc_handle *h, uint64_t seed, int n_blocks, int iters,
+                           uint64_t *mismatches);
 /* threads per CTA (= per replica): 0 = auto, else a multiple of 32 in [32,256] */
 int cemc_set_block_threads(cemc_handle *h, int n);
 

@@ -1,5 +1,10 @@
 """Summarise an ncu `--page source --print-source cuda,sass --csv` dump per CUDA line."""
 import csv, sys
+def _f(x):
+    try:
+        return float(x)
+    except ValueError:
+        return 0.0
 rows = list(csv.reader(open(sys.argv[1])))
 thresh = float(sys.argv[2]) if len(sys.argv) > 2 else 0.7
 H = None
@@ -12,7 +17,7 @@ for r in rows[start:]:
     if len(r) <= ie or r[0] in ("", "Line No", "File Path", "Function Name"):
         continue
     try:
-        lines.append((int(r[0]), float(r[ie] or 0), float(r[smp] or 0), r[1]))
+        lines.append((int(r[0]), _f(r[ie]), _f(r[smp]), r[1]))
     except ValueError:
         pass
 tot_i = sum(l[1] for l in lines); tot_s = sum(l[2] for l in lines)

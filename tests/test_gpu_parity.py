@@ -370,3 +370,80 @@ def test_block_size_invariance(cuda_device, threads):
         c.run_canonical(300)
         c.run_sgc(300)
     assert_state_equal(gpu, chains)
+
+
+@pytest.mark.parametrize("case", [BINARY, TERNARY])
+def test_generic_path_matches_oracle(cuda_device, case):
+    """The shared-memory CF path (used for > 32 ECIs or several symmetry
+    groups) is forced on a small problem and must equal the oracle too."""
+    st, eci, symbols, ft = build(**case)
+    gpu, chains = make_pair(ft, [symbols] * 2, [0.03, 0.07], seed=13)
+    gpu.set_generic_path(True)
+    gpu.reset_accumulators([2.0, 3.0])
+    for c, ref in zip(chains, [2.0, 3.0]):
+        c.set_ref(ref)
+    gpu.run_sgc(400)
+    gpu.run_canonical(400)
+    gpu.synchronize()
+    for c in chains:
+        c.run_sgc(400)
+        c.run_canonical(400)
+    assert_state_equal(gpu, chains)
+    accs = gpu.get_accumulators()
+    for r, c in enumerate(chains):
+        assert np.array_equal(accs[r], c.acc)
+
+
+def test_many_ecis_generic_path(cuda_device):
+    """> 32 ECIs: ternary with six families (generic kernel path by size)."""
+    st, eci, symbols, ft = build(5, ["Al", "Cu", "Mg", "Si"],
+                                 ["nn", "2nn", "tri", "iso", "tet"],
+                                 {"Al": 0.4, "Cu": 0.2, "Mg": 0.2, "Si": 0.2})
+    assert ft.n_eci > 32 and ft.D == 3
+    gpu, chains = make_pair(ft, [symbols], [0.05], seed=3)
+    gpu.run_canonical(300)
+    gpu.run_sgc(300)
+    gpu.synchronize()
+    chains[0].run_canonical(300)
+    chains[0].run_sgc(300)
+    assert_state_equal(gpu, chains)
+
+
+def test_averager_reference_value(cuda_device):
+    """Averager sums E/ref and E^2/ref (averager.py:21-23) with ref != 1."""
+    st, eci, symbols, ft = build(**TERNARY)
+    gpu, chains = make_pair(ft, [symbols] * 2, [0.03, 0.07], seed=17)
+    refs = gpu.get_energy()
+    gpu.reset_accumulators(refs)
+    for c, ref in zip(chains, refs):
+        c.set_ref(ref)
+    gpu.run_canonical(500)
+    gpu.synchronize()
+    accs = gpu.get_accumulators()
+    for r, c in enumerate(chains):
+        c.run_canonical(500)
+        assert np.array_equal(accs[r], c.acc)
+
+
+def test_exact_division_selftest(cuda_device):
+    """The FMA-based division in the kernels is bit-identical to IEEE division
+    (1.5e8 random operand pairs incl. the kernels' real denominators)."""
+    st, eci, symbols, ft = build(**TERNARY)
+    gpu = BatchedCEUpdater(ft, 1)
+    assert gpu.selftest_division(seed=5, n_blocks=296, iters=2000) == 0
+
+
+def test_sgc_restricted_species(cuda_device):
+    """SGCMonteCarlo(symbols=[...]) restricts the inserted species
+    (sgc_montecarlo.py:38-43,72-74)."""
+    st, eci, symbols, ft = build(**TERNARY)
+    gpu, chains = make_pair(ft, [symbols], [0.05], seed=23)
+    gpu.set_sgc_species([0, 2])
+    gpu.set_trace(500)
+    gpu.run_sgc(500)
+    gpu.synchronize()
+    tr = chains[0].run_sgc(500, allowed=[0, 2], trace=True)
+    sites, news, u, acc, e = gpu.get_trace(500)
+    assert np.array_equal(news[0], tr[1]) and np.array_equal(acc[0], tr[3])
+    assert set(np.unique(news[0][:, 0])) <= {0, 2}
+    assert_state_equal(gpu, chains)
