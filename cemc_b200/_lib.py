@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CEMC_B200_LIB") or os.path.join(_HERE, "_cemc_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "cemc_b200.cu"),
            os.path.join(_HERE, "csrc", "cemc_kernels.cuh"),
+           os.path.join(_HERE, "csrc", "cemc_spin_kernel.cuh"),
            os.path.join(os.path.dirname(_HERE), "include", "cemc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-fmad=false"]

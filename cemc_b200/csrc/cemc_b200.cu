@@ -15,6 +15,7 @@
 
 #include "../../include/cemc_b200.h"
 #include "cemc_kernels.cuh"
+#include "cemc_spin_kernel.cuh"
 
 using namespace cemc;
 
@@ -71,7 +72,9 @@ struct cemc_handle {
   int n_jobs = 0;
   bool integer_bf = false;
   int block_threads = 0;              // 0 = auto
-  bool force_generic = false;         // testing: disable the register-resident P3
+  bool force_generic = false;         // testing: disable the register-resident P3 and the spin kernel
+  bool spin_ok = false;               // binary +-1 basis: warp-per-replica spin kernel usable
+  SpinTables spin{};
 };
 
 // ---------------------------------------------------------------------------
@@ -413,6 +416,45 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
     if (v != std::floor(v) || std::fabs(v) > 1024.0) h->integer_bf = false;
   }
 
+  // ---- binary +-1 basis: tables of the warp-per-replica spin kernel ------------
+  std::vector<uint32_t> sp_items, sp_masks(32 * 4, 0u);
+  std::vector<int32_t> sp_coef(32, 0), sp_msub(32, 1);
+  {
+    bool ok = (S == 2 && D == 1 && tb->n_symm == 1 && n_eci <= 32 &&
+               std::fabs(tb->bf[0]) == 1.0 && tb->bf[1] == -tb->bf[0]);
+    for (int s = 0; s < N && ok; s++) if (tb->symm_of_site[s] != 0) ok = false;
+    const int b0 = ok ? (int)tb->bf[0] : 1;
+    for (int i = 0; i < n_eci && ok; i++) {
+      const int kind = tb->eci_kind[i];
+      if (kind == CEMC_ECI_SINGLET) { sp_coef[i] = 1; sp_msub[i] = 1; continue; }
+      if (kind != CEMC_ECI_CLUSTER) continue;
+      const int fam = tb->term_fam[i];
+      if (fam < 0) continue;                                   // copied
+      if (tb->term_deco_off[i + 1] - tb->term_deco_off[i] != 1) { ok = false; break; }
+      const int n = tb->fam_size[fam], M = tb->fam_nsub[fam];
+      const int32_t *pos = tb->fam_pos + tb->fam_pos_off[fam];
+      sp_coef[i] = n * ((n - 1) % 2 == 0 ? 1 : b0);            // n * b0^(n-1)
+      sp_msub[i] = M;
+      for (int m = 0; m < M; m++) {
+        uint32_t w = 0; int nn = 0;
+        for (int k = 0; k < n; k++) {
+          const int p = pos[m * n + k];
+          if (p == CEMC_POS_REF) continue;
+          w |= (uint32_t)p << (8 * nn++);
+        }
+        for (; nn < 3; nn++) w |= 0xffu << (8 * nn);
+        const int q = (int)sp_items.size();
+        if (q >= 128) { ok = false; break; }
+        sp_masks[i * 4 + q / 32] |= 1u << (q % 32);
+        sp_items.push_back(w);
+      }
+    }
+    h->spin_ok = ok && !sp_items.empty();
+    h->spin.n_items = (int)sp_items.size();
+    h->spin.n_rounds = ((int)sp_items.size() + 31) / 32;
+    h->spin.b0 = b0;
+  }
+
   std::vector<int32_t> trans(tb->trans, tb->trans + (size_t)N * K);
   std::vector<int32_t> symm(tb->symm_of_site, tb->symm_of_site + N);
   std::vector<double> bf(tb->bf, tb->bf + (size_t)D * S);
@@ -436,6 +478,12 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   if ((rc = dupload(h, &t.fin_i, fin_i))) return rc;
   if ((rc = dupload(h, &t.fin_d, fin_d))) return rc;
   if ((rc = dupload(h, &t.singlet_idx, singlet_idx))) return rc;
+  if (h->spin_ok) {
+    if ((rc = dupload(h, &h->spin.items, sp_items))) return rc;
+    if ((rc = dupload(h, &h->spin.masks, sp_masks))) return rc;
+    if ((rc = dupload(h, &h->spin.coef, sp_coef))) return rc;
+    if ((rc = dupload(h, &h->spin.msub, sp_msub))) return rc;
+  }
   if (t.n_active != N) { if ((rc = dupload(h, &t.active, active))) return rc; }
   else t.active = nullptr;
   t.uniform_group = (tb->n_symm == 1 && t.n_active == N) ? 1 : 0;
@@ -770,6 +818,30 @@ static int launch_mc(cemc_handle *h, const RunArgs &a, int first_replica, int n_
               : launch_fast<MODE, false, false>(h, st, a, n_rep, nthr, sm);
 }
 
+template <int MODE, int NR>
+static int launch_spin_nr(cemc_handle *h, const RunArgs &a, size_t sm) {
+  CU(cudaFuncSetAttribute(spin_kernel<MODE, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  spin_kernel<MODE, NR><<<h->R, 32, sm, h->stream>>>(h->spin, h->t, h->st, a, h->acc_stride);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// returns -1 when the spin kernel is not applicable (caller falls back to the generic kernel)
+template <int MODE>
+static int launch_spin(cemc_handle *h, const RunArgs &a) {
+  if (!h->spin_ok || h->force_generic || !h->t.allowed_identity) return -1;
+  const size_t N = (size_t)h->t.N;
+  const size_t sm = 1024 + 4 * (size_t)((h->spin.n_items + 3) & ~3) +
+                    (MODE == MODE_CANONICAL ? 4 * ((N + 3) & ~(size_t)3) : 0) + ((N + 15) & ~(size_t)15);
+  if (sm > (size_t)h->max_smem_optin) return -1;
+  const int nr = h->spin.n_rounds * 1;
+  if (nr <= 1) return launch_spin_nr<MODE, 1>(h, a, sm);
+  if (nr <= 2) return launch_spin_nr<MODE, 2>(h, a, sm);
+  if (nr <= 4) return launch_spin_nr<MODE, 4>(h, a, sm);
+  return -1;
+}
+
 static int ensure_scratch(cemc_handle *h, long long n_steps) {
   if (n_steps <= h->scratch_steps) return 0;
   void *old[] = {h->d_sites, h->d_news, h->d_u, h->d_acc, h->d_e};
@@ -829,7 +901,9 @@ int cemc_run_sgc(cemc_handle *h, int64_t n_steps) {
   CU(cudaSetDevice(h->device));
   drop_trials(h);
   h->tracker_dirty = true;
-  return launch_mc<MODE_SGC>(h, run_args(h, n_steps), 0, h->R);
+  const RunArgs a = run_args(h, n_steps);
+  const int rc = launch_spin<MODE_SGC>(h, a);
+  return rc >= 0 ? rc : launch_mc<MODE_SGC>(h, a, 0, h->R);
 }
 
 int cemc_run_canonical(cemc_handle *h, int64_t n_steps) {
@@ -844,7 +918,9 @@ int cemc_run_canonical(cemc_handle *h, int64_t n_steps) {
     CU(cudaGetLastError());
     h->tracker_dirty = false;
   }
-  return launch_mc<MODE_CANONICAL>(h, run_args(h, n_steps), 0, h->R);
+  const RunArgs a = run_args(h, n_steps);
+  const int rc = launch_spin<MODE_CANONICAL>(h, a);
+  return rc >= 0 ? rc : launch_mc<MODE_CANONICAL>(h, a, 0, h->R);
 }
 
 int cemc_set_trace(cemc_handle *h, int64_t capacity) {

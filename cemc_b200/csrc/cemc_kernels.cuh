@@ -139,13 +139,22 @@ __device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32
 // instead of the ~30-instruction DDIV sequence; tests/test_exact_div.py and the
 // cemc_selftest_division entry point check it against true division.
 __device__ __forceinline__ double exact_div(double a, double b, double y) {
-  if (!(fabs(a) > 1e-250 && fabs(a) < 1e250)) return __ddiv_rn(a, b);   // incl. 0, inf, nan
   const double q0 = __dmul_rn(a, y);
   const double r0 = __fma_rn(-b, q0, a);
   const double q1 = __fma_rn(r0, y, q0);
   const double r1 = __fma_rn(-b, q1, a);
-  return __fma_rn(r1, y, q1);
+  const double q2 = __fma_rn(r1, y, q1);
+  const double m = fabs(a);
+  // zero is returned as is (+-0 / b == +-0); the IEEE routine only for operands
+  // whose intermediate products could leave the normal range (never in practice)
+  if (m != 0.0 && !(m > 1e-250 && m < 1e250)) return __ddiv_rn(a, b);
+  return m == 0.0 ? a : q2;
 }
+
+// Keep a loop-invariant kernel parameter in a register: without this ptxas
+// re-reads it from the constant bank (LDCU) inside the per-move loop, and with one
+// warp per replica that latency is fully exposed.
+__device__ __forceinline__ int pin_reg(int x) { asm volatile("" : "+r"(x)); return x; }
 
 // exp(x) for -60 < x <= 0 to ~3e-6 relative: only used to pre-screen the
 // Metropolis test; borderline cases fall through to the exact expression.
