@@ -73,6 +73,8 @@ SIGNATURES = {
     "cemc_seed": [_H, C.c_uint64],
     "cemc_set_step": [_H, _u64p],
     "cemc_set_sgc_species": [_H, C.c_int, _i8p],
+    "cemc_get_tracker": [_H, _i32p, _i32p],
+    "cemc_set_tracker": [_H, _i32p],
     "cemc_get_counters": [_H, _u64p, _u64p],
     "cemc_reset_counters": [_H],
     "cemc_trial_changes": [_H, C.c_int, C.c_int, _i32p, _i8p, _i8p, _f64p],

@@ -249,6 +249,16 @@ static int dupload(cemc_handle *h, const T **p, const std::vector<T> &v) {
   return 0;
 }
 
+static int ensure_tracker(cemc_handle *h) {
+  if (!h->tracker_dirty) return 0;
+  tracker_init_kernel<<<h->R, 128, 0, h->stream>>>(h->t.N, h->t.S, h->t.symm_of_site, h->st.occ,
+                                                   h->st.list, h->st.loc, h->st.off);
+  h->launches++;
+  CU(cudaGetLastError());
+  h->tracker_dirty = false;
+  return 0;
+}
+
 static int upload_allowed(cemc_handle *h) {
   int8_t al[128], ap[128];
   memset(al, 0, sizeof al);
@@ -911,16 +921,56 @@ int cemc_run_canonical(cemc_handle *h, int64_t n_steps) {
   if (n_steps <= 0) return 0;
   CU(cudaSetDevice(h->device));
   drop_trials(h);
-  if (h->tracker_dirty) {
-    tracker_init_kernel<<<h->R, 128, 0, h->stream>>>(h->t.N, h->t.S, h->t.symm_of_site, h->st.occ,
-                                                     h->st.list, h->st.loc, h->st.off);
-    h->launches++;
-    CU(cudaGetLastError());
-    h->tracker_dirty = false;
-  }
+  { const int rc0 = ensure_tracker(h); if (rc0) return rc0; }
   const RunArgs a = run_args(h, n_steps);
   const int rc = launch_spin<MODE_CANONICAL>(h, a);
   return rc >= 0 ? rc : launch_mc<MODE_CANONICAL>(h, a, 0, h->R);
+}
+
+// Checkpoint support: the per-species site lists of the canonical sampler
+// (SwapMoveIndexTracker.tracker, swap_move_index_tracker.py:8-36) are chain state.
+int cemc_get_tracker(cemc_handle *h, int32_t *list, int32_t *off) {
+  if (!h || !list || !off) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  int rc = ensure_tracker(h);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(list, h->st.list, sizeof(int32_t) * h->R * h->t.N, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(off, h->st.off, sizeof(int32_t) * h->R * (h->t.S + 1), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cemc_set_tracker(cemc_handle *h, const int32_t *list) {
+  if (!h || !list) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  const int N = h->t.N, S = h->t.S;
+  std::vector<int8_t> occ((size_t)h->R * N);
+  CU(cudaMemcpyAsync(occ.data(), h->st.occ, occ.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<int32_t> loc((size_t)h->R * N, -1), off((size_t)h->R * (S + 1), 0);
+  for (int r = 0; r < h->R; r++) {
+    const int8_t *o = &occ[(size_t)r * N];
+    int32_t *of = &off[(size_t)r * (S + 1)];
+    std::vector<int> cnt(S, 0);
+    int n_act = 0;
+    for (int a = 0; a < N; a++) if (h->symm_of_site[a] >= 0) { cnt[o[a]]++; n_act++; }
+    for (int sp = 0; sp < S; sp++) of[sp + 1] = of[sp] + cnt[sp];
+    const int32_t *ls = list + (size_t)r * N;
+    for (int sp = 0; sp < S; sp++)
+      for (int k = of[sp]; k < of[sp + 1]; k++) {
+        const int a = ls[k];
+        if (a < 0 || a >= N || h->symm_of_site[a] < 0 || o[a] != sp || loc[(size_t)r * N + a] != -1)
+          return fail("The atom position tracker does not match the current state");
+        loc[(size_t)r * N + a] = k - of[sp];
+      }
+    (void)n_act;
+  }
+  CU(cudaMemcpyAsync(h->st.list, list, sizeof(int32_t) * h->R * N, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->st.loc, loc.data(), sizeof(int32_t) * h->R * N, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->st.off, off.data(), sizeof(int32_t) * h->R * (S + 1), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->tracker_dirty = false;
+  return 0;
 }
 
 int cemc_set_trace(cemc_handle *h, int64_t capacity) {

@@ -1,0 +1,232 @@
+"""Semi-grand-canonical Monte Carlo -- host-side mirror of the reference's
+``cemc.mcmc.SGCMonteCarlo`` (/root/reference/cemc/mcmc/sgc_montecarlo.py:12-471).
+
+Trial move (:62-76) = flip one site to another species; the chemical
+potentials are folded into the singlet ECIs (:239-261); the SGCObserver sums
+(:46, mc_observers.py:222-270) are accumulated inside the CUDA kernel every
+step.
+"""
+import numpy as np
+
+from . import montecarlo as mc
+from .mc_observers import SGCObserver
+from .montecarlo import KB
+
+
+class InvalidChemicalPotentialError(Exception):
+    pass
+
+
+class SGCMonteCarlo(mc.Montecarlo):
+    def __init__(self, atoms, temp, indeces=None, symbols=None, logfile="",
+                 plot_debug=False, min_acc_rate=0.0, recycle_waste=False, seed=None):
+        mc.Montecarlo.__init__(self, atoms, temp, indeces=indeces, logfile=logfile,
+                               plot_debug=plot_debug, min_acc_rate=min_acc_rate,
+                               recycle_waste=recycle_waste, seed=seed)
+        if symbols is not None:
+            self.symbols = list(symbols)          # :38-40
+        if len(self.symbols) <= 1:
+            raise ValueError("At least 2 symbols have to be specified")
+        self.sgc_symbols = list(self.symbols)
+        sid = self._tables.species_id
+        for s in self.symbols:
+            if s not in sid:
+                raise ValueError("Unknown symbol {}".format(s))
+        self._gpu.set_sgc_species([sid[s] for s in self.symbols])
+        self.averager = SGCObserver(self.atoms.get_calculator(), self,
+                                    len(self._tables.singlet_indices))
+        self.averager.device_backed = True
+        self.chem_pots = []
+        self.chem_pot_names = []
+        self.has_attached_avg = False
+        self.name = "SGCMonteCarlo"
+        self._chemical_potential = None
+        self.chem_pot_in_ecis = False
+        self.composition_correlation_time = np.zeros(len(self.symbols) - 1)
+        self.current_singlets = None
+        self.attach(self.averager)
+
+    def _check_symbols(self):
+        pass                                          # :78-82
+
+    def _device_run(self, n):
+        self._gpu.run_sgc(n)
+
+    def _pull_averages(self):
+        acc = mc.Montecarlo._pull_averages(self)
+        self.averager.load_device_sums(acc)
+        return acc
+
+    def _on_window_done(self):
+        pass
+
+    def reset(self):
+        super(SGCMonteCarlo, self).reset()
+        self.averager.reset()
+        # SGCObserver's Averagers have their own reference value
+        # (mc_observers.py:207-208); the device keeps one per replica
+        self._gpu.reset_accumulators([self.averager.energy.ref_value])
+
+    def _pull_for_stats(self):
+        self._pull_averages()
+
+    # ---- variances / equilibrium of the composition (:86-221) --------------------
+    def _get_var_average_singlets(self):
+        N = self.averager.counter
+        singlets = self.averager.quantities["singlets"] / N
+        singlets_sq = self.averager.quantities["singlets_sq"] / N
+        var_n = singlets_sq - singlets ** 2
+        nproc = 1
+        no_corr_info = self.correlation_info is None
+        corr_time_found = (not no_corr_info) and self.correlation_info["correlation_time_found"]
+        if no_corr_info or not corr_time_found:
+            return var_n / (N * nproc)
+        if not np.all(var_n > 0.0):
+            var_n = np.abs(var_n)
+        tau = self.correlation_info["correlation_time"]
+        if tau < 1.0:
+            tau = 1.0
+        return 2.0 * var_n * tau / (N * nproc)
+
+    def _composition_reached_equillibrium(self, prev_composition, var_prev,
+                                          confidence_level=0.05):
+        min_percentile = mc._norm_ppf(confidence_level)
+        max_percentile = mc._norm_ppf(1.0 - confidence_level)
+        N = self.averager.counter
+        singlets = self.averager.singlets / N
+        var_n = self._get_var_average_singlets()
+        if len(prev_composition) != len(singlets):
+            return False, singlets, var_n, 0.0
+        var_n[var_n < 0.0] = 0.0
+        diff = singlets - prev_composition
+        var_diff = var_n + var_prev
+        if len(var_diff[var_diff > 0.0]) == 0:
+            return True, singlets, var_n, 0.0
+        z = np.abs(diff[var_diff > 0.0]) / np.sqrt(var_diff[var_diff > 0.0])
+        z = np.max(z)
+        converged = bool(min_percentile < z < max_percentile)
+        return converged, singlets, var_n, z
+
+    def _has_converged_prec_mode(self, prec=0.01, confidence_level=0.05,
+                                 log_status=False):
+        percentile = mc._norm_ppf(1.0 - confidence_level)
+        var_n = self._get_var_average_singlets()
+        return bool(np.max(var_n) < (prec / percentile) ** 2)
+
+    # ---- chemical potential (:219-278) ----------------------------------------------
+    @property
+    def chemical_potential(self):
+        return self._chemical_potential
+
+    @chemical_potential.setter
+    def chemical_potential(self, chem_pot):
+        eci = self.atoms.get_calculator().eci
+        if any([k not in eci.keys() for k in chem_pot.keys()]):
+            raise InvalidChemicalPotentialError(
+                "A chemical potential that is currently not tracked is added. "
+                "Make sure that all the following keys are in the ECI before "
+                "the ECI are passed to the calculator: {} (if not add them "
+                "with a zero value)".format(list(chem_pot.keys())))
+        self._chemical_potential = chem_pot
+        if self.chem_pot_in_ecis:
+            self._reset_eci_to_original(self.atoms.get_calculator().eci)
+        self._include_chemical_potential_in_ecis(chem_pot, self.atoms.get_calculator().eci)
+
+    def _include_chemical_potential_in_ecis(self, chem_potential, eci):
+        self.chem_pots = []
+        self.chem_pot_names = []
+        keys = sorted(chem_potential.keys())
+        for key in keys:
+            self.chem_pots.append(chem_potential[key])
+            self.chem_pot_names.append(key)
+            eci[key] = eci.get(key, 0.0) - chem_potential[key]
+        self.atoms.get_calculator().update_ecis(eci)
+        self.chem_pot_in_ecis = True
+        self.current_energy = self.atoms.get_calculator().get_energy()
+        return eci
+
+    def _reset_eci_to_original(self, eci_with_chem_pot):
+        for name, val in zip(self.chem_pot_names, self.chem_pots):
+            eci_with_chem_pot[name] += val
+        self.atoms.get_calculator().update_ecis(eci_with_chem_pot)
+        self.chem_pot_in_ecis = False
+        self.current_energy = self.atoms.get_calculator().get_energy()
+        return eci_with_chem_pot
+
+    def reset_ecis(self):
+        if self.chem_pot_in_ecis:
+            self._reset_eci_to_original(self.atoms.get_calculator().eci)
+
+    def _equillibriate(self, *args, **kwargs):
+        self._in_equil = True
+        try:
+            return mc.Montecarlo._equillibriate(self, *args, **kwargs)
+        finally:
+            self._in_equil = False
+
+    def runMC(self, mode="fixed", steps=10, verbose=False, chem_potential=None,
+              equil=True, equil_params={}, prec_confidence=0.05, prec=0.01):
+        """Run SGC Monte Carlo (sgc_montecarlo.py:336-378)."""
+        if chem_potential is None and self.chemical_potential is None:
+            ex_chem_pot = {"c1_1": -0.1, "c1_2": 0.05}
+            raise ValueError("No chemicalpotentials given. Has to be "
+                             "dictionary of the form {}".format(ex_chem_pot))
+        if chem_potential is not None:
+            self.chemical_potential = chem_potential
+        self.reset()
+        self._gpu.set_kT([self.T * KB])
+        if equil:
+            res = self._estimate_correlation_time(restart=True)
+            if not res["correlation_time_found"]:
+                res["correlation_time_found"] = True
+                res["correlation_time"] = 1000
+            self._equillibriate(**equil_params)
+        self.reset()
+        mc.Montecarlo.runMC(self, steps=steps, verbose=verbose, equil=False, mode=mode,
+                            prec_confidence=prec_confidence, prec=prec)
+        self._pull_averages()
+
+    def singlet2composition(self, avg_singlets):
+        bf = self.atoms.get_calculator().BC.basis_functions
+        matrix = np.zeros((len(self.symbols), len(self.symbols)))
+        index = {s: i for i, s in enumerate(self.symbols)}
+        for i, b in enumerate(bf):
+            for s, col in index.items():
+                matrix[i, col] = b[s]
+        matrix[-1, :] = 1.0
+        rhs = np.zeros(len(self.symbols))
+        rhs[:-1] = avg_singlets
+        rhs[-1] = 1.0
+        x = np.linalg.solve(matrix, rhs)
+        return {s + "_conc": x[i] for s, i in index.items()}
+
+    def get_thermodynamic(self, reset_ecis=True):
+        """Thermodynamic quantities (sgc_montecarlo.py:398-448)."""
+        N = self.averager.counter
+        quantities = {}
+        singlets = self.averager.singlets / N
+        singlets_sq = self.averager.quantities["singlets_sq"] / N
+        quantities["sgc_energy"] = self.averager.energy.mean + self.energy_bias
+        quantities["sgc_heat_capacity"] = self.averager.energy_sq.mean - \
+            self.averager.energy.mean ** 2
+        quantities["sgc_heat_capacity"] /= (KB * self.T ** 2)
+        quantities["energy"] = self.averager.energy.mean + self.energy_bias
+        natoms = len(self.atoms)
+        for i in range(len(self.chem_pots)):
+            quantities["energy"] += self.chem_pots[i] * singlets[i] * natoms
+        quantities["temperature"] = self.T
+        quantities["n_mc_steps"] = self.averager.counter
+        for i in range(len(singlets)):
+            quantities["singlet_{}".format(self.chem_pot_names[i])] = singlets[i]
+            quantities["var_singlet_{}".format(self.chem_pot_names[i])] = \
+                singlets_sq[i] - singlets[i] ** 2
+            quantities["mu_{}".format(self.chem_pot_names[i])] = self.chem_pots[i]
+        quantities.update(self.meta_info)
+        try:
+            quantities.update(self.singlet2composition(singlets))
+        except Exception as exc:           # same behaviour as the reference (:440-444)
+            print("Could not find average singlets!")
+            print(exc)
+        if reset_ecis:
+            self._reset_eci_to_original(self.atoms.get_calculator().eci)
+        return quantities

@@ -130,6 +130,17 @@ class BatchedCEUpdater(object):
     def set_block_threads(self, n: int):
         _lib.check(self.lib.cemc_set_block_threads(self._h, int(n)))
 
+    def get_tracker(self):
+        lst = np.zeros((self.R, self.N), dtype=np.int32)
+        off = np.zeros((self.R, self.tables.S + 1), dtype=np.int32)
+        _lib.check(self.lib.cemc_get_tracker(self._h, _p(lst, C.c_int32),
+                                             _p(off, C.c_int32)))
+        return lst, off
+
+    def set_tracker(self, lst):
+        lst = np.ascontiguousarray(lst, dtype=np.int32).reshape(self.R, self.N)
+        _lib.check(self.lib.cemc_set_tracker(self._h, _p(lst, C.c_int32)))
+
     def set_generic_path(self, on: bool):
         _lib.check(self.lib.cemc_set_generic_path(self._h, int(bool(on))))
 
@@ -266,7 +277,12 @@ class PyCEUpdater(object):
         self.tables = FlatTables(bc, eci, symbols)
         self.batch = BatchedCEUpdater(self.tables, 1, device=device)
         self.batch.set_occupancy(self.tables.occupancy(symbols)[None, :])
-        self.batch.set_cf(self.tables.cf_vector(corr_func)[None, :])
+        if corr_func is None:
+            # from the definition, on the GPU (the reference needs
+            # ase.clease.CorrFunction for this, ce_calculator.py:169-175)
+            self.batch.recompute_cf()
+        else:
+            self.batch.set_cf(self.tables.cf_vector(corr_func)[None, :])
         self._log = []          # (index, old_symbol) since clear_history
 
     # -- reference names ---------------------------------------------------

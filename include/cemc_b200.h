@@ -144,6 +144,10 @@ int cemc_set_step(cemc_handle *h, const uint64_t *steps /*[R]*/);
 /* species ids the SGC sampler may insert (SGCMonteCarlo(symbols=...),
  * sgc_montecarlo.py:38-43); default: all species                            */
 int cemc_set_sgc_species(cemc_handle *h, int n_allowed, const int8_t *allowed);
+/* checkpointing of the canonical sampler: per-species site lists, species-major
+ * ([R][N]; species s occupies [off[s], off[s+1]) of a replica's row)           */
+int cemc_get_tracker(cemc_handle *h, int32_t *list /*[R][N]*/, int32_t *off /*[R][S+1]*/);
+int cemc_set_tracker(cemc_handle *h, const int32_t *list /*[R][N]*/);
 int cemc_get_counters(cemc_handle *h, uint64_t *steps /*[R]*/, uint64_t *accepted /*[R]*/);
 int cemc_reset_counters(cemc_handle *h);
 
