@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("CEMC_B200_LIB") or os.path.join(_HERE, "_cemc_b200.so
 SOURCES = [os.path.join(_HERE, "csrc", "cemc_b200.cu"),
            os.path.join(_HERE, "csrc", "cemc_kernels.cuh"),
            os.path.join(_HERE, "csrc", "cemc_spin_kernel.cuh"),
+           os.path.join(_HERE, "csrc", "cemc_batch_kernel.cuh"),
            os.path.join(os.path.dirname(_HERE), "include", "cemc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-fmad=false"]
@@ -58,6 +59,7 @@ SIGNATURES = {
     "cemc_set_order_mode": [_H, C.c_int],
     "cemc_set_block_threads": [_H, C.c_int],
     "cemc_set_generic_path": [_H, C.c_int],
+    "cemc_set_batch": [_H, C.c_int],
     "cemc_debug_phase_cycles": [_H, _u64p],
     "cemc_selftest_division": [_H, C.c_uint64, C.c_int, C.c_int, _u64p],
     "cemc_set_occupancy": [_H, _i8p],

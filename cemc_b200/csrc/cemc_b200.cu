@@ -16,6 +16,7 @@
 #include "../../include/cemc_b200.h"
 #include "cemc_kernels.cuh"
 #include "cemc_spin_kernel.cuh"
+#include "cemc_batch_kernel.cuh"
 
 using namespace cemc;
 
@@ -73,6 +74,7 @@ struct cemc_handle {
   bool integer_bf = false;
   int block_threads = 0;              // 0 = auto
   bool force_generic = false;         // testing: disable the register-resident P3 and the spin kernel
+  int batch = 0;                      // moves evaluated speculatively per batch (0 = auto)
   bool spin_ok = false;               // binary +-1 basis: warp-per-replica spin kernel usable
   SpinTables spin{};
 };
@@ -689,11 +691,18 @@ int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8) {
 #ifdef CEMC_PHASE_TIMING
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaMemcpyFromSymbol(out8, g_phase_cycles, 8 * sizeof(uint64_t)));
+  CU(cudaMemcpyFromSymbol(out8, g_phase_cycles, 16 * sizeof(uint64_t)));
   return 0;
 #else
   return fail("library built without -DCEMC_PHASE_TIMING");
 #endif
+}
+
+int cemc_set_batch(cemc_handle *h, int b) {
+  if (!h) return fail("null handle");
+  if (!(b == -1 || b == 0 || b == 4 || b == 8 || b == 16)) return fail("batch must be -1 (off), 0 (auto), 4, 8 or 16");
+  h->batch = b;
+  return 0;
 }
 
 int cemc_set_generic_path(cemc_handle *h, int on) {
@@ -852,6 +861,31 @@ static int launch_spin(cemc_handle *h, const RunArgs &a) {
   return -1;
 }
 
+template <int MODE, bool kTree, int B>
+static int launch_batch_b(cemc_handle *h, const RunArgs &a) {
+  const size_t sm = batch_smem_layout<B>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL);
+  if (sm > (size_t)h->max_smem_optin) return -1;
+  CU(cudaFuncSetAttribute(batch_kernel<MODE, kTree, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  batch_kernel<MODE, kTree, B><<<h->R, B * 32, sm, h->stream>>>(h->t, h->st, a, h->acc_stride);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// speculative batch kernel; -1 when not applicable (caller falls back to mc_kernel)
+template <int MODE>
+static int launch_batch(cemc_handle *h, const RunArgs &a) {
+  if (h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
+      2 * h->t.KP > 64) return -1;
+  const bool tree = (h->order_mode == CEMC_ORDER_TREE) || h->integer_bf;
+  const int B = h->batch > 0 ? h->batch : 16;
+  int rc = -1;
+  if (B >= 16) rc = tree ? launch_batch_b<MODE, true, 16>(h, a) : launch_batch_b<MODE, false, 16>(h, a);
+  if (rc == -1 && B >= 8) rc = tree ? launch_batch_b<MODE, true, 8>(h, a) : launch_batch_b<MODE, false, 8>(h, a);
+  if (rc == -1) rc = tree ? launch_batch_b<MODE, true, 4>(h, a) : launch_batch_b<MODE, false, 4>(h, a);
+  return rc;
+}
+
 static int ensure_scratch(cemc_handle *h, long long n_steps) {
   if (n_steps <= h->scratch_steps) return 0;
   void *old[] = {h->d_sites, h->d_news, h->d_u, h->d_acc, h->d_e};
@@ -912,7 +946,8 @@ int cemc_run_sgc(cemc_handle *h, int64_t n_steps) {
   drop_trials(h);
   h->tracker_dirty = true;
   const RunArgs a = run_args(h, n_steps);
-  const int rc = launch_spin<MODE_SGC>(h, a);
+  int rc = launch_spin<MODE_SGC>(h, a);
+  if (rc == -1) rc = launch_batch<MODE_SGC>(h, a);
   return rc >= 0 ? rc : launch_mc<MODE_SGC>(h, a, 0, h->R);
 }
 
@@ -923,7 +958,8 @@ int cemc_run_canonical(cemc_handle *h, int64_t n_steps) {
   drop_trials(h);
   { const int rc0 = ensure_tracker(h); if (rc0) return rc0; }
   const RunArgs a = run_args(h, n_steps);
-  const int rc = launch_spin<MODE_CANONICAL>(h, a);
+  int rc = launch_spin<MODE_CANONICAL>(h, a);
+  if (rc == -1) rc = launch_batch<MODE_CANONICAL>(h, a);
   return rc >= 0 ? rc : launch_mc<MODE_CANONICAL>(h, a, 0, h->R);
 }
 

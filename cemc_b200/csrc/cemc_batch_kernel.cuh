@@ -1,0 +1,465 @@
+// cemc_batch_kernel.cuh -- speculative batch evaluation of one Markov chain.
+//
+// A single chain is a dependent sequence of trial moves, so with few replicas
+// (64 on 148 SMs) a B200 is latency bound: every cycle of one move's evaluation
+// is exposed.  This kernel keeps the chain EXACTLY sequential but takes the
+// expensive part off the critical path:
+//
+//   * B warps of a CTA evaluate the CF increments of the next B trial moves
+//     concurrently, one WARP per move, all against the current state (phases
+//     P0-P2b of cemc_kernels.cuh plus the per-ECI quotients; warp-level syncs only);
+//   * warp 0 then decides the moves IN ORDER (per-ECI normalisation, ordered
+//     energy dot product, Metropolis test, commit).  A move whose inputs were
+//     touched by an earlier accepted move of the same batch -- one of its
+//     gathered sites (or, for swaps, one of its list slots) changed -- is not
+//     decided: the batch ends there and the next batch re-evaluates it from the
+//     committed state.  The Philox stream is keyed by the step index, so the
+//     restart changes nothing.
+//
+// Results are bit-identical to the one-move-at-a-time kernels (tested): the
+// arithmetic of each phase is the same code path, operation for operation.
+// Used when the CF vector fits one warp (<= 32 ECIs), one symmetry group, state
+// in shared memory; everything else runs mc_kernel.
+#pragma once
+#include "cemc_kernels.cuh"
+
+namespace cemc {
+
+struct BatchSmem {
+  double *V, *PO, *PN, *diff, *sq, *bf;
+  unsigned long long *items;
+  int2 *task_sum;
+  uint4 *ring;              // [32][2]: proposal; uniform + Metropolis threshold
+  int32_t *prop;            // [B][8] decoded proposal
+  int32_t *cmask;           // [B] bit k: move b reads a site that move k changes
+  int32_t *ctl;             // control words
+  int32_t *list;
+  int8_t *occ;
+};
+
+template <int B>
+__host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char *base,
+                                                    const DeviceTables &t, bool canonical) {
+  size_t o = 0;
+#define CEMC_TAKE(field, type, count)                                   \
+  do {                                                                  \
+    o = align_up(o, sizeof(type) < 16 ? sizeof(type) : 16);             \
+    if (s) s->field = reinterpret_cast<type *>(base + o);               \
+    o += sizeof(type) * at_least_1((int)(count));                       \
+  } while (0)
+  const int nj = canonical ? 2 : 1;
+  CEMC_TAKE(V, double, B * nj * t.VS);
+  CEMC_TAKE(PO, double, B * nj * t.max_slots);
+  CEMC_TAKE(PN, double, B * nj * t.max_slots);
+  CEMC_TAKE(diff, double, B * nj * t.max_tasks);
+  CEMC_TAKE(sq, double, B * 2 * 32);
+  CEMC_TAKE(bf, double, t.D * t.S);
+  CEMC_TAKE(items, unsigned long long, t.n_items_total);
+  CEMC_TAKE(task_sum, int2, t.n_tasks_total);
+  CEMC_TAKE(ring, uint4, 32 * 2);
+  CEMC_TAKE(prop, int32_t, B * 8);
+  CEMC_TAKE(cmask, int32_t, B);
+  CEMC_TAKE(ctl, int32_t, 8);
+  if (canonical) CEMC_TAKE(list, int32_t, t.N);
+  o = align_up(o, 16);
+  if (s) s->occ = reinterpret_cast<int8_t *>(base + o);
+  o += align_up((size_t)t.N, 16);
+#undef CEMC_TAKE
+  return align_up(o, 16);
+}
+
+// offs[sp] for a runtime sp without spilling the 9-entry array to local memory
+__device__ __forceinline__ int offs_of(const int (&offs)[9], int sp) {
+  int v = 0;
+#pragma unroll
+  for (int q = 0; q < 9; q++) if (q == sp) v = offs[q];
+  return v;
+}
+
+// One WARP evaluates one trial move; B warps = B moves per batch.
+template <int MODE, bool kTree, int B>
+__global__ void __launch_bounds__(B * 32, 1)
+batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool kCanon = (MODE == MODE_CANONICAL);
+  constexpr int NJ = kCanon ? 2 : 1;
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, nthr = B * 32;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int N = t.N, K = t.K, KP = t.KP, S = t.S, D = t.D, VS = t.VS, n_eci = t.n_eci;
+  const int RB = D * KP;
+  const int max_slots = t.max_slots, max_tasks = t.max_tasks;
+  const int n_items = t.item_base[1] - t.item_base[0];
+  const int n_tasks = t.task_base[1] - t.task_base[0];
+
+  int8_t *g_occ = st.occ + (size_t)r * N;
+  int32_t *g_list = st.list + (size_t)r * N;
+  int32_t *g_loc = st.loc + (size_t)r * N;
+  BatchSmem s;
+  batch_smem_layout<B>(&s, smem_raw, t, kCanon);
+
+  // ---- stage ----------------------------------------------------------------
+  for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
+  for (int i = tid; i < t.n_items_total; i += nthr) s.items[i] = t.items[i];
+  for (int i = tid; i < t.n_tasks_total; i += nthr) s.task_sum[i] = t.task_sum[i];
+  for (int i = tid; i < B * NJ * VS; i += nthr) s.V[i] = 1.0;      // V[K] is the constant 1.0
+  for (int i = tid; i < N; i += nthr) s.occ[i] = g_occ[i];
+  if (kCanon) for (int i = tid; i < N; i += nthr) s.list[i] = g_list[i];
+  // canonical: species present and their list ranges (constant during a launch)
+  int n_present = 0, present[8], offs[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) offs[q] = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) present[q] = 0;
+  if (kCanon) {
+#pragma unroll
+    for (int sp = 0; sp < 9; sp++) if (sp <= S) offs[sp] = st.off[(size_t)r * (S + 1) + sp];
+#pragma unroll
+    for (int sp = 0; sp < 8; sp++)
+      if (sp < S && offs[sp + 1] > offs[sp]) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (q == n_present) present[q] = sp;
+        n_present++;
+      }
+    if (n_present < 2) {                       // TooFewElementsError, montecarlo.py:310
+      if (tid == 0) st.status[r] = 2;
+      return;
+    }
+  }
+  __syncthreads();
+
+  // ---- lane i owns ECI i (every warp: per-ECI quotients; warp 0: CF vector) -------
+  const double dN = (double)(unsigned)N;
+  int f_kind = 0, f_d = 0, f_t0 = 0, f_nd = 0, my_singlet = -1;
+  double f_scale = 0.0, f_den = 1.0, f_rden = 1.0, eci_reg = 0.0, cf_reg = 0.0;
+  double aE0 = 0.0, aE1 = 0.0, aE2 = 0.0, aS0 = 0.0, aS1 = 0.0, aS2 = 0.0;
+  if (lane < n_eci) {
+    const int4 f = t.fin_i[lane];
+    f_kind = f.x; f_d = f.y; f_t0 = f.z; f_nd = f.w - f.z;
+    const double2 fd = t.fin_d[lane];
+    f_scale = fd.x;
+    f_den = (f_kind == 1) ? dN : fd.y;
+    f_rden = __ddiv_rn(1.0, f_den);
+    eci_reg = st.eci[(size_t)r * n_eci + lane];
+    cf_reg = st.cf[(size_t)r * n_eci + lane];
+    for (int d = 0; d < t.n_singlets; d++) if (t.singlet_idx[d] == lane) my_singlet = d;
+  }
+  if (warp == 0) {
+    const double *ag = st.acc + (size_t)r * acc_stride;
+    if (my_singlet >= 0) { aS0 = ag[3 + 3 * my_singlet]; aS1 = ag[4 + 3 * my_singlet]; aS2 = ag[5 + 3 * my_singlet]; }
+    aE0 = ag[0]; aE1 = ag[1]; aE2 = ag[2];
+  }
+  double e_cur = st.e_cur[r];
+  const double kT = st.kT[r];
+  const double rkT = __ddiv_rn(1.0, kT);
+  const double ref = st.ref[r];
+  const double rref = __ddiv_rn(1.0, ref);
+  const bool ref_is_one = (ref == 1.0);
+  const unsigned long long step0 = st.step[r];
+  unsigned long long n_acc = 0;
+  const uint32_t rep_global = a.replica_offset + (uint32_t)r;
+  const int n_eci4 = pin_reg((n_eci + 3) & ~3);
+  const int observe = pin_reg(a.observe);
+  const bool tracing = (a.tr_acc != nullptr) || (a.tr_e != nullptr);
+  const int n_allowed = t.n_allowed;
+
+#ifdef CEMC_PHASE_TIMING
+  unsigned long long tph[16] = {0};
+  long long tlast = clock64();
+#endif
+  long long sdone = 0;                 // moves decided so far
+  long long rbase = -(1LL << 40);      // first step held by the ring
+
+  while (sdone < a.n_steps) {
+    const int nb = (int)((a.n_steps - sdone) < B ? (a.n_steps - sdone) : B);
+    // ---- ring refill: proposals of steps [rbase, rbase + 32) ---------------------
+    if (sdone + nb > rbase + 32) {
+      rbase = sdone;
+      if (warp == 0) {
+        const unsigned long long stp = step0 + (unsigned long long)rbase + lane;
+        uint32_t c0 = (uint32_t)stp, c1 = (uint32_t)(stp >> 32), c2 = rep_global, c3 = 0;
+        philox4x32_10(c0, c1, c2, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        uint4 rec0;
+        double u;
+        if (!kCanon) {
+          const uint32_t ia = __umulhi(c0, (uint32_t)t.n_active);       // sgc_montecarlo.py:69
+          rec0 = make_uint4(ia, c1, 0u, 0u);
+          u = u53(c2, c3);
+        } else {                                                         // montecarlo.py:899-907
+          uint32_t d0 = (uint32_t)stp, d1 = (uint32_t)(stp >> 32), d2 = rep_global, d3 = 1;
+          philox4x32_10(d0, d1, d2, d3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+          const int ia = (int)__umulhi(c0, (uint32_t)n_present);
+          int ib = (int)__umulhi(c1, (uint32_t)(n_present - 1)); ib += (ib >= ia);
+          int sa = 0, sb = 0;
+#pragma unroll
+          for (int q = 0; q < 8; q++) { if (q == ia) sa = present[q]; if (q == ib) sb = present[q]; }
+          const int oa0 = offs_of(offs, sa), oa1 = offs_of(offs, sa + 1);
+          const int ob0 = offs_of(offs, sb), ob1 = offs_of(offs, sb + 1);
+          const int slot0 = oa0 + (int)__umulhi(c2, (uint32_t)(oa1 - oa0));
+          const int slot1 = ob0 + (int)__umulhi(c3, (uint32_t)(ob1 - ob0));
+          rec0 = make_uint4((uint32_t)slot0, (uint32_t)slot1, (uint32_t)sb, (uint32_t)sa);
+          u = u53(d0, d1);
+        }
+        // Metropolis threshold: u <= exp(-dE/kT)  <=>  dE <= -kT ln u   (screen only)
+        const double L = -kT * log(u);
+        s.ring[lane * 2] = rec0;
+        s.ring[lane * 2 + 1] = make_uint4((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u),
+                                          (uint32_t)__double2loint(L), (uint32_t)__double2hiint(L));
+      }
+      __syncthreads();
+    }
+    CEMC_TICK(0);
+
+    // ---- E1: warp b evaluates move sdone + b against the current state --------------
+    int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check); host: NJ*KP <= 64
+    if (warp < nb) {
+      const int b = warp;
+      const uint4 rec0 = s.ring[(int)(sdone + b - rbase) * 2];
+      int site0, site1 = -1, new0, new1 = 0, old0, old1 = 0, slot0 = -1, slot1 = -1;
+      if (!kCanon) {
+        site0 = t.active ? t.active[rec0.x] : (int)rec0.x;
+        old0 = s.occ[site0];
+        if (t.allowed_identity) {                       // sgc_montecarlo.py:70-75
+          int rr = (int)__umulhi(rec0.y, (uint32_t)(S - 1)); rr += (rr >= old0);
+          new0 = rr;
+        } else {
+          const int p = t.allowed_pos[old0];
+          int rr;
+          if (p >= 0) { rr = (int)__umulhi(rec0.y, (uint32_t)(n_allowed - 1)); rr += (rr >= p); }
+          else rr = (int)__umulhi(rec0.y, (uint32_t)n_allowed);
+          new0 = t.allowed[rr];
+        }
+      } else {
+        slot0 = (int)rec0.x; slot1 = (int)rec0.y; new0 = (int)rec0.z; new1 = (int)rec0.w;
+        site0 = s.list[slot0]; site1 = s.list[slot1];
+        old0 = new1; old1 = new0;
+      }
+      double *Vb = s.V + b * NJ * VS;
+      if (lane == 0) {
+        int32_t *pp = s.prop + b * 8;
+        *reinterpret_cast<int4 *>(pp) = make_int4(site0, site1, new0, new1);
+        *reinterpret_cast<int4 *>(pp + 4) = make_int4(old0, old1, slot0, slot1);
+      }
+      // P1: gather
+#pragma unroll
+      for (int x = 0; x < 2; x++) {
+        const int q = lane + 32 * x;
+        if (q < NJ * KP) {
+          const int j = q >= KP, c = j ? q - KP : q;
+          double *Vj = Vb + j * VS;
+          const int sj = j ? site1 : site0;
+          if (c < K) {
+            const int nbs = __ldg(&t.trans[(size_t)sj * K + c]);        // :264
+            gsx[x] = nbs;
+            int v = s.occ[nbs];
+            if (j && nbs == site0) v = new0;    // change 1 sees change 0 applied (:845-852)
+            for (int d = 0; d < D; d++) Vj[d * KP + c] = s.bf[d * S + v];
+          } else {
+            gsx[x] = sj;
+            const int oid = j ? old1 : old0, nid = j ? new1 : new0;
+            for (int d = 0; d < D; d++) {
+              Vj[RB + d] = s.bf[d * S + oid];
+              Vj[RB + D + d] = s.bf[d * S + nid];
+            }
+          }
+        }
+      }
+      __syncwarp();
+      // P2a: products
+      double *POb = s.PO + b * NJ * max_slots, *PNb = s.PN + b * NJ * max_slots;
+      for (int q = lane; q < NJ * n_items; q += 32) {
+        const int j = q >= n_items;
+        const unsigned long long w = s.items[j ? q - n_items : q];
+        const double *Vj = Vb + j * VS;
+        const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+        const int i0 = lo & CEMC_ITEM_MASK, i1 = (lo >> 12) & CEMC_ITEM_MASK;
+        const int i2 = (uint32_t)(w >> 24) & CEMC_ITEM_MASK, i3 = (hi >> 4) & CEMC_ITEM_MASK;
+        const int kref = (hi >> 16) & 3;
+        const int slot = (int)(hi >> 18) + j * max_slots;
+        const double f0 = Vj[i0], f1 = Vj[i1], f2 = Vj[i2], f3 = Vj[i3];
+        const int iref = kref == 0 ? i0 : kref == 1 ? i1 : kref == 2 ? i2 : i3;
+        const double fr = Vj[iref + D];
+        const double tO = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), f2), f3);      // :271-281
+        const double tN = __dmul_rn(__dmul_rn(__dmul_rn(kref == 0 ? fr : f0, kref == 1 ? fr : f1),
+                                              kref == 2 ? fr : f2), kref == 3 ? fr : f3);
+        POb[slot] = tO;
+        PNb[slot] = tN;
+      }
+      __syncwarp();
+      // P2b: sums
+      double *db = s.diff + b * NJ * max_tasks;
+      for (int q = lane; q < NJ * n_tasks; q += 32) {
+        const int j = q >= n_tasks;
+        const int tk = j ? q - n_tasks : q;
+        const int2 ts = s.task_sum[tk];
+        const double *po = POb + ts.x + j * max_slots;
+        const double *pn = PNb + ts.x + j * max_slots;
+        double dv;
+        if (!kTree) {
+          double spO = 0.0, spN = 0.0;                       // :246, :282
+          int m = 0;
+          for (; m + 7 < ts.y; m += 8) {
+            double o[8], n[8];
+#pragma unroll
+            for (int x = 0; x < 8; x++) { o[x] = po[m + x]; n[x] = pn[m + x]; }
+#pragma unroll
+            for (int x = 0; x < 8; x++) { spO = __dadd_rn(spO, o[x]); spN = __dadd_rn(spN, n[x]); }
+          }
+          for (; m < ts.y; m++) { spO = __dadd_rn(spO, po[m]); spN = __dadd_rn(spN, pn[m]); }
+          dv = __dsub_rn(spN, spO);                          // :397
+        } else {
+          double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0, n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+          int m = 0;
+          for (; m + 3 < ts.y; m += 4) {
+            o0 = __dadd_rn(o0, po[m]); o1 = __dadd_rn(o1, po[m + 1]);
+            o2 = __dadd_rn(o2, po[m + 2]); o3 = __dadd_rn(o3, po[m + 3]);
+            n0 = __dadd_rn(n0, pn[m]); n1 = __dadd_rn(n1, pn[m + 1]);
+            n2 = __dadd_rn(n2, pn[m + 2]); n3 = __dadd_rn(n3, pn[m + 3]);
+          }
+          for (; m < ts.y; m++) { o0 = __dadd_rn(o0, po[m]); n0 = __dadd_rn(n0, pn[m]); }
+          dv = __dsub_rn(__dadd_rn(__dadd_rn(n0, n1), __dadd_rn(n2, n3)),
+                         __dadd_rn(__dadd_rn(o0, o1), __dadd_rn(o2, o3)));
+        }
+        db[j * max_tasks + tk] = dv;
+      }
+      __syncwarp();
+      // P2c: per-ECI quotients (:393-402): lane i = ECI i, both changed sites
+      {
+        double num0 = 0.0, num1 = 0.0;
+        if (f_kind == 1) {                                  // :366-371
+          num0 = __dsub_rn(Vb[RB + D + f_d], Vb[RB + f_d]);
+          if (kCanon) num1 = __dsub_rn(Vb[VS + RB + D + f_d], Vb[VS + RB + f_d]);
+        } else if (f_kind == 2) {
+          for (int q = 0; q < f_nd; q++) {                  // :397
+            num0 = __dadd_rn(num0, db[f_t0 + q]);
+            if (kCanon) num1 = __dadd_rn(num1, db[max_tasks + f_t0 + q]);
+          }
+          num0 = __dmul_rn(num0, f_scale);                  // :400
+          num1 = __dmul_rn(num1, f_scale);
+        }
+        s.sq[(b * 2 + 0) * 32 + lane] = exact_div(num0, f_den, f_rden);       // :402
+        s.sq[(b * 2 + 1) * 32 + lane] = kCanon ? exact_div(num1, f_den, f_rden) : 0.0;
+      }
+    }
+    __syncthreads();
+    CEMC_TICK(1);
+
+    // ---- E2: which earlier moves of the batch would invalidate this evaluation? -------
+    if (warp < nb) {
+      uint32_t m = 0;
+      for (int k = 0; k < warp; k++) {
+        const int sk0 = s.prop[k * 8], sk1 = s.prop[k * 8 + 1];       // sk1 = -1 for SGC
+        const bool hit = (gsx[0] == sk0) | (gsx[1] == sk0) | (kCanon & ((gsx[0] == sk1) | (gsx[1] == sk1)));
+        if (__ballot_sync(0xffffffffu, hit)) m |= 1u << k;
+      }
+      if (lane == 0) s.cmask[warp] = (int32_t)m;
+    }
+    __syncthreads();
+    CEMC_TICK(2);
+
+    // ---- D: warp 0 decides the moves strictly in order ---------------------------------
+    if (warp == 0) {
+      uint32_t accmask = 0;
+      int ndone = 0;
+      double e_rec = 0.0;          // lane b keeps the energy after move b (trace)
+      for (int b = 0; b < nb; b++) {
+        if ((uint32_t)s.cmask[b] & accmask) break;        // an input of this evaluation changed
+        double c = cf_reg;
+        if (f_kind > 0) {                                     // kinds 0 / -1: copied (:360,:382)
+          c = __dadd_rn(c, s.sq[(b * 2 + 0) * 32 + lane]);    // :404
+          if (kCanon) c = __dadd_rn(c, s.sq[(b * 2 + 1) * 32 + lane]);
+        }
+        const double p = __dmul_rn(eci_reg, c);               // 0 for lanes >= n_eci
+        double e_new = 0.0;                                   // named_array.cpp:27-31, in order
+        for (int i = 0; i < n_eci4; i += 4) {
+          const double p0 = __shfl_sync(0xffffffffu, p, i), p1 = __shfl_sync(0xffffffffu, p, i + 1);
+          const double p2 = __shfl_sync(0xffffffffu, p, i + 2), p3 = __shfl_sync(0xffffffffu, p, i + 3);
+          e_new = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(e_new, p0), p1), p2), p3);
+        }
+        e_new = __dmul_rn(e_new, dN);                                // ce_updater.cpp:241
+        // Metropolis (montecarlo.py:951-956): screened by dE <= -kT ln u; the exact
+        // expression decides inside a 1e-9 relative band around the threshold
+        const uint4 rec1 = s.ring[(int)(sdone + b - rbase) * 2 + 1];
+        const double L = __hiloint2double((int)rec1.w, (int)rec1.z);
+        bool accept;
+        {
+          const double dE = __dsub_rn(e_new, e_cur);
+          if (e_new < e_cur || dE < L * (1.0 - 1e-9)) accept = true;
+          else if (dE > L * (1.0 + 1e-9)) accept = false;
+          else accept = __hiloint2double((int)rec1.y, (int)rec1.x) <= exp(exact_div(-dE, kT, rkT));
+        }
+        if (accept) {
+          cf_reg = c;
+          e_cur = e_new;
+          n_acc++;
+          accmask |= 1u << b;
+        }
+        if (lane == b) e_rec = e_cur;
+        if (observe) {                                               // montecarlo.py:811-814,
+          const double e2 = __dmul_rn(e_cur, e_cur);                 // mc_observers.py:264-270
+          aE0 = __dadd_rn(aE0, 1.0);
+          aE1 = __dadd_rn(aE1, ref_is_one ? e_cur : exact_div(e_cur, ref, rref));
+          aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
+          aS0 = __dadd_rn(aS0, cf_reg);
+          aS1 = __dadd_rn(aS1, __dmul_rn(cf_reg, cf_reg));
+          aS2 = __dadd_rn(aS2, __dmul_rn(cf_reg, e_cur));
+        }
+        ndone++;
+      }
+      // commits of the decided moves: lane b applies move b (accepted moves of one
+      // batch never share a site, so the order among them is irrelevant)
+      if (lane < ndone) {
+        const int4 pa = *reinterpret_cast<const int4 *>(s.prop + lane * 8);
+        const int4 pb = *reinterpret_cast<const int4 *>(s.prop + lane * 8 + 4);
+        const bool acc = (accmask >> lane) & 1u;
+        if (acc) {
+          s.occ[pa.x] = (int8_t)pa.z;
+          if (kCanon) {                        // swap_move_index_tracker.py:39-59
+            s.occ[pa.y] = (int8_t)pa.w;
+            s.list[pb.z] = pa.y; s.list[pb.w] = pa.x;
+            g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z);
+          }
+        }
+        if (tracing && sdone + lane < a.tr_capacity) {
+          const size_t q = (size_t)r * a.tr_capacity + (size_t)(sdone + lane);
+          const uint4 rec1 = s.ring[(int)(sdone + lane - rbase) * 2 + 1];
+          if (a.tr_sites) { a.tr_sites[2 * q] = pa.x; a.tr_sites[2 * q + 1] = pa.y; }
+          if (a.tr_news) { a.tr_news[2 * q] = (int8_t)pa.z; a.tr_news[2 * q + 1] = (int8_t)pa.w; }
+          if (a.tr_u) a.tr_u[q] = __hiloint2double((int)rec1.y, (int)rec1.x);
+          if (a.tr_acc) a.tr_acc[q] = acc ? 1 : 0;
+          if (a.tr_e) a.tr_e[q] = e_rec;
+        }
+      }
+      if (lane == 0) s.ctl[0] = ndone;
+      CEMC_TICK(3);
+#ifdef CEMC_PHASE_TIMING
+      if (tid == 0) { tph[8] += 1; tph[9] += ndone; }
+#endif
+    }
+    __syncthreads();
+    sdone += s.ctl[0];
+    __syncthreads();
+    CEMC_TICK(4);
+  }
+
+#ifdef CEMC_PHASE_TIMING
+  if (tid == 0 && r == 0)
+    for (int i = 0; i < 16; i++) g_phase_cycles[i] = tph[i];
+#endif
+  // ---- write back ------------------------------------------------------------
+  if (warp == 0) {
+    if (lane < n_eci) st.cf[(size_t)r * n_eci + lane] = cf_reg;
+    double *aw = st.acc + (size_t)r * acc_stride;
+    if (lane == 0) { aw[0] = aE0; aw[1] = aE1; aw[2] = aE2; }
+    if (my_singlet >= 0) { aw[3 + 3 * my_singlet] = aS0; aw[4 + 3 * my_singlet] = aS1; aw[5 + 3 * my_singlet] = aS2; }
+    if (lane == 0) {
+      st.e_cur[r] = e_cur;
+      st.step[r] = step0 + (unsigned long long)a.n_steps;
+      st.accepted[r] += n_acc;
+    }
+  }
+  for (int i = tid; i < N; i += nthr) g_occ[i] = s.occ[i];
+  if (kCanon) for (int i = tid; i < N; i += nthr) g_list[i] = s.list[i];
+}
+
+}  // namespace cemc

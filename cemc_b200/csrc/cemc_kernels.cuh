@@ -40,7 +40,7 @@ namespace cemc {
 // -DCEMC_PHASE_TIMING: per-phase clock64() accounting of warp 0 (debug builds only;
 // scripts/phase_timing.py).  Slots: 0 refill 1 P0 2 P1 3 P2a 4 P2b 5 P3 6 end barrier
 #ifdef CEMC_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_phase_cycles[16];
 #define CEMC_TICK(slot)                                              \
   do {                                                               \
     const long long now_ = clock64();                                \
@@ -359,7 +359,7 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   }
 
 #ifdef CEMC_PHASE_TIMING
-  unsigned long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long tph[16] = {0};
   long long tlast = clock64();
 #endif
   for (long long it0 = 0; it0 < a.n_steps && !err; it0 += 32) {
@@ -659,7 +659,7 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   }
 #ifdef CEMC_PHASE_TIMING
   if (tid == 0 && r == 0)
-    for (int i = 0; i < 8; i++) g_phase_cycles[i] = tph[i];
+    for (int i = 0; i < 16; i++) g_phase_cycles[i] = tph[i];
 #endif
 
   // ---- write back --------------------------------------------------------

@@ -141,6 +141,9 @@ class BatchedCEUpdater(object):
         lst = np.ascontiguousarray(lst, dtype=np.int32).reshape(self.R, self.N)
         _lib.check(self.lib.cemc_set_tracker(self._h, _p(lst, C.c_int32)))
 
+    def set_batch(self, b: int):
+        _lib.check(self.lib.cemc_set_batch(self._h, int(b)))
+
     def set_generic_path(self, on: bool):
         _lib.check(self.lib.cemc_set_generic_path(self._h, int(bool(on))))
 

@@ -116,9 +116,12 @@ int cemc_set_order_mode(cemc_handle *h, int mode);
  * FMA-based exact division used by the kernels with IEEE division on
  * n_blocks*256*iters random operand pairs                                    */
 int cemc_set_generic_path(cemc_handle *h, int on);
+/* trial moves evaluated speculatively per batch by the batch kernel
+ * (cemc_batch_kernel.cuh): 0 = auto, 4/8/16, -1 = one move at a time           */
+int cemc_set_batch(cemc_handle *h, int b);
 /* debug builds (-DCEMC_PHASE_TIMING) only: clock64() cycles warp 0 of replica 0
  * spent per kernel phase in the last launch                                   */
-int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8);
+int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out16 /*[16]*/);
 int cemc_selftest_division(cemc_handle *h, uint64_t seed, int n_blocks, int iters,
                            uint64_t *mismatches);
 /* threads per CTA (= per replica): 0 = auto, else a multiple of 32 in [32,256] */

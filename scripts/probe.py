@@ -36,6 +36,8 @@ def timeit(gpu, fn, n, reps=3):
 if __name__ == "__main__":
     which = [a for a in sys.argv[1:] if not a.startswith("t=")] or ["c2", "c3"]
     threads = [int(a[2:]) for a in sys.argv[1:] if a.startswith("t=")] or [0]
+    batches = [int(a[2:]) for a in sys.argv[1:] if a.startswith("b=")] or [0]
+    which = [a for a in which if not a.startswith("b=")]
     if "c2" in which:
         T = np.linspace(200, 1000, 16); mu = np.linspace(-1.1, -0.9, 16)
         kTs = np.repeat(T * KB, 16); mus = np.tile(mu, 16)
@@ -50,12 +52,14 @@ if __name__ == "__main__":
     if "c3" in which:
         kTs = np.linspace(300, 900, 64) * KB
         ft, gpu = setup(20, ["Al", "Mg", "Si"], {"Al": 0.8, "Mg": 0.1, "Si": 0.1}, 64, kTs)
-        for th in threads:
+        for bt in batches:
+          for th in threads:
             gpu.set_block_threads(th)
+            gpu.set_batch(bt)
             n = 50000
             ms = timeit(gpu, gpu.run_canonical, n)
-            print("C3 canonical ternary L=20 R=64 threads=%d n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
-                th, n, ms, 64 * n / ms / 1e3, ms * 1e6 / n))
+            print("C3 canonical ternary L=20 R=64 batch=%d threads=%d n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
+                bt, th, n, ms, 64 * n / ms / 1e3, ms * 1e6 / n))
             ms = timeit(gpu, gpu.run_sgc, n)
-            print("C3-lattice sgc ternary threads=%d: %.1f M moves/s (%.0f ns/move/chain)" % (th, 64 * n / ms / 1e3, ms * 1e6 / n))
+            print("C3-lattice sgc ternary batch=%d threads=%d: %.1f M moves/s (%.0f ns/move/chain)" % (bt, th, 64 * n / ms / 1e3, ms * 1e6 / n))
         st, acc = gpu.get_counters(); print("  accept rate", acc.sum() / st.sum())

@@ -447,3 +447,32 @@ def test_sgc_restricted_species(cuda_device):
     assert np.array_equal(news[0], tr[1]) and np.array_equal(acc[0], tr[3])
     assert set(np.unique(news[0][:, 0])) <= {0, 2}
     assert_state_equal(gpu, chains)
+
+
+@pytest.mark.parametrize("batch", [-1, 4, 8, 16])
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+def test_speculative_batch_kernel(cuda_device, batch, mode):
+    """Speculative batch evaluation (cemc_batch_kernel.cuh) keeps the chain
+    exactly sequential: every batch size gives the oracle's trajectory, also on
+    a tiny cell where moves of one batch collide all the time."""
+    for case, R in ((TERNARY, 3), (dict(TERNARY, L=3), 2)):
+        st, eci, symbols, ft = build(**case)
+        kTs = np.linspace(0.02, 0.2, R)
+        gpu, chains = make_pair(ft, [symbols] * R, kTs, seed=41)
+        gpu.set_batch(batch)
+        n = 1500
+        gpu.set_trace(n)
+        gpu.reset_accumulators()
+        (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+        (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(7)
+        gpu.synchronize()
+        tr = gpu.get_trace(7)
+        for c in chains:
+            c.run_sgc(n) if mode == "sgc" else c.run_canonical(n)
+            o = c.run_sgc(7, trace=True) if mode == "sgc" else c.run_canonical(7, trace=True)
+        assert_state_equal(gpu, chains)
+        accs = gpu.get_accumulators()
+        steps, n_acc = gpu.get_counters()
+        for r, c in enumerate(chains):
+            assert np.array_equal(accs[r], c.acc)
+            assert steps[r] == n + 7 and n_acc[r] == c.n_accepted.value
