@@ -74,6 +74,7 @@ struct cemc_handle {
   bool integer_bf = false;
   int block_threads = 0;              // 0 = auto
   bool force_generic = false;         // testing: disable the register-resident P3 and the spin kernel
+  double screen_slack = 1.0;          // testing: widen the Metropolis screening band
   int batch = 0;                      // moves evaluated speculatively per batch (0 = auto)
   bool spin_ok = false;               // binary +-1 basis: warp-per-replica spin kernel usable
   SpinTables spin{};
@@ -698,6 +699,13 @@ int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8) {
 #endif
 }
 
+int cemc_set_screen_slack(cemc_handle *h, double factor) {
+  if (!h) return fail("null handle");
+  if (!(factor >= 1.0)) return fail("screen slack must be >= 1");
+  h->screen_slack = factor;
+  return 0;
+}
+
 int cemc_set_batch(cemc_handle *h, int b) {
   if (!h) return fail("null handle");
   if (!(b == -1 || b == 0 || b == 4 || b == 8 || b == 16)) return fail("batch must be -1 (off), 0 (auto), 4, 8 or 16");
@@ -932,6 +940,7 @@ static RunArgs run_args(cemc_handle *h, long long n_steps) {
   RunArgs a{};
   a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset;
   a.observe = 1;
+  a.screen_slack = h->screen_slack;
   if (h->trace_capacity > 0) {
     a.tr_sites = h->tr_sites; a.tr_news = h->tr_news; a.tr_u = h->tr_u; a.tr_acc = h->tr_acc;
     a.tr_e = h->tr_e; a.tr_capacity = h->trace_capacity;

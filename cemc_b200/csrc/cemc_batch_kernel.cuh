@@ -26,7 +26,7 @@
 namespace cemc {
 
 struct BatchSmem {
-  double *V, *PO, *PN, *diff, *sq, *bf;
+  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *Pm, *Ch;
   unsigned long long *items;
   int2 *task_sum;
   uint4 *ring;              // [32][2]: proposal; uniform + Metropolis threshold
@@ -53,6 +53,9 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(PN, double, B * nj * t.max_slots);
   CEMC_TAKE(diff, double, B * nj * t.max_tasks);
   CEMC_TAKE(sq, double, B * 2 * 32);
+  CEMC_TAKE(dEa, double, B);
+  CEMC_TAKE(Pm, double, B * 33);
+  CEMC_TAKE(Ch, double, B * 32);
   CEMC_TAKE(bf, double, t.D * t.S);
   CEMC_TAKE(items, unsigned long long, t.n_items_total);
   CEMC_TAKE(task_sum, int2, t.n_tasks_total);
@@ -162,6 +165,15 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   const int observe = pin_reg(a.observe);
   const bool tracing = (a.tr_acc != nullptr) || (a.tr_e != nullptr);
   const int n_allowed = t.n_allowed;
+  // absolute slack of the Metropolis screen: rounding noise of the two ordered dot
+  // products the reference subtracts, N * sum_i |eci_i| * max|cf| * O(n_eci * eps)
+  double etol;
+  {
+    double sa = lane < n_eci ? fabs(eci_reg) * fmax(1.0, fabs(cf_reg)) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    etol = 1e-13 * dN * sa * 16.0 * a.screen_slack;
+  }
 
 #ifdef CEMC_PHASE_TIMING
   unsigned long long tph[16] = {0};
@@ -337,8 +349,16 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
           num0 = __dmul_rn(num0, f_scale);                  // :400
           num1 = __dmul_rn(num1, f_scale);
         }
-        s.sq[(b * 2 + 0) * 32 + lane] = exact_div(num0, f_den, f_rden);       // :402
-        s.sq[(b * 2 + 1) * 32 + lane] = kCanon ? exact_div(num1, f_den, f_rden) : 0.0;
+        const double qa = exact_div(num0, f_den, f_rden);                     // :402
+        const double qb = kCanon ? exact_div(num1, f_den, f_rden) : 0.0;
+        s.sq[(b * 2 + 0) * 32 + lane] = qa;
+        s.sq[(b * 2 + 1) * 32 + lane] = qb;
+        // state-independent energy change of this move, N * sum_i eci_i (q0_i + q1_i):
+        // only used to SCREEN the Metropolis test (any summation order will do)
+        double de = f_kind > 0 ? eci_reg * (qa + qb) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
+        if (lane == 0) s.dEa[b] = de * dN;
       }
     }
     __syncthreads();
@@ -358,61 +378,101 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
     CEMC_TICK(2);
 
     // ---- D: warp 0 decides the moves strictly in order ---------------------------------
+    // The Metropolis outcome of a move depends on the chain state only through
+    // E_new - E_cur = N sum_i eci_i dcf_i (+ rounding), i.e. on the move alone, as long
+    // as none of its inputs was changed by an earlier accepted move.  So: (1) every
+    // lane screens one move against its threshold -kT ln u; (2) a scalar pass applies
+    // the conflict masks in order; (3) the exact bookkeeping (CF vector, ordered energy
+    // dot, observer sums) of the decided moves follows, lane-parallel over moves
+    // where the reference's operation order allows.  A move whose screen is
+    // inconclusive (|dE - L| inside the band) is decided with the exact expression.
     if (warp == 0) {
+      const uint4 rec1 = s.ring[(int)(sdone + (lane < nb ? lane : 0) - rbase) * 2 + 1];
+      const double u_l = __hiloint2double((int)rec1.y, (int)rec1.x);
+      const double L_l = __hiloint2double((int)rec1.w, (int)rec1.z);
+      const double dE_l = s.dEa[lane < nb ? lane : 0];
+      const double band = 1e-9 * a.screen_slack * fmax(fabs(dE_l), fabs(L_l)) + etol;
+      const bool t_acc = lane < nb && (dE_l < L_l - band);
+      const bool t_bdr = lane < nb && !t_acc && !(dE_l > L_l + band);
+      const uint32_t tmask = __ballot_sync(0xffffffffu, t_acc);
+      const uint32_t bmask = __ballot_sync(0xffffffffu, t_bdr);
+      const uint32_t cm_l = lane < nb ? (uint32_t)s.cmask[lane] : 0u;
       uint32_t accmask = 0;
       int ndone = 0;
-      double e_rec = 0.0;          // lane b keeps the energy after move b (trace)
+      double c = cf_reg;                 // CF of this lane's ECI, after the moves decided so far
+      double E_l = 0.0;                  // lane b: energy after move b (if accepted)
       for (int b = 0; b < nb; b++) {
-        if ((uint32_t)s.cmask[b] & accmask) break;        // an input of this evaluation changed
-        double c = cf_reg;
-        if (f_kind > 0) {                                     // kinds 0 / -1: copied (:360,:382)
-          c = __dadd_rn(c, s.sq[(b * 2 + 0) * 32 + lane]);    // :404
-          if (kCanon) c = __dadd_rn(c, s.sq[(b * 2 + 1) * 32 + lane]);
+        const uint32_t cm = __shfl_sync(0xffffffffu, cm_l, b);
+        if (cm & accmask) break;                           // an input of this evaluation changed
+        bool accept = (tmask >> b) & 1u;
+        const bool bdr = (bmask >> b) & 1u;
+        double cn = c;
+        if (accept || bdr) {
+          if (f_kind > 0) {                                  // kinds 0 / -1: copied (:360,:382)
+            cn = __dadd_rn(cn, s.sq[(b * 2 + 0) * 32 + lane]);   // :404
+            if (kCanon) cn = __dadd_rn(cn, s.sq[(b * 2 + 1) * 32 + lane]);
+          }
         }
-        const double p = __dmul_rn(eci_reg, c);               // 0 for lanes >= n_eci
-        double e_new = 0.0;                                   // named_array.cpp:27-31, in order
-        for (int i = 0; i < n_eci4; i += 4) {
-          const double p0 = __shfl_sync(0xffffffffu, p, i), p1 = __shfl_sync(0xffffffffu, p, i + 1);
-          const double p2 = __shfl_sync(0xffffffffu, p, i + 2), p3 = __shfl_sync(0xffffffffu, p, i + 3);
-          e_new = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(e_new, p0), p1), p2), p3);
-        }
-        e_new = __dmul_rn(e_new, dN);                                // ce_updater.cpp:241
-        // Metropolis (montecarlo.py:951-956): screened by dE <= -kT ln u; the exact
-        // expression decides inside a 1e-9 relative band around the threshold
-        const uint4 rec1 = s.ring[(int)(sdone + b - rbase) * 2 + 1];
-        const double L = __hiloint2double((int)rec1.w, (int)rec1.z);
-        bool accept;
-        {
-          const double dE = __dsub_rn(e_new, e_cur);
-          if (e_new < e_cur || dE < L * (1.0 - 1e-9)) accept = true;
-          else if (dE > L * (1.0 + 1e-9)) accept = false;
-          else accept = __hiloint2double((int)rec1.y, (int)rec1.x) <= exp(exact_div(-dE, kT, rkT));
+        if (bdr) {
+          // exact path (rare): ordered dot (named_array.cpp:27-31) + montecarlo.py:951-956
+          // needs the exact current energy: flush the pending energies first
+          if (accmask) break;                                // decide it first thing next batch
+          const double p = __dmul_rn(eci_reg, cn);
+          double e_new = 0.0;
+          for (int i = 0; i < n_eci4; i++) e_new = __dadd_rn(e_new, __shfl_sync(0xffffffffu, p, i));
+          e_new = __dmul_rn(e_new, dN);
+          const double ub = __shfl_sync(0xffffffffu, u_l, b);
+          accept = metropolis(e_new, e_cur, ub, kT, rkT);
         }
         if (accept) {
-          cf_reg = c;
-          e_cur = e_new;
-          n_acc++;
+          c = cn;
           accmask |= 1u << b;
+          s.Pm[b * 33 + lane] = __dmul_rn(eci_reg, c);      // products of the ordered dot
         }
-        if (lane == b) e_rec = e_cur;
-        if (observe) {                                               // montecarlo.py:811-814,
-          const double e2 = __dmul_rn(e_cur, e_cur);                 // mc_observers.py:264-270
-          aE0 = __dadd_rn(aE0, 1.0);
-          aE1 = __dadd_rn(aE1, ref_is_one ? e_cur : exact_div(e_cur, ref, rref));
-          aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
-          aS0 = __dadd_rn(aS0, cf_reg);
-          aS1 = __dadd_rn(aS1, __dmul_rn(cf_reg, cf_reg));
-          aS2 = __dadd_rn(aS2, __dmul_rn(cf_reg, e_cur));
-        }
+        s.Ch[b * 32 + lane] = c;                             // CF after move b (observers)
         ndone++;
+      }
+      __syncwarp();
+      // exact energies of the accepted moves, one lane per move (ordered dot, :236-242)
+      const bool my_acc = lane < ndone && ((accmask >> lane) & 1u);
+      if (my_acc) {
+        double e = 0.0;
+        for (int i = 0; i < n_eci; i++) e = __dadd_rn(e, s.Pm[lane * 33 + i]);
+        E_l = __dmul_rn(e, dN);
+      }
+      // energy after move b = energy of the last accepted move <= b (else the old one)
+      double E_after;
+      {
+        const uint32_t upto = accmask & (lane >= 31 ? 0xffffffffu : ((2u << lane) - 1u));
+        const int src = upto ? 31 - __clz(upto) : 0;
+        const double Es = __shfl_sync(0xffffffffu, E_l, src);
+        E_after = upto ? Es : e_cur;
+      }
+      if (accmask) {
+        const int last = 31 - __clz(accmask);
+        e_cur = __shfl_sync(0xffffffffu, E_l, last);
+        cf_reg = c;
+        n_acc += __popc(accmask);
+      }
+      if (observe) {                                               // montecarlo.py:811-814,
+        for (int b = 0; b < ndone; b++) {                          // mc_observers.py:264-270
+          const double Eb = __shfl_sync(0xffffffffu, E_after, b);
+          const double cb = s.Ch[b * 32 + lane];
+          const double e2 = __dmul_rn(Eb, Eb);
+          aE0 = __dadd_rn(aE0, 1.0);
+          aE1 = __dadd_rn(aE1, ref_is_one ? Eb : exact_div(Eb, ref, rref));
+          aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
+          aS0 = __dadd_rn(aS0, cb);
+          aS1 = __dadd_rn(aS1, __dmul_rn(cb, cb));
+          aS2 = __dadd_rn(aS2, __dmul_rn(cb, Eb));
+        }
       }
       // commits of the decided moves: lane b applies move b (accepted moves of one
       // batch never share a site, so the order among them is irrelevant)
       if (lane < ndone) {
         const int4 pa = *reinterpret_cast<const int4 *>(s.prop + lane * 8);
         const int4 pb = *reinterpret_cast<const int4 *>(s.prop + lane * 8 + 4);
-        const bool acc = (accmask >> lane) & 1u;
-        if (acc) {
+        if (my_acc) {
           s.occ[pa.x] = (int8_t)pa.z;
           if (kCanon) {                        // swap_move_index_tracker.py:39-59
             s.occ[pa.y] = (int8_t)pa.w;
@@ -422,12 +482,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
         }
         if (tracing && sdone + lane < a.tr_capacity) {
           const size_t q = (size_t)r * a.tr_capacity + (size_t)(sdone + lane);
-          const uint4 rec1 = s.ring[(int)(sdone + lane - rbase) * 2 + 1];
           if (a.tr_sites) { a.tr_sites[2 * q] = pa.x; a.tr_sites[2 * q + 1] = pa.y; }
           if (a.tr_news) { a.tr_news[2 * q] = (int8_t)pa.z; a.tr_news[2 * q + 1] = (int8_t)pa.w; }
-          if (a.tr_u) a.tr_u[q] = __hiloint2double((int)rec1.y, (int)rec1.x);
-          if (a.tr_acc) a.tr_acc[q] = acc ? 1 : 0;
-          if (a.tr_e) a.tr_e[q] = e_rec;
+          if (a.tr_u) a.tr_u[q] = u_l;
+          if (a.tr_acc) a.tr_acc[q] = my_acc ? 1 : 0;
+          if (a.tr_e) a.tr_e[q] = E_after;
         }
       }
       if (lane == 0) s.ctl[0] = ndone;

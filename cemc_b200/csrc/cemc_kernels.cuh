@@ -106,6 +106,7 @@ struct RunArgs {
   uint32_t replica_offset;
   int force_accept;      // trial semantics: commit every step (CEUpdater::calculate)
   int observe;           // accumulate observers
+  double screen_slack;   // multiplies the Metropolis screening band (testing; default 1)
   // replay inputs (device)
   const int32_t *rp_sites;   // [R][n][2]
   const int8_t *rp_news;     // [R][n][2]

@@ -141,6 +141,9 @@ class BatchedCEUpdater(object):
         lst = np.ascontiguousarray(lst, dtype=np.int32).reshape(self.R, self.N)
         _lib.check(self.lib.cemc_set_tracker(self._h, _p(lst, C.c_int32)))
 
+    def set_screen_slack(self, factor: float):
+        _lib.check(self.lib.cemc_set_screen_slack(self._h, C.c_double(factor)))
+
     def set_batch(self, b: int):
         _lib.check(self.lib.cemc_set_batch(self._h, int(b)))
 

@@ -476,3 +476,23 @@ def test_speculative_batch_kernel(cuda_device, batch, mode):
         for r, c in enumerate(chains):
             assert np.array_equal(accs[r], c.acc)
             assert steps[r] == n + 7 and n_acc[r] == c.n_accepted.value
+
+
+@pytest.mark.parametrize("slack", [1e30, 1e6])
+def test_batch_kernel_exact_decision_path(cuda_device, slack):
+    """Force the batch kernel's Metropolis screen to defer to the exact
+    expression (always / often): the trajectory must not change."""
+    st, eci, symbols, ft = build(**TERNARY)
+    gpu, chains = make_pair(ft, [symbols] * 2, [0.03, 0.08], seed=53)
+    gpu.set_screen_slack(slack)
+    gpu.reset_accumulators()
+    gpu.run_canonical(800)
+    gpu.run_sgc(800)
+    gpu.synchronize()
+    for c in chains:
+        c.run_canonical(800)
+        c.run_sgc(800)
+    assert_state_equal(gpu, chains)
+    accs = gpu.get_accumulators()
+    for r, c in enumerate(chains):
+        assert np.array_equal(accs[r], c.acc)
