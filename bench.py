@@ -287,9 +287,35 @@ def gpu_arm(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_extra:
+            line["other_workloads"] = extra_workloads(local_rank)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_workloads(device):
+    """Short device-timed runs of the other BASELINE configurations (informational:
+    the north-star target line is the 64-replica Al-Mg-Si SGC sweep)."""
+    from cemc_b200 import workloads as wl
+    out = {}
+    for name, n in (("C3S", 40000), ("C3", 40000), ("C1", 40000)):
+        w = wl.WORKLOADS[name](R=64) if name != "C1" else wl.WORKLOADS[name](R=64)
+        gpu = wl.make_updater(w, device=device)
+        run = gpu.run_sgc if w.mode == "sgc" else gpu.run_canonical
+        run(n)
+        gpu.synchronize()
+        best = 1e30
+        for _ in range(3):
+            gpu.timer_start()
+            run(n)
+            best = min(best, gpu.timer_stop())
+        gpu.synchronize()
+        out[name] = {"workload": w.description, "moves_per_s": w.R * n / (best * 1e-3),
+                     "ns_per_move_per_chain": best * 1e6 / n,
+                     "algorithmic_bytes_per_move": w.tables.algorithmic_bytes_per_move(w.sites_changed)}
+        gpu.close()
+    return out
 
 
 def reference_arm(args):
@@ -335,6 +361,7 @@ def main():
     ap.add_argument("--ref-moves", type=int, default=100000,
                     help="moves per chain per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other_workloads block")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

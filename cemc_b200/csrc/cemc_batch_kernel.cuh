@@ -397,47 +397,74 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
       const uint32_t tmask = __ballot_sync(0xffffffffu, t_acc);
       const uint32_t bmask = __ballot_sync(0xffffffffu, t_bdr);
       const uint32_t cm_l = lane < nb ? (uint32_t)s.cmask[lane] : 0u;
-      uint32_t accmask = 0;
-      int ndone = 0;
+      uint32_t tm = tmask;
       double c = cf_reg;                 // CF of this lane's ECI, after the moves decided so far
       double E_l = 0.0;                  // lane b: energy after move b (if accepted)
-      for (int b = 0; b < nb; b++) {
-        const uint32_t cm = __shfl_sync(0xffffffffu, cm_l, b);
-        if (cm & accmask) break;                           // an input of this evaluation changed
-        bool accept = (tmask >> b) & 1u;
-        const bool bdr = (bmask >> b) & 1u;
+      if (bmask & 1u) {
+        // move 0 is inconclusive: exact path (rare) -- ordered dot (named_array.cpp:27-31)
+        // and the reference expression (montecarlo.py:951-956) on the current state
         double cn = c;
-        if (accept || bdr) {
-          if (f_kind > 0) {                                  // kinds 0 / -1: copied (:360,:382)
-            cn = __dadd_rn(cn, s.sq[(b * 2 + 0) * 32 + lane]);   // :404
-            if (kCanon) cn = __dadd_rn(cn, s.sq[(b * 2 + 1) * 32 + lane]);
+        if (f_kind > 0) {
+          cn = __dadd_rn(cn, s.sq[lane]);
+          if (kCanon) cn = __dadd_rn(cn, s.sq[32 + lane]);
+        }
+        const double p = __dmul_rn(eci_reg, cn);
+        double e_new = 0.0;
+        for (int i = 0; i < n_eci4; i++) e_new = __dadd_rn(e_new, __shfl_sync(0xffffffffu, p, i));
+        e_new = __dmul_rn(e_new, dN);
+        const double ub = __shfl_sync(0xffffffffu, u_l, 0);
+        if (metropolis(e_new, e_cur, ub, kT, rkT)) tm |= 1u; else tm &= ~1u;
+      }
+      // In-order semantics without a loop: all moves before the first invalid one are
+      // decided by their screen bit, so move b is invalid iff one of the moves it
+      // conflicts with (cm_l) is accepted among its predecessors.  The batch ends at the
+      // first invalid move or at the first inconclusive move other than move 0.
+      const uint32_t below = lane ? ((1u << lane) - 1u) : 0u;
+      const bool stop_here = lane < nb && (((cm_l & tm & below) != 0u) || (lane > 0 && ((bmask >> lane) & 1u)));
+      const uint32_t stops = __ballot_sync(0xffffffffu, stop_here);
+      const int ndone = stops ? (__ffs(stops) - 1) : nb;
+      const uint32_t accmask = tm & (ndone >= 32 ? 0xffffffffu : ((1u << ndone) - 1u));
+      // CF vector through the accepted moves, in order (:404); products for the dots
+      {
+        uint32_t rem = accmask;
+        int bn = rem ? __ffs(rem) - 1 : 0;
+        double qa = s.sq[(bn * 2 + 0) * 32 + lane], qb = kCanon ? s.sq[(bn * 2 + 1) * 32 + lane] : 0.0;
+        int bprev = 0;
+        while (rem) {
+          const int bc = bn;
+          rem &= rem - 1;
+          const double qa_c = qa, qb_c = qb;
+          if (rem) {                                         // prefetch the next accepted move
+            bn = __ffs(rem) - 1;
+            qa = s.sq[(bn * 2 + 0) * 32 + lane];
+            if (kCanon) qb = s.sq[(bn * 2 + 1) * 32 + lane];
           }
+          for (int x = bprev; x < bc; x++) s.Ch[x * 32 + lane] = c;     // rejected moves keep c
+          if (f_kind > 0) {                                  // kinds 0 / -1: copied (:360,:382)
+            c = __dadd_rn(c, qa_c);                          // :404
+            if (kCanon) c = __dadd_rn(c, qb_c);
+          }
+          s.Pm[bc * 33 + lane] = __dmul_rn(eci_reg, c);
+          s.Ch[bc * 32 + lane] = c;
+          bprev = bc + 1;
         }
-        if (bdr) {
-          // exact path (rare): ordered dot (named_array.cpp:27-31) + montecarlo.py:951-956
-          // needs the exact current energy: flush the pending energies first
-          if (accmask) break;                                // decide it first thing next batch
-          const double p = __dmul_rn(eci_reg, cn);
-          double e_new = 0.0;
-          for (int i = 0; i < n_eci4; i++) e_new = __dadd_rn(e_new, __shfl_sync(0xffffffffu, p, i));
-          e_new = __dmul_rn(e_new, dN);
-          const double ub = __shfl_sync(0xffffffffu, u_l, b);
-          accept = metropolis(e_new, e_cur, ub, kT, rkT);
-        }
-        if (accept) {
-          c = cn;
-          accmask |= 1u << b;
-          s.Pm[b * 33 + lane] = __dmul_rn(eci_reg, c);      // products of the ordered dot
-        }
-        s.Ch[b * 32 + lane] = c;                             // CF after move b (observers)
-        ndone++;
+        for (int x = bprev; x < ndone; x++) s.Ch[x * 32 + lane] = c;
       }
       __syncwarp();
       // exact energies of the accepted moves, one lane per move (ordered dot, :236-242)
       const bool my_acc = lane < ndone && ((accmask >> lane) & 1u);
       if (my_acc) {
+        const double *pm = s.Pm + lane * 33;
         double e = 0.0;
-        for (int i = 0; i < n_eci; i++) e = __dadd_rn(e, s.Pm[lane * 33 + i]);
+        int i = 0;
+        for (; i + 7 < n_eci; i += 8) {
+          double v[8];
+#pragma unroll
+          for (int x = 0; x < 8; x++) v[x] = pm[i + x];
+#pragma unroll
+          for (int x = 0; x < 8; x++) e = __dadd_rn(e, v[x]);
+        }
+        for (; i < n_eci; i++) e = __dadd_rn(e, pm[i]);
         E_l = __dmul_rn(e, dN);
       }
       // energy after move b = energy of the last accepted move <= b (else the old one)
@@ -455,7 +482,23 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
         n_acc += __popc(accmask);
       }
       if (observe) {                                               // montecarlo.py:811-814,
-        for (int b = 0; b < ndone; b++) {                          // mc_observers.py:264-270
+        int b = 0;                                                 // mc_observers.py:264-270
+        for (; b + 3 < ndone; b += 4) {
+          double Eb[4], cb[4];
+#pragma unroll
+          for (int x = 0; x < 4; x++) { Eb[x] = __shfl_sync(0xffffffffu, E_after, b + x); cb[x] = s.Ch[(b + x) * 32 + lane]; }
+#pragma unroll
+          for (int x = 0; x < 4; x++) {
+            const double e2 = __dmul_rn(Eb[x], Eb[x]);
+            aE0 = __dadd_rn(aE0, 1.0);
+            aE1 = __dadd_rn(aE1, ref_is_one ? Eb[x] : exact_div(Eb[x], ref, rref));
+            aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
+            aS0 = __dadd_rn(aS0, cb[x]);
+            aS1 = __dadd_rn(aS1, __dmul_rn(cb[x], cb[x]));
+            aS2 = __dadd_rn(aS2, __dmul_rn(cb[x], Eb[x]));
+          }
+        }
+        for (; b < ndone; b++) {
           const double Eb = __shfl_sync(0xffffffffu, E_after, b);
           const double cb = s.Ch[b * 32 + lane];
           const double e2 = __dmul_rn(Eb, Eb);

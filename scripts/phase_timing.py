@@ -26,4 +26,4 @@ for which in args or ["C2", "C3", "C3S"]:
     _lib.check(gpu.lib.cemc_debug_phase_cycles(gpu._h, out))
     cyc = np.array(list(out), dtype=float) / n
     print("%s: %.0f ns/move/chain; cycles/move by phase: %s  total %.0f" % (
-        which, ms * 1e6 / n, ", ".join("%s %.0f" % (a, b) for a, b in zip(names, cyc) if b > 0), cyc.sum()))
+        which, ms * 1e6 / n, ", ".join("%s %.2f" % (a, b) for a, b in zip(names, cyc) if b > 0), cyc.sum()))

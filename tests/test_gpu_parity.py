@@ -496,3 +496,33 @@ def test_batch_kernel_exact_decision_path(cuda_device, slack):
     accs = gpu.get_accumulators()
     for r, c in enumerate(chains):
         assert np.array_equal(accs[r], c.acc)
+
+
+@pytest.mark.parametrize("species,conc", [(["Al", "Mg"], {"Al": 0.9, "Mg": 0.1}),
+                                          (["Al", "Mg", "Si"], {"Al": 0.8, "Mg": 0.1, "Si": 0.1})])
+def test_large_cell_global_state(cuda_device, species, conc):
+    """BASELINE config 5 size (fcc 64^3 = 262 144 sites): the occupations do not
+    fit in shared memory, the kernels keep them in global memory.  One chain,
+    canonical + SGC moves, bit-compared with the oracle."""
+    st, eci, symbols, ft = build(64, species, ["nn", "2nn", "tri", "tet"], conc)
+    assert ft.N == 262144
+    occ = ft.occupancy(symbols)
+    gpu = BatchedCEUpdater(ft, 1)
+    gpu.set_occupancy(occ[None])
+    gpu.recompute_cf()
+    cf0 = gpu.get_cf()[0]
+    oc = OracleChain(ft, occ, cf=cf0, kT=0.04, seed=3)
+    assert gpu.get_energy()[0] == oc.e
+    gpu.set_kT([0.04])
+    gpu.seed(3)
+    gpu.run_canonical(1500)
+    gpu.run_sgc(1500)
+    gpu.synchronize()
+    oc.run_canonical(1500)
+    oc.run_sgc(1500)
+    assert np.array_equal(gpu.get_occupancy()[0], oc.occ)
+    assert np.array_equal(gpu.get_cf()[0], oc.cf)
+    assert gpu.get_energy()[0] == oc.e
+    # from-scratch CFs agree with the incrementally updated ones at this size
+    gpu.recompute_cf()
+    np.testing.assert_allclose(gpu.get_cf()[0], oc.cf, rtol=0, atol=1e-12)
