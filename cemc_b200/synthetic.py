@@ -134,6 +134,7 @@ class SyntheticSettings(object):
         self.cluster_info = []
         self.basis_functions = []
         self.trans_matrix = None
+        self.trans_matrix_columns = None   # compact form only (see fcc_settings)
         self.atoms = None
         self.size = None
         self.max_cluster_dia = 0.0
@@ -201,7 +202,7 @@ STANDARD_FAMILIES = ("nn", "2nn", "tri", "tet")
 
 def fcc_settings(L: int, species: Sequence[str] = ("Al", "Mg"),
                  families: Sequence[str] = STANDARD_FAMILIES,
-                 trans_matrix_format: str = "ndarray") -> SyntheticSettings:
+                 trans_matrix_format: str = "auto") -> SyntheticSettings:
     """fcc primitive L^3 cell with the requested cluster families."""
     if L < 3:
         raise ValueError("L >= 3 required (self interaction otherwise)")
@@ -281,7 +282,21 @@ def fcc_settings(L: int, species: Sequence[str] = ("Al", "Mg"),
     used_cols = sorted({c for f in info.values() for sub in f["indices"]
                         for c in sub})
     ijk = np.stack(np.unravel_index(np.arange(N), (L, L, L)), axis=1)
-    if trans_matrix_format == "ndarray":
+    if trans_matrix_format == "auto":
+        # a dense [N, max_col + 1] table (the reference's ndarray form) is O(N^2) memory
+        trans_matrix_format = "ndarray" if N <= 4096 else "compact"
+    if trans_matrix_format == "compact":
+        # only the used columns: trans_matrix[:, k] belongs to column id
+        # trans_matrix_columns[k] (extension understood by cemc_b200.tables.FlatTables;
+        # the reference needs the dense or the list-of-dict form)
+        tm = np.zeros((N, len(used_cols)), dtype=np.int32)
+        for k, c in enumerate(used_cols):
+            cijk = np.array(np.unravel_index(c, (L, L, L)))
+            t = (ijk + cijk[None, :]) % L
+            tm[:, k] = (t[:, 0] * L + t[:, 1]) * L + t[:, 2]
+        st.trans_matrix = tm
+        st.trans_matrix_columns = list(used_cols)
+    elif trans_matrix_format == "ndarray":
         ncol = max(used_cols) + 1
         tm = np.zeros((N, ncol), dtype=np.int32)
         for c in used_cols:

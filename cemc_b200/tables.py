@@ -146,7 +146,14 @@ class FlatTables(object):
         # translation matrix restricted to used columns (:899-979)
         tm = settings.trans_matrix
         trans = np.zeros((N, K), dtype=np.int32)
-        if isinstance(tm, np.ndarray):
+        compact_cols = getattr(settings, "trans_matrix_columns", None)
+        if isinstance(tm, np.ndarray) and compact_cols is not None:
+            pos = {c: k for k, c in enumerate(compact_cols)}
+            if tm.shape != (N, len(compact_cols)) or any(c not in pos for c in self.cols):
+                raise ValueError("compact translation matrix does not cover "
+                                 "the columns used by the clusters")
+            trans[:, :] = tm[:, [pos[c] for c in self.cols]]
+        elif isinstance(tm, np.ndarray):
             if tm.shape[0] != N:
                 raise ValueError("The number of atoms and the dimension of "
                                  "the translation matrix is inconsistent")

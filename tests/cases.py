@@ -15,7 +15,7 @@ KB = 8.617330337217213e-05   # eV/K (ase.units.kB, CODATA 2014)
 
 
 def build(L, species, families, conc, eci_kind="synthetic", seed=3,
-          trans_matrix_format="ndarray"):
+          trans_matrix_format="auto"):
     st = syn.fcc_settings(L, species, families,
                           trans_matrix_format=trans_matrix_format)
     eci = syn.almg_ecis(st) if eci_kind == "almg" else \
