@@ -74,6 +74,7 @@ struct cemc_handle {
   bool integer_bf = false;
   int block_threads = 0;              // 0 = auto
   bool force_generic = false;         // testing: disable the register-resident P3 and the spin kernel
+  bool no_spin = false;               // testing: skip the binary spin kernel
   double screen_slack = 1.0;          // testing: widen the Metropolis screening band
   int batch = 0;                      // moves evaluated speculatively per batch (0 = auto)
   bool spin_ok = false;               // binary +-1 basis: warp-per-replica spin kernel usable
@@ -699,6 +700,12 @@ int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8) {
 #endif
 }
 
+int cemc_set_spin_kernel(cemc_handle *h, int on) {
+  if (!h) return fail("null handle");
+  h->no_spin = (on == 0);
+  return 0;
+}
+
 int cemc_set_screen_slack(cemc_handle *h, double factor) {
   if (!h) return fail("null handle");
   if (!(factor >= 1.0)) return fail("screen slack must be >= 1");
@@ -857,7 +864,7 @@ static int launch_spin_nr(cemc_handle *h, const RunArgs &a, size_t sm) {
 // returns -1 when the spin kernel is not applicable (caller falls back to the generic kernel)
 template <int MODE>
 static int launch_spin(cemc_handle *h, const RunArgs &a) {
-  if (!h->spin_ok || h->force_generic || !h->t.allowed_identity) return -1;
+  if (!h->spin_ok || h->force_generic || h->no_spin || !h->t.allowed_identity) return -1;
   const size_t N = (size_t)h->t.N;
   const size_t sm = 1024 + 4 * (size_t)((h->spin.n_items + 3) & ~3) +
                     (MODE == MODE_CANONICAL ? 4 * ((N + 3) & ~(size_t)3) : 0) + ((N + 15) & ~(size_t)15);
@@ -871,10 +878,17 @@ static int launch_spin(cemc_handle *h, const RunArgs &a) {
 
 template <int MODE, bool kTree, int B>
 static int launch_batch_b(cemc_handle *h, const RunArgs &a) {
-  const size_t sm = batch_smem_layout<B>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL);
+  size_t sm = batch_smem_layout<B>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, true);
+  const bool in_smem = sm <= (size_t)h->max_smem_optin;
+  if (!in_smem) sm = batch_smem_layout<B>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, false);
   if (sm > (size_t)h->max_smem_optin) return -1;
-  CU(cudaFuncSetAttribute(batch_kernel<MODE, kTree, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  batch_kernel<MODE, kTree, B><<<h->R, B * 32, sm, h->stream>>>(h->t, h->st, a, h->acc_stride);
+  if (in_smem) {
+    CU(cudaFuncSetAttribute(batch_kernel<MODE, kTree, B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    batch_kernel<MODE, kTree, B, true><<<h->R, B * 32, sm, h->stream>>>(h->t, h->st, a, h->acc_stride);
+  } else {
+    CU(cudaFuncSetAttribute(batch_kernel<MODE, kTree, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    batch_kernel<MODE, kTree, B, false><<<h->R, B * 32, sm, h->stream>>>(h->t, h->st, a, h->acc_stride);
+  }
   h->launches++;
   CU(cudaGetLastError());
   return 0;

@@ -39,7 +39,8 @@ struct BatchSmem {
 
 template <int B>
 __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char *base,
-                                                    const DeviceTables &t, bool canonical) {
+                                                    const DeviceTables &t, bool canonical,
+                                                    bool state_in_smem = true) {
   size_t o = 0;
 #define CEMC_TAKE(field, type, count)                                   \
   do {                                                                  \
@@ -63,10 +64,12 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(prop, int32_t, B * 8);
   CEMC_TAKE(cmask, int32_t, B);
   CEMC_TAKE(ctl, int32_t, 8);
-  if (canonical) CEMC_TAKE(list, int32_t, t.N);
-  o = align_up(o, 16);
-  if (s) s->occ = reinterpret_cast<int8_t *>(base + o);
-  o += align_up((size_t)t.N, 16);
+  if (state_in_smem) {
+    if (canonical) CEMC_TAKE(list, int32_t, t.N);
+    o = align_up(o, 16);
+    if (s) s->occ = reinterpret_cast<int8_t *>(base + o);
+    o += align_up((size_t)t.N, 16);
+  }
 #undef CEMC_TAKE
   return align_up(o, 16);
 }
@@ -80,7 +83,9 @@ __device__ __forceinline__ int offs_of(const int (&offs)[9], int sp) {
 }
 
 // One WARP evaluates one trial move; B warps = B moves per batch.
-template <int MODE, bool kTree, int B>
+// kStateSmem = false: occupations / site lists stay in global memory (L2): supercells
+// whose occupations do not fit in shared memory (64^3); the batch hides the latency.
+template <int MODE, bool kTree, int B, bool kStateSmem>
 __global__ void __launch_bounds__(B * 32, 1)
 batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -99,15 +104,18 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   int32_t *g_list = st.list + (size_t)r * N;
   int32_t *g_loc = st.loc + (size_t)r * N;
   BatchSmem s;
-  batch_smem_layout<B>(&s, smem_raw, t, kCanon);
+  batch_smem_layout<B>(&s, smem_raw, t, kCanon, kStateSmem);
+  if (!kStateSmem) { s.occ = g_occ; s.list = g_list; }
 
   // ---- stage ----------------------------------------------------------------
   for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
   for (int i = tid; i < t.n_items_total; i += nthr) s.items[i] = t.items[i];
   for (int i = tid; i < t.n_tasks_total; i += nthr) s.task_sum[i] = t.task_sum[i];
   for (int i = tid; i < B * NJ * VS; i += nthr) s.V[i] = 1.0;      // V[K] is the constant 1.0
-  for (int i = tid; i < N; i += nthr) s.occ[i] = g_occ[i];
-  if (kCanon) for (int i = tid; i < N; i += nthr) s.list[i] = g_list[i];
+  if (kStateSmem) {
+    for (int i = tid; i < N; i += nthr) s.occ[i] = g_occ[i];
+    if (kCanon) for (int i = tid; i < N; i += nthr) s.list[i] = g_list[i];
+  }
   // canonical: species present and their list ranges (constant during a launch)
   int n_present = 0, present[8], offs[9];
 #pragma unroll
@@ -532,6 +540,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
           if (a.tr_e) a.tr_e[q] = E_after;
         }
       }
+      if (!kStateSmem) __threadfence_block();
       if (lane == 0) s.ctl[0] = ndone;
       CEMC_TICK(3);
 #ifdef CEMC_PHASE_TIMING
@@ -560,8 +569,10 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
       st.accepted[r] += n_acc;
     }
   }
-  for (int i = tid; i < N; i += nthr) g_occ[i] = s.occ[i];
-  if (kCanon) for (int i = tid; i < N; i += nthr) g_list[i] = s.list[i];
+  if (kStateSmem) {
+    for (int i = tid; i < N; i += nthr) g_occ[i] = s.occ[i];
+    if (kCanon) for (int i = tid; i < N; i += nthr) g_list[i] = s.list[i];
+  }
 }
 
 }  // namespace cemc

@@ -144,6 +144,9 @@ class BatchedCEUpdater(object):
     def set_screen_slack(self, factor: float):
         _lib.check(self.lib.cemc_set_screen_slack(self._h, C.c_double(factor)))
 
+    def set_spin_kernel(self, on: bool):
+        _lib.check(self.lib.cemc_set_spin_kernel(self._h, int(bool(on))))
+
     def set_batch(self, b: int):
         _lib.check(self.lib.cemc_set_batch(self._h, int(b)))
 

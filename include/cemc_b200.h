@@ -119,6 +119,8 @@ int cemc_set_generic_path(cemc_handle *h, int on);
 /* trial moves evaluated speculatively per batch by the batch kernel
  * (cemc_batch_kernel.cuh): 0 = auto, 4/8/16, -1 = one move at a time           */
 int cemc_set_batch(cemc_handle *h, int b);
+/* testing hook: 0 = do not use the binary spin kernel (cemc_spin_kernel.cuh)   */
+int cemc_set_spin_kernel(cemc_handle *h, int on);
 /* testing hook: widen the band in which the batch kernel's Metropolis screen
  * defers to the exact expression (factor >= 1; 1e30 = always exact)           */
 int cemc_set_screen_slack(cemc_handle *h, double factor);

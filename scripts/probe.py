@@ -42,12 +42,13 @@ if __name__ == "__main__":
         T = np.linspace(200, 1000, 16); mu = np.linspace(-1.1, -0.9, 16)
         kTs = np.repeat(T * KB, 16); mus = np.tile(mu, 16)
         ft, gpu = setup(10, ["Al", "Mg"], {"Al": 0.5, "Mg": 0.5}, 256, kTs, mus * 0.0)
-        for th in threads:
-            gpu.set_block_threads(th)
+        for spin in (True, False):
+          for bt in (batches if not spin else [0]):
+            gpu.set_spin_kernel(spin); gpu.set_batch(bt)
             n = 50000
             ms = timeit(gpu, gpu.run_sgc, n)
-            print("C2 sgc binary L=10 R=256 threads=%d n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
-                th, n, ms, 256 * n / ms / 1e3, ms * 1e6 / n))
+            print("C2 sgc binary L=10 R=256 spin=%s batch=%d n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
+                spin, bt, n, ms, 256 * n / ms / 1e3, ms * 1e6 / n))
         st, acc = gpu.get_counters(); print("  accept rate", acc.sum() / st.sum())
     if "c3" in which:
         kTs = np.linspace(300, 900, 64) * KB
@@ -63,3 +64,19 @@ if __name__ == "__main__":
             ms = timeit(gpu, gpu.run_sgc, n)
             print("C3-lattice sgc ternary batch=%d threads=%d: %.1f M moves/s (%.0f ns/move/chain)" % (bt, th, 64 * n / ms / 1e3, ms * 1e6 / n))
         st, acc = gpu.get_counters(); print("  accept rate", acc.sum() / st.sum())
+    if "c5" in which:
+        from cemc_b200 import workloads as wl
+        st = syn.fcc_settings(64, ["Al", "Mg"], ["nn", "2nn", "tri", "tet"])
+        eci = syn.synthetic_ecis(st)
+        syms = syn.random_symbols(st, {"Al": 0.9, "Mg": 0.1}, seed=1)
+        ft = FlatTables(st, eci, syms)
+        for R in (1, 8):
+            gpu = BatchedCEUpdater(ft, R)
+            gpu.set_occupancy(np.stack([ft.occupancy(syms)] * R)); gpu.recompute_cf(); gpu.set_kT(np.full(R, 0.03)); gpu.seed(5)
+            for bt in batches:
+                gpu.set_batch(bt)
+                for gen in (False, True):
+                    gpu.set_generic_path(gen)
+                    n = 20000
+                    ms = timeit(gpu, gpu.run_canonical, n)
+                    print("C5 64^3 binary canonical R=%d batch=%d generic=%s: %.2f M moves/s (%.0f ns/move/chain)" % (R, bt, gen, R * n / ms / 1e3, ms * 1e6 / n))
