@@ -60,6 +60,7 @@ SIGNATURES = {
     "cemc_set_block_threads": [_H, C.c_int],
     "cemc_set_generic_path": [_H, C.c_int],
     "cemc_set_batch": [_H, C.c_int],
+    "cemc_set_cluster": [_H, C.c_int],
     "cemc_set_spin_kernel": [_H, C.c_int],
     "cemc_set_screen_slack": [_H, C.c_double],
     "cemc_debug_phase_cycles": [_H, _u64p],

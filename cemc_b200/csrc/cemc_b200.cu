@@ -76,6 +76,8 @@ struct cemc_handle {
   bool force_generic = false;         // testing: disable the register-resident P3 and the spin kernel
   bool no_spin = false;               // testing: skip the binary spin kernel
   double screen_slack = 1.0;          // testing: widen the Metropolis screening band
+  int cluster = 0;                    // CTAs per chain in the batch kernel (0 = auto, 1, 2)
+  int n_sms = 148;
   int batch = 0;                      // moves evaluated speculatively per batch (0 = auto)
   bool spin_ok = false;               // binary +-1 basis: warp-per-replica spin kernel usable
   SpinTables spin{};
@@ -342,6 +344,7 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   if (stream) h->stream = (cudaStream_t)stream;
   else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
   CU(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  CU(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
 
@@ -700,6 +703,13 @@ int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8) {
 #endif
 }
 
+int cemc_set_cluster(cemc_handle *h, int c) {
+  if (!h) return fail("null handle");
+  if (c < 0 || c > 2) return fail("cluster size must be 0 (auto), 1 or 2");
+  h->cluster = c;
+  return 0;
+}
+
 int cemc_set_spin_kernel(cemc_handle *h, int on) {
   if (!h) return fail("null handle");
   h->no_spin = (on == 0);
@@ -876,22 +886,34 @@ static int launch_spin(cemc_handle *h, const RunArgs &a) {
   return -1;
 }
 
-template <int MODE, bool kTree, int B>
-static int launch_batch_b(cemc_handle *h, const RunArgs &a) {
-  size_t sm = batch_smem_layout<B>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, true);
-  const bool in_smem = sm <= (size_t)h->max_smem_optin;
-  if (!in_smem) sm = batch_smem_layout<B>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, false);
-  if (sm > (size_t)h->max_smem_optin) return -1;
-  if (in_smem) {
-    CU(cudaFuncSetAttribute(batch_kernel<MODE, kTree, B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    batch_kernel<MODE, kTree, B, true><<<h->R, B * 32, sm, h->stream>>>(h->t, h->st, a, h->acc_stride);
-  } else {
-    CU(cudaFuncSetAttribute(batch_kernel<MODE, kTree, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    batch_kernel<MODE, kTree, B, false><<<h->R, B * 32, sm, h->stream>>>(h->t, h->st, a, h->acc_stride);
-  }
+template <int MODE, bool kTree, int B, bool kSmem, int C>
+static int launch_batch_kc(cemc_handle *h, const RunArgs &a, size_t sm) {
+  auto kern = batch_kernel<MODE, kTree, B, kSmem, C>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(h->R * C);
+  cfg.blockDim = dim3(B * 32);
+  cfg.dynamicSmemBytes = sm;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = C > 1 ? 1 : 0;
+  CU(cudaLaunchKernelEx(&cfg, kern, h->t, h->st, a, h->acc_stride));
   h->launches++;
   CU(cudaGetLastError());
   return 0;
+}
+
+template <int MODE, bool kTree, int B, int C>
+static int launch_batch_b(cemc_handle *h, const RunArgs &a) {
+  size_t sm = batch_smem_layout<B, B * C>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, true);
+  const bool in_smem = sm <= (size_t)h->max_smem_optin;
+  if (!in_smem) sm = batch_smem_layout<B, B * C>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, false);
+  if (sm > (size_t)h->max_smem_optin) return -1;
+  return in_smem ? launch_batch_kc<MODE, kTree, B, true, C>(h, a, sm)
+                 : launch_batch_kc<MODE, kTree, B, false, C>(h, a, sm);
 }
 
 // speculative batch kernel; -1 when not applicable (caller falls back to mc_kernel)
@@ -901,10 +923,13 @@ static int launch_batch(cemc_handle *h, const RunArgs &a) {
       2 * h->t.KP > 64) return -1;
   const bool tree = (h->order_mode == CEMC_ORDER_TREE) || h->integer_bf;
   const int B = h->batch > 0 ? h->batch : 16;
+  // CTA clusters: 2 CTAs (SMs) per chain when that still fits the GPU in one wave
+  const int C = h->cluster > 0 ? h->cluster : (2 * h->R <= h->n_sms ? 2 : 1);
   int rc = -1;
-  if (B >= 16) rc = tree ? launch_batch_b<MODE, true, 16>(h, a) : launch_batch_b<MODE, false, 16>(h, a);
-  if (rc == -1 && B >= 8) rc = tree ? launch_batch_b<MODE, true, 8>(h, a) : launch_batch_b<MODE, false, 8>(h, a);
-  if (rc == -1) rc = tree ? launch_batch_b<MODE, true, 4>(h, a) : launch_batch_b<MODE, false, 4>(h, a);
+  if (C == 2 && B >= 16) rc = tree ? launch_batch_b<MODE, true, 16, 2>(h, a) : launch_batch_b<MODE, false, 16, 2>(h, a);
+  if (rc == -1 && B >= 16) rc = tree ? launch_batch_b<MODE, true, 16, 1>(h, a) : launch_batch_b<MODE, false, 16, 1>(h, a);
+  if (rc == -1 && B >= 8) rc = tree ? launch_batch_b<MODE, true, 8, 1>(h, a) : launch_batch_b<MODE, false, 8, 1>(h, a);
+  if (rc == -1) rc = tree ? launch_batch_b<MODE, true, 4, 1>(h, a) : launch_batch_b<MODE, false, 4, 1>(h, a);
   return rc;
 }
 

@@ -18,9 +18,20 @@
 //
 // Results are bit-identical to the one-move-at-a-time kernels (tested): the
 // arithmetic of each phase is the same code path, operation for operation.
+// CTA clusters (template parameter C > 1): C CTAs of one thread-block cluster work on
+// ONE chain.  Each CTA evaluates B moves of the batch (C*B <= 32 moves per batch);
+// proposals, per-ECI quotients, screens and conflict masks are written straight into
+// CTA 0's shared memory through distributed shared memory (DSMEM), CTA 0's warp 0
+// decides, and the commits go to every CTA's copy of the occupations (or to global
+// memory for supercells that do not fit).  barrier.cluster replaces __syncthreads.
+// This is the "large supercell / few replicas" mode: twice the evaluation
+// throughput for one chain, the exact sequential Markov chain is kept.
+//
 // Used when the CF vector fits one warp (<= 32 ECIs), one symmetry group, state
 // in shared memory; everything else runs mc_kernel.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "cemc_kernels.cuh"
 
 namespace cemc {
@@ -37,7 +48,8 @@ struct BatchSmem {
   int8_t *occ;
 };
 
-template <int B>
+// B = moves evaluated by this CTA, BT = moves per batch over the whole cluster
+template <int B, int BT = B>
 __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char *base,
                                                     const DeviceTables &t, bool canonical,
                                                     bool state_in_smem = true) {
@@ -53,16 +65,16 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(PO, double, B * nj * t.max_slots);
   CEMC_TAKE(PN, double, B * nj * t.max_slots);
   CEMC_TAKE(diff, double, B * nj * t.max_tasks);
-  CEMC_TAKE(sq, double, B * 2 * 32);
-  CEMC_TAKE(dEa, double, B);
-  CEMC_TAKE(Pm, double, B * 33);
-  CEMC_TAKE(Ch, double, B * 32);
+  CEMC_TAKE(sq, double, BT * 2 * 32);
+  CEMC_TAKE(dEa, double, BT);
+  CEMC_TAKE(Pm, double, BT * 33);
+  CEMC_TAKE(Ch, double, BT * 32);
   CEMC_TAKE(bf, double, t.D * t.S);
   CEMC_TAKE(items, unsigned long long, t.n_items_total);
   CEMC_TAKE(task_sum, int2, t.n_tasks_total);
   CEMC_TAKE(ring, uint4, 32 * 2);
-  CEMC_TAKE(prop, int32_t, B * 8);
-  CEMC_TAKE(cmask, int32_t, B);
+  CEMC_TAKE(prop, int32_t, BT * 8);
+  CEMC_TAKE(cmask, int32_t, BT);
   CEMC_TAKE(ctl, int32_t, 8);
   if (state_in_smem) {
     if (canonical) CEMC_TAKE(list, int32_t, t.N);
@@ -85,15 +97,21 @@ __device__ __forceinline__ int offs_of(const int (&offs)[9], int sp) {
 // One WARP evaluates one trial move; B warps = B moves per batch.
 // kStateSmem = false: occupations / site lists stay in global memory (L2): supercells
 // whose occupations do not fit in shared memory (64^3); the batch hides the latency.
-template <int MODE, bool kTree, int B, bool kStateSmem>
+template <int MODE, bool kTree, int B, bool kStateSmem, int C>
 __global__ void __launch_bounds__(B * 32, 1)
 batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  namespace cg = cooperative_groups;
   constexpr bool kCanon = (MODE == MODE_CANONICAL);
   constexpr int NJ = kCanon ? 2 : 1;
-  const int r = blockIdx.x;
+  constexpr int BT = B * C;                      // moves per batch over the whole cluster
+  static_assert(BT <= 32, "one decision lane per move");
+  const int crank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  const int r = blockIdx.x / C;
   const int tid = threadIdx.x, nthr = B * 32;
-  const int lane = tid & 31, warp = tid >> 5;
+  const int lane = tid & 31, lwarp = tid >> 5;
+  const int warp = crank * B + lwarp;            // cluster-wide warp index = move index
+  auto csync = [&]() { if (C > 1) cg::this_cluster().sync(); else __syncthreads(); };
   const int N = t.N, K = t.K, KP = t.KP, S = t.S, D = t.D, VS = t.VS, n_eci = t.n_eci;
   const int RB = D * KP;
   const int max_slots = t.max_slots, max_tasks = t.max_tasks;
@@ -104,8 +122,28 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   int32_t *g_list = st.list + (size_t)r * N;
   int32_t *g_loc = st.loc + (size_t)r * N;
   BatchSmem s;
-  batch_smem_layout<B>(&s, smem_raw, t, kCanon, kStateSmem);
+  batch_smem_layout<B, BT>(&s, smem_raw, t, kCanon, kStateSmem);
   if (!kStateSmem) { s.occ = g_occ; s.list = g_list; }
+  // CTA 0's copies of the arrays the deciding warp reads (DSMEM when C > 1)
+  BatchSmem s0 = s;
+  int8_t *occ_of[C];
+  int32_t *list_of[C], *prop_of[C], *ctl_of[C];
+  if (C > 1) {
+    cg::cluster_group cl = cg::this_cluster();
+    s0.prop = cl.map_shared_rank(s.prop, 0);
+    s0.sq = cl.map_shared_rank(s.sq, 0);
+    s0.dEa = cl.map_shared_rank(s.dEa, 0);
+    s0.cmask = cl.map_shared_rank(s.cmask, 0);
+#pragma unroll
+    for (int q = 0; q < C; q++) {
+      occ_of[q] = kStateSmem ? cl.map_shared_rank(s.occ, q) : g_occ;
+      list_of[q] = (kStateSmem && kCanon) ? cl.map_shared_rank(s.list, q) : g_list;
+      prop_of[q] = cl.map_shared_rank(s.prop, q);
+      ctl_of[q] = cl.map_shared_rank(s.ctl, q);
+    }
+  } else {
+    occ_of[0] = s.occ; list_of[0] = s.list; prop_of[0] = s.prop; ctl_of[0] = s.ctl;
+  }
 
   // ---- stage ----------------------------------------------------------------
   for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
@@ -137,7 +175,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
       return;
     }
   }
-  __syncthreads();
+  csync();
 
   // ---- lane i owns ECI i (every warp: per-ECI quotients; warp 0: CF vector) -------
   const double dN = (double)(unsigned)N;
@@ -191,11 +229,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   long long rbase = -(1LL << 40);      // first step held by the ring
 
   while (sdone < a.n_steps) {
-    const int nb = (int)((a.n_steps - sdone) < B ? (a.n_steps - sdone) : B);
+    const int nb = (int)((a.n_steps - sdone) < BT ? (a.n_steps - sdone) : BT);
     // ---- ring refill: proposals of steps [rbase, rbase + 32) ---------------------
     if (sdone + nb > rbase + 32) {
       rbase = sdone;
-      if (warp == 0) {
+      if (lwarp == 0) {                          // every CTA keeps its own copy of the ring
         const unsigned long long stp = step0 + (unsigned long long)rbase + lane;
         uint32_t c0 = (uint32_t)stp, c1 = (uint32_t)(stp >> 32), c2 = rep_global, c3 = 0;
         philox4x32_10(c0, c1, c2, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
@@ -254,9 +292,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
         site0 = s.list[slot0]; site1 = s.list[slot1];
         old0 = new1; old1 = new0;
       }
-      double *Vb = s.V + b * NJ * VS;
-      if (lane == 0) {
-        int32_t *pp = s.prop + b * 8;
+      double *Vb = s.V + lwarp * NJ * VS;
+      if (lane < C) {                            // every CTA gets the proposal (conflict masks)
+        int32_t *pp = prop_of[0] + b * 8;
+#pragma unroll
+        for (int q = 1; q < C; q++) if (lane == q) pp = prop_of[q] + b * 8;
         *reinterpret_cast<int4 *>(pp) = make_int4(site0, site1, new0, new1);
         *reinterpret_cast<int4 *>(pp + 4) = make_int4(old0, old1, slot0, slot1);
       }
@@ -286,7 +326,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
       }
       __syncwarp();
       // P2a: products
-      double *POb = s.PO + b * NJ * max_slots, *PNb = s.PN + b * NJ * max_slots;
+      double *POb = s.PO + lwarp * NJ * max_slots, *PNb = s.PN + lwarp * NJ * max_slots;
       for (int q = lane; q < NJ * n_items; q += 32) {
         const int j = q >= n_items;
         const unsigned long long w = s.items[j ? q - n_items : q];
@@ -307,7 +347,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
       }
       __syncwarp();
       // P2b: sums
-      double *db = s.diff + b * NJ * max_tasks;
+      double *db = s.diff + lwarp * NJ * max_tasks;
       for (int q = lane; q < NJ * n_tasks; q += 32) {
         const int j = q >= n_tasks;
         const int tk = j ? q - n_tasks : q;
@@ -359,17 +399,17 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
         }
         const double qa = exact_div(num0, f_den, f_rden);                     // :402
         const double qb = kCanon ? exact_div(num1, f_den, f_rden) : 0.0;
-        s.sq[(b * 2 + 0) * 32 + lane] = qa;
-        s.sq[(b * 2 + 1) * 32 + lane] = qb;
+        s0.sq[(b * 2 + 0) * 32 + lane] = qa;
+        s0.sq[(b * 2 + 1) * 32 + lane] = qb;
         // state-independent energy change of this move, N * sum_i eci_i (q0_i + q1_i):
         // only used to SCREEN the Metropolis test (any summation order will do)
         double de = f_kind > 0 ? eci_reg * (qa + qb) : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
-        if (lane == 0) s.dEa[b] = de * dN;
+        if (lane == 0) s0.dEa[b] = de * dN;
       }
     }
-    __syncthreads();
+    csync();
     CEMC_TICK(1);
 
     // ---- E2: which earlier moves of the batch would invalidate this evaluation? -------
@@ -380,9 +420,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
         const bool hit = (gsx[0] == sk0) | (gsx[1] == sk0) | (kCanon & ((gsx[0] == sk1) | (gsx[1] == sk1)));
         if (__ballot_sync(0xffffffffu, hit)) m |= 1u << k;
       }
-      if (lane == 0) s.cmask[warp] = (int32_t)m;
+      if (lane == 0) s0.cmask[warp] = (int32_t)m;
     }
-    __syncthreads();
+    csync();
     CEMC_TICK(2);
 
     // ---- D: warp 0 decides the moves strictly in order ---------------------------------
@@ -524,12 +564,15 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
         const int4 pa = *reinterpret_cast<const int4 *>(s.prop + lane * 8);
         const int4 pb = *reinterpret_cast<const int4 *>(s.prop + lane * 8 + 4);
         if (my_acc) {
-          s.occ[pa.x] = (int8_t)pa.z;
-          if (kCanon) {                        // swap_move_index_tracker.py:39-59
-            s.occ[pa.y] = (int8_t)pa.w;
-            s.list[pb.z] = pa.y; s.list[pb.w] = pa.x;
-            g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z);
+#pragma unroll
+          for (int q = 0; q < (kStateSmem ? C : 1); q++) {       // every CTA's copy of the state
+            occ_of[q][pa.x] = (int8_t)pa.z;
+            if (kCanon) {                      // swap_move_index_tracker.py:39-59
+              occ_of[q][pa.y] = (int8_t)pa.w;
+              list_of[q][pb.z] = pa.y; list_of[q][pb.w] = pa.x;
+            }
           }
+          if (kCanon) { g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z); }
         }
         if (tracing && sdone + lane < a.tr_capacity) {
           const size_t q = (size_t)r * a.tr_capacity + (size_t)(sdone + lane);
@@ -540,16 +583,21 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
           if (a.tr_e) a.tr_e[q] = E_after;
         }
       }
-      if (!kStateSmem) __threadfence_block();
-      if (lane == 0) s.ctl[0] = ndone;
+      if (!kStateSmem) { if (C > 1) __threadfence(); else __threadfence_block(); }
+      if (lane < C) {
+        int32_t *cp = ctl_of[0];
+#pragma unroll
+        for (int q = 1; q < C; q++) if (lane == q) cp = ctl_of[q];
+        cp[0] = ndone;
+      }
       CEMC_TICK(3);
 #ifdef CEMC_PHASE_TIMING
       if (tid == 0) { tph[8] += 1; tph[9] += ndone; }
 #endif
     }
-    __syncthreads();
+    csync();
     sdone += s.ctl[0];
-    __syncthreads();
+    csync();
     CEMC_TICK(4);
   }
 
@@ -569,7 +617,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
       st.accepted[r] += n_acc;
     }
   }
-  if (kStateSmem) {
+  if (kStateSmem && crank == 0) {
     for (int i = tid; i < N; i += nthr) g_occ[i] = s.occ[i];
     if (kCanon) for (int i = tid; i < N; i += nthr) g_list[i] = s.list[i];
   }

@@ -147,6 +147,9 @@ class BatchedCEUpdater(object):
     def set_spin_kernel(self, on: bool):
         _lib.check(self.lib.cemc_set_spin_kernel(self._h, int(bool(on))))
 
+    def set_cluster(self, c: int):
+        _lib.check(self.lib.cemc_set_cluster(self._h, int(c)))
+
     def set_batch(self, b: int):
         _lib.check(self.lib.cemc_set_batch(self._h, int(b)))
 

@@ -119,6 +119,9 @@ int cemc_set_generic_path(cemc_handle *h, int on);
 /* trial moves evaluated speculatively per batch by the batch kernel
  * (cemc_batch_kernel.cuh): 0 = auto, 4/8/16, -1 = one move at a time           */
 int cemc_set_batch(cemc_handle *h, int b);
+/* CTAs (SMs) of one thread-block cluster that cooperate on ONE chain in the batch
+ * kernel: 0 = auto (2 when 2 x replicas still fit the GPU in one wave), 1, 2   */
+int cemc_set_cluster(cemc_handle *h, int c);
 /* testing hook: 0 = do not use the binary spin kernel (cemc_spin_kernel.cuh)   */
 int cemc_set_spin_kernel(cemc_handle *h, int on);
 /* testing hook: widen the band in which the batch kernel's Metropolis screen

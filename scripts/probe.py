@@ -54,15 +54,15 @@ if __name__ == "__main__":
         kTs = np.linspace(300, 900, 64) * KB
         ft, gpu = setup(20, ["Al", "Mg", "Si"], {"Al": 0.8, "Mg": 0.1, "Si": 0.1}, 64, kTs)
         for bt in batches:
-          for th in threads:
-            gpu.set_block_threads(th)
+          for th in (1, 2):
+            gpu.set_cluster(th)
             gpu.set_batch(bt)
             n = 50000
             ms = timeit(gpu, gpu.run_canonical, n)
-            print("C3 canonical ternary L=20 R=64 batch=%d threads=%d n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
+            print("C3 canonical ternary L=20 R=64 batch=%d cluster=%d n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (
                 bt, th, n, ms, 64 * n / ms / 1e3, ms * 1e6 / n))
             ms = timeit(gpu, gpu.run_sgc, n)
-            print("C3-lattice sgc ternary batch=%d threads=%d: %.1f M moves/s (%.0f ns/move/chain)" % (bt, th, 64 * n / ms / 1e3, ms * 1e6 / n))
+            print("C3-lattice sgc ternary batch=%d cluster=%d: %.1f M moves/s (%.0f ns/move/chain)" % (bt, th, 64 * n / ms / 1e3, ms * 1e6 / n))
         st, acc = gpu.get_counters(); print("  accept rate", acc.sum() / st.sum())
     if "c5" in which:
         from cemc_b200 import workloads as wl
@@ -75,8 +75,8 @@ if __name__ == "__main__":
             gpu.set_occupancy(np.stack([ft.occupancy(syms)] * R)); gpu.recompute_cf(); gpu.set_kT(np.full(R, 0.03)); gpu.seed(5)
             for bt in batches:
                 gpu.set_batch(bt)
-                for gen in (False, True):
-                    gpu.set_generic_path(gen)
+                for cl in (1, 2):
+                    gpu.set_cluster(cl)
                     n = 20000
                     ms = timeit(gpu, gpu.run_canonical, n)
-                    print("C5 64^3 binary canonical R=%d batch=%d generic=%s: %.2f M moves/s (%.0f ns/move/chain)" % (R, bt, gen, R * n / ms / 1e3, ms * 1e6 / n))
+                    print("C5 64^3 binary canonical R=%d batch=%d cluster=%d: %.2f M moves/s (%.0f ns/move/chain)" % (R, bt, cl, R * n / ms / 1e3, ms * 1e6 / n))

@@ -526,3 +526,31 @@ def test_large_cell_global_state(cuda_device, species, conc):
     # from-scratch CFs agree with the incrementally updated ones at this size
     gpu.recompute_cf()
     np.testing.assert_allclose(gpu.get_cf()[0], oc.cf, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+def test_cta_cluster_batch_kernel(cuda_device, cluster, mode):
+    """Two CTAs of a thread-block cluster cooperating on one chain (DSMEM exchange
+    of proposals / quotients / conflict masks, commits to both copies of the
+    state): same trajectory as the oracle, for state in shared memory (4^3, 3^3)
+    and in global memory (64^3 is covered by test_large_cell_global_state)."""
+    for case, R in ((TERNARY, 3), (dict(TERNARY, L=3), 2)):
+        st, eci, symbols, ft = build(**case)
+        kTs = np.linspace(0.02, 0.2, R)
+        gpu, chains = make_pair(ft, [symbols] * R, kTs, seed=61)
+        gpu.set_cluster(cluster)
+        n = 1200
+        gpu.set_trace(n)
+        gpu.reset_accumulators()
+        (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+        gpu.synchronize()
+        tr = gpu.get_trace(n)
+        for r, c in enumerate(chains):
+            o = c.run_sgc(n, trace=True) if mode == "sgc" else c.run_canonical(n, trace=True)
+            assert np.array_equal(tr[0][r], o[0]) and np.array_equal(tr[3][r], o[3])
+            assert np.array_equal(tr[4][r], o[4])
+        assert_state_equal(gpu, chains)
+        accs = gpu.get_accumulators()
+        for r, c in enumerate(chains):
+            assert np.array_equal(accs[r], c.acc)
