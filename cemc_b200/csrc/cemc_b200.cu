@@ -892,7 +892,7 @@ static int launch_batch_kc(cemc_handle *h, const RunArgs &a, size_t sm) {
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(h->R * C);
-  cfg.blockDim = dim3(B * 32);
+  cfg.blockDim = dim3((B + 1) * 32);
   cfg.dynamicSmemBytes = sm;
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];

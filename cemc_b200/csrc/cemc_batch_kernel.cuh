@@ -37,7 +37,7 @@
 namespace cemc {
 
 struct BatchSmem {
-  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *Pm, *Ch;
+  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *Pm, *Ch, *obE;
   unsigned long long *items;
   int2 *task_sum;
   uint4 *ring;              // [32][2]: proposal; uniform + Metropolis threshold
@@ -69,6 +69,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(dEa, double, BT);
   CEMC_TAKE(Pm, double, BT * 33);
   CEMC_TAKE(Ch, double, BT * 32);
+  CEMC_TAKE(obE, double, BT);
   CEMC_TAKE(bf, double, t.D * t.S);
   CEMC_TAKE(items, unsigned long long, t.n_items_total);
   CEMC_TAKE(task_sum, int2, t.n_tasks_total);
@@ -97,8 +98,12 @@ __device__ __forceinline__ int offs_of(const int (&offs)[9], int sp) {
 // One WARP evaluates one trial move; B warps = B moves per batch.
 // kStateSmem = false: occupations / site lists stay in global memory (L2): supercells
 // whose occupations do not fit in shared memory (64^3); the batch hides the latency.
+// The CTA has B evaluation warps plus one OBSERVER warp (CTA 0 only does work in
+// it): it folds the decided moves of batch k into the Averager / SGCObserver sums
+// while the evaluation warps are already busy with batch k+1, which takes the
+// per-move observer arithmetic off the deciding warp.
 template <int MODE, bool kTree, int B, bool kStateSmem, int C>
-__global__ void __launch_bounds__(B * 32, 1)
+__global__ void __launch_bounds__((B + 1) * 32, 1)
 batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   namespace cg = cooperative_groups;
@@ -108,9 +113,10 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   static_assert(BT <= 32, "one decision lane per move");
   const int crank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int r = blockIdx.x / C;
-  const int tid = threadIdx.x, nthr = B * 32;
+  const int tid = threadIdx.x, nthr = (B + 1) * 32;
   const int lane = tid & 31, lwarp = tid >> 5;
-  const int warp = crank * B + lwarp;            // cluster-wide warp index = move index
+  const bool is_obs = (lwarp == B);              // the observer warp (works in CTA 0 only)
+  const int warp = is_obs ? 1000 : crank * B + lwarp;   // cluster-wide move index of an evaluation warp
   auto csync = [&]() { if (C > 1) cg::this_cluster().sync(); else __syncthreads(); };
   const int N = t.N, K = t.K, KP = t.KP, S = t.S, D = t.D, VS = t.VS, n_eci = t.n_eci;
   const int RB = D * KP;
@@ -193,11 +199,12 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
     cf_reg = st.cf[(size_t)r * n_eci + lane];
     for (int d = 0; d < t.n_singlets; d++) if (t.singlet_idx[d] == lane) my_singlet = d;
   }
-  if (warp == 0) {
+  if (is_obs && crank == 0) {
     const double *ag = st.acc + (size_t)r * acc_stride;
     if (my_singlet >= 0) { aS0 = ag[3 + 3 * my_singlet]; aS1 = ag[4 + 3 * my_singlet]; aS2 = ag[5 + 3 * my_singlet]; }
     aE0 = ag[0]; aE1 = ag[1]; aE2 = ag[2];
   }
+  int ob_pending = 0;                  // decided moves of the previous batch still to observe
   double e_cur = st.e_cur[r];
   const double kT = st.kT[r];
   const double rkT = __ddiv_rn(1.0, kT);
@@ -268,6 +275,39 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
     }
     CEMC_TICK(0);
 
+    // ---- observer warp: Averager / SGCObserver sums of the previous batch ---------------
+    // (montecarlo.py:811-814, mc_observers.py:264-270), in move order, while the
+    // evaluation warps work on the next batch
+    if (is_obs && crank == 0 && observe && ob_pending > 0) {
+      int b = 0;
+      for (; b + 3 < ob_pending; b += 4) {
+        double Eb[4], cb[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) { Eb[x] = s.obE[b + x]; cb[x] = s.Ch[(b + x) * 32 + lane]; }
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          const double e2 = __dmul_rn(Eb[x], Eb[x]);
+          aE0 = __dadd_rn(aE0, 1.0);
+          aE1 = __dadd_rn(aE1, ref_is_one ? Eb[x] : exact_div(Eb[x], ref, rref));
+          aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
+          aS0 = __dadd_rn(aS0, cb[x]);
+          aS1 = __dadd_rn(aS1, __dmul_rn(cb[x], cb[x]));
+          aS2 = __dadd_rn(aS2, __dmul_rn(cb[x], Eb[x]));
+        }
+      }
+      for (; b < ob_pending; b++) {
+        const double Eb = s.obE[b];
+        const double cb = s.Ch[b * 32 + lane];
+        const double e2 = __dmul_rn(Eb, Eb);
+        aE0 = __dadd_rn(aE0, 1.0);
+        aE1 = __dadd_rn(aE1, ref_is_one ? Eb : exact_div(Eb, ref, rref));
+        aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
+        aS0 = __dadd_rn(aS0, cb);
+        aS1 = __dadd_rn(aS1, __dmul_rn(cb, cb));
+        aS2 = __dadd_rn(aS2, __dmul_rn(cb, Eb));
+      }
+    }
+    ob_pending = 0;
     // ---- E1: warp b evaluates move sdone + b against the current state --------------
     int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check); host: NJ*KP <= 64
     if (warp < nb) {
@@ -529,35 +569,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
         cf_reg = c;
         n_acc += __popc(accmask);
       }
-      if (observe) {                                               // montecarlo.py:811-814,
-        int b = 0;                                                 // mc_observers.py:264-270
-        for (; b + 3 < ndone; b += 4) {
-          double Eb[4], cb[4];
-#pragma unroll
-          for (int x = 0; x < 4; x++) { Eb[x] = __shfl_sync(0xffffffffu, E_after, b + x); cb[x] = s.Ch[(b + x) * 32 + lane]; }
-#pragma unroll
-          for (int x = 0; x < 4; x++) {
-            const double e2 = __dmul_rn(Eb[x], Eb[x]);
-            aE0 = __dadd_rn(aE0, 1.0);
-            aE1 = __dadd_rn(aE1, ref_is_one ? Eb[x] : exact_div(Eb[x], ref, rref));
-            aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
-            aS0 = __dadd_rn(aS0, cb[x]);
-            aS1 = __dadd_rn(aS1, __dmul_rn(cb[x], cb[x]));
-            aS2 = __dadd_rn(aS2, __dmul_rn(cb[x], Eb[x]));
-          }
-        }
-        for (; b < ndone; b++) {
-          const double Eb = __shfl_sync(0xffffffffu, E_after, b);
-          const double cb = s.Ch[b * 32 + lane];
-          const double e2 = __dmul_rn(Eb, Eb);
-          aE0 = __dadd_rn(aE0, 1.0);
-          aE1 = __dadd_rn(aE1, ref_is_one ? Eb : exact_div(Eb, ref, rref));
-          aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
-          aS0 = __dadd_rn(aS0, cb);
-          aS1 = __dadd_rn(aS1, __dmul_rn(cb, cb));
-          aS2 = __dadd_rn(aS2, __dmul_rn(cb, Eb));
-        }
-      }
+      if (lane < ndone) s.obE[lane] = E_after;      // the observer warp folds these in during the next E1
       // commits of the decided moves: lane b applies move b (accepted moves of one
       // batch never share a site, so the order among them is irrelevant)
       if (lane < ndone) {
@@ -597,20 +609,56 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
     }
     csync();
     sdone += s.ctl[0];
+    ob_pending = s.ctl[0];
     csync();
     CEMC_TICK(4);
   }
+  // ---- observer warp: Averager / SGCObserver sums of the previous batch ---------------
+  // (montecarlo.py:811-814, mc_observers.py:264-270), in move order, while the
+  // evaluation warps work on the next batch
+  if (is_obs && crank == 0 && observe && ob_pending > 0) {
+    int b = 0;
+    for (; b + 3 < ob_pending; b += 4) {
+      double Eb[4], cb[4];
+#pragma unroll
+      for (int x = 0; x < 4; x++) { Eb[x] = s.obE[b + x]; cb[x] = s.Ch[(b + x) * 32 + lane]; }
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        const double e2 = __dmul_rn(Eb[x], Eb[x]);
+        aE0 = __dadd_rn(aE0, 1.0);
+        aE1 = __dadd_rn(aE1, ref_is_one ? Eb[x] : exact_div(Eb[x], ref, rref));
+        aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
+        aS0 = __dadd_rn(aS0, cb[x]);
+        aS1 = __dadd_rn(aS1, __dmul_rn(cb[x], cb[x]));
+        aS2 = __dadd_rn(aS2, __dmul_rn(cb[x], Eb[x]));
+      }
+    }
+    for (; b < ob_pending; b++) {
+      const double Eb = s.obE[b];
+      const double cb = s.Ch[b * 32 + lane];
+      const double e2 = __dmul_rn(Eb, Eb);
+      aE0 = __dadd_rn(aE0, 1.0);
+      aE1 = __dadd_rn(aE1, ref_is_one ? Eb : exact_div(Eb, ref, rref));
+      aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
+      aS0 = __dadd_rn(aS0, cb);
+      aS1 = __dadd_rn(aS1, __dmul_rn(cb, cb));
+      aS2 = __dadd_rn(aS2, __dmul_rn(cb, Eb));
+    }
+  }
+
 
 #ifdef CEMC_PHASE_TIMING
   if (tid == 0 && r == 0)
     for (int i = 0; i < 16; i++) g_phase_cycles[i] = tph[i];
 #endif
   // ---- write back ------------------------------------------------------------
-  if (warp == 0) {
-    if (lane < n_eci) st.cf[(size_t)r * n_eci + lane] = cf_reg;
+  if (is_obs && crank == 0) {
     double *aw = st.acc + (size_t)r * acc_stride;
     if (lane == 0) { aw[0] = aE0; aw[1] = aE1; aw[2] = aE2; }
     if (my_singlet >= 0) { aw[3 + 3 * my_singlet] = aS0; aw[4 + 3 * my_singlet] = aS1; aw[5 + 3 * my_singlet] = aS2; }
+  }
+  if (warp == 0) {
+    if (lane < n_eci) st.cf[(size_t)r * n_eci + lane] = cf_reg;
     if (lane == 0) {
       st.e_cur[r] = e_cur;
       st.step[r] = step0 + (unsigned long long)a.n_steps;
