@@ -61,6 +61,8 @@ SIGNATURES = {
     "cemc_set_generic_path": [_H, C.c_int],
     "cemc_set_batch": [_H, C.c_int],
     "cemc_set_cluster": [_H, C.c_int],
+    "cemc_set_autotune": [_H, C.c_int],
+    "cemc_get_variant": [_H, _i32p, _i32p],
     "cemc_set_spin_kernel": [_H, C.c_int],
     "cemc_set_screen_slack": [_H, C.c_double],
     "cemc_debug_phase_cycles": [_H, _u64p],

@@ -76,6 +76,8 @@ struct cemc_handle {
   bool force_generic = false;         // testing: disable the register-resident P3 and the spin kernel
   bool no_spin = false;               // testing: skip the binary spin kernel
   double screen_slack = 1.0;          // testing: widen the Metropolis screening band
+  bool autotune = true;               // pick the fastest kernel variant on long runs
+  int tuned_sgc = -1, tuned_can = -1;  // variant chosen by the autotuner
   int cluster = 0;                    // CTAs per chain in the batch kernel (0 = auto, 1, 2)
   int n_sms = 148;
   int batch = 0;                      // moves evaluated speculatively per batch (0 = auto)
@@ -703,9 +705,24 @@ int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8) {
 #endif
 }
 
+int cemc_set_autotune(cemc_handle *h, int on) {
+  if (!h) return fail("null handle");
+  h->autotune = on != 0;
+  h->tuned_sgc = h->tuned_can = -1;
+  return 0;
+}
+
+int cemc_get_variant(cemc_handle *h, int *sgc, int *canonical) {
+  if (!h) return fail("null handle");
+  if (sgc) *sgc = h->tuned_sgc;
+  if (canonical) *canonical = h->tuned_can;
+  return 0;
+}
+
 int cemc_set_cluster(cemc_handle *h, int c) {
   if (!h) return fail("null handle");
   if (c < 0 || c > 2) return fail("cluster size must be 0 (auto), 1 or 2");
+  h->tuned_sgc = h->tuned_can = -1;
   h->cluster = c;
   return 0;
 }
@@ -713,6 +730,7 @@ int cemc_set_cluster(cemc_handle *h, int c) {
 int cemc_set_spin_kernel(cemc_handle *h, int on) {
   if (!h) return fail("null handle");
   h->no_spin = (on == 0);
+  h->tuned_sgc = h->tuned_can = -1;
   return 0;
 }
 
@@ -726,6 +744,7 @@ int cemc_set_screen_slack(cemc_handle *h, double factor) {
 int cemc_set_batch(cemc_handle *h, int b) {
   if (!h) return fail("null handle");
   if (!(b == -1 || b == 0 || b == 4 || b == 8 || b == 16)) return fail("batch must be -1 (off), 0 (auto), 4, 8 or 16");
+  h->tuned_sgc = h->tuned_can = -1;
   h->batch = b;
   return 0;
 }
@@ -733,6 +752,7 @@ int cemc_set_batch(cemc_handle *h, int b) {
 int cemc_set_generic_path(cemc_handle *h, int on) {
   if (!h) return fail("null handle");
   h->force_generic = on != 0;
+  h->tuned_sgc = h->tuned_can = -1;
   return 0;
 }
 
@@ -916,21 +936,95 @@ static int launch_batch_b(cemc_handle *h, const RunArgs &a) {
                  : launch_batch_kc<MODE, kTree, B, false, C>(h, a, sm);
 }
 
-// speculative batch kernel; -1 when not applicable (caller falls back to mc_kernel)
+static RunArgs run_args(cemc_handle *h, long long n_steps) {
+  RunArgs a{};
+  a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset;
+  a.observe = 1;
+  a.screen_slack = h->screen_slack;
+  if (h->trace_capacity > 0) {
+    a.tr_sites = h->tr_sites; a.tr_news = h->tr_news; a.tr_u = h->tr_u; a.tr_acc = h->tr_acc;
+    a.tr_e = h->tr_e; a.tr_capacity = h->trace_capacity;
+  }
+  return a;
+}
+
+// speculative batch kernel with B moves per CTA and C CTAs per chain; -1 when not applicable
 template <int MODE>
-static int launch_batch(cemc_handle *h, const RunArgs &a) {
+static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C) {
   if (h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
       2 * h->t.KP > 64) return -1;
   const bool tree = (h->order_mode == CEMC_ORDER_TREE) || h->integer_bf;
-  const int B = h->batch > 0 ? h->batch : 16;
-  // CTA clusters: 2 CTAs (SMs) per chain when that still fits the GPU in one wave
-  const int C = h->cluster > 0 ? h->cluster : (2 * h->R <= h->n_sms ? 2 : 1);
-  int rc = -1;
-  if (C == 2 && B >= 16) rc = tree ? launch_batch_b<MODE, true, 16, 2>(h, a) : launch_batch_b<MODE, false, 16, 2>(h, a);
-  if (rc == -1 && B >= 16) rc = tree ? launch_batch_b<MODE, true, 16, 1>(h, a) : launch_batch_b<MODE, false, 16, 1>(h, a);
-  if (rc == -1 && B >= 8) rc = tree ? launch_batch_b<MODE, true, 8, 1>(h, a) : launch_batch_b<MODE, false, 8, 1>(h, a);
-  if (rc == -1) rc = tree ? launch_batch_b<MODE, true, 4, 1>(h, a) : launch_batch_b<MODE, false, 4, 1>(h, a);
-  return rc;
+  if (B == 16 && C == 2) return tree ? launch_batch_b<MODE, true, 16, 2>(h, a) : launch_batch_b<MODE, false, 16, 2>(h, a);
+  if (B == 16 && C == 1) return tree ? launch_batch_b<MODE, true, 16, 1>(h, a) : launch_batch_b<MODE, false, 16, 1>(h, a);
+  if (B == 8 && C == 1) return tree ? launch_batch_b<MODE, true, 8, 1>(h, a) : launch_batch_b<MODE, false, 8, 1>(h, a);
+  if (B == 4 && C == 1) return tree ? launch_batch_b<MODE, true, 4, 1>(h, a) : launch_batch_b<MODE, false, 4, 1>(h, a);
+  return -1;
+}
+
+// Kernel variants of one sampler.  All of them produce the same trajectory bit for
+// bit, so the choice is a pure performance knob: 0 spin, 1..4 batch (B,C) =
+// (16,2) (16,1) (8,1) (4,1), 5 one move at a time (mc_kernel, always applicable).
+static const int kNumVariants = 6;
+
+template <int MODE>
+static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
+  switch (v) {
+    case 0: return launch_spin<MODE>(h, a);
+    case 1: return (2 * h->R <= h->n_sms || h->cluster == 2) ? launch_batch<MODE>(h, a, 16, 2) : -1;
+    case 2: return launch_batch<MODE>(h, a, 16, 1);
+    case 3: return launch_batch<MODE>(h, a, 8, 1);
+    case 4: return launch_batch<MODE>(h, a, 4, 1);
+    default: return launch_mc<MODE>(h, a, 0, h->R);
+  }
+}
+
+static bool variant_allowed(const cemc_handle *h, int v) {
+  if (v >= 1 && v <= 4) {
+    static const int Bs[5] = {0, 16, 16, 8, 4}, Cs[5] = {0, 2, 1, 1, 1};
+    if (h->batch > 0 && h->batch != Bs[v]) return false;
+    if (h->cluster > 0 && h->cluster != Cs[v]) return false;
+  }
+  return true;
+}
+
+// Run n_steps with the preferred variant; on long runs without a trace, time the
+// applicable variants on short segments of the run itself (productive work, the
+// trajectory does not depend on the variant) and keep the fastest.
+template <int MODE>
+static int run_tuned(cemc_handle *h, long long n_steps) {
+  int &best = (MODE == MODE_SGC) ? h->tuned_sgc : h->tuned_can;
+  const long long seg = 4096;
+  long long done = 0;
+  if (best < 0 && h->autotune && h->trace_capacity == 0 && n_steps >= 16 * seg) {
+    float best_ms = 1e30f;
+    for (int v = 0; v < kNumVariants; v++) {
+      if (!variant_allowed(h, v)) continue;
+      RunArgs a = run_args(h, seg);
+      CU(cudaEventRecord(h->ev0, h->stream));
+      const int rc = launch_variant<MODE>(h, a, v);
+      if (rc == -1) continue;
+      if (rc) return rc;
+      CU(cudaEventRecord(h->ev1, h->stream));
+      CU(cudaEventSynchronize(h->ev1));
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      done += seg;
+      if (ms < best_ms) { best_ms = ms; best = v; }
+      if (v == 0) break;      // the spin kernel, when applicable, is the specialised path
+    }
+  }
+  if (done >= n_steps) return 0;
+  RunArgs a = run_args(h, n_steps - done);
+  if (best >= 0) {
+    const int rc = launch_variant<MODE>(h, a, best);
+    if (rc != -1) return rc;
+  }
+  for (int v = 0; v < kNumVariants; v++) {          // default preference order
+    if (!variant_allowed(h, v)) continue;
+    const int rc = launch_variant<MODE>(h, a, v);
+    if (rc != -1) return rc;
+  }
+  return fail("no kernel variant applicable");
 }
 
 static int ensure_scratch(cemc_handle *h, long long n_steps) {
@@ -975,17 +1069,6 @@ int cemc_replay(cemc_handle *h, int n_steps, const int32_t *sites, const int8_t 
   return check_status(h);
 }
 
-static RunArgs run_args(cemc_handle *h, long long n_steps) {
-  RunArgs a{};
-  a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset;
-  a.observe = 1;
-  a.screen_slack = h->screen_slack;
-  if (h->trace_capacity > 0) {
-    a.tr_sites = h->tr_sites; a.tr_news = h->tr_news; a.tr_u = h->tr_u; a.tr_acc = h->tr_acc;
-    a.tr_e = h->tr_e; a.tr_capacity = h->trace_capacity;
-  }
-  return a;
-}
 
 int cemc_run_sgc(cemc_handle *h, int64_t n_steps) {
   if (!h) return fail("null handle");
@@ -993,10 +1076,7 @@ int cemc_run_sgc(cemc_handle *h, int64_t n_steps) {
   CU(cudaSetDevice(h->device));
   drop_trials(h);
   h->tracker_dirty = true;
-  const RunArgs a = run_args(h, n_steps);
-  int rc = launch_spin<MODE_SGC>(h, a);
-  if (rc == -1) rc = launch_batch<MODE_SGC>(h, a);
-  return rc >= 0 ? rc : launch_mc<MODE_SGC>(h, a, 0, h->R);
+  return run_tuned<MODE_SGC>(h, n_steps);
 }
 
 int cemc_run_canonical(cemc_handle *h, int64_t n_steps) {
@@ -1005,10 +1085,7 @@ int cemc_run_canonical(cemc_handle *h, int64_t n_steps) {
   CU(cudaSetDevice(h->device));
   drop_trials(h);
   { const int rc0 = ensure_tracker(h); if (rc0) return rc0; }
-  const RunArgs a = run_args(h, n_steps);
-  int rc = launch_spin<MODE_CANONICAL>(h, a);
-  if (rc == -1) rc = launch_batch<MODE_CANONICAL>(h, a);
-  return rc >= 0 ? rc : launch_mc<MODE_CANONICAL>(h, a, 0, h->R);
+  return run_tuned<MODE_CANONICAL>(h, n_steps);
 }
 
 // Checkpoint support: the per-species site lists of the canonical sampler

@@ -147,6 +147,14 @@ class BatchedCEUpdater(object):
     def set_spin_kernel(self, on: bool):
         _lib.check(self.lib.cemc_set_spin_kernel(self._h, int(bool(on))))
 
+    def set_autotune(self, on: bool):
+        _lib.check(self.lib.cemc_set_autotune(self._h, int(bool(on))))
+
+    def get_variant(self):
+        a, b = C.c_int32(-1), C.c_int32(-1)
+        _lib.check(self.lib.cemc_get_variant(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_cluster(self, c: int):
         _lib.check(self.lib.cemc_set_cluster(self._h, int(c)))
 

@@ -119,6 +119,12 @@ int cemc_set_generic_path(cemc_handle *h, int on);
 /* trial moves evaluated speculatively per batch by the batch kernel
  * (cemc_batch_kernel.cuh): 0 = auto, 4/8/16, -1 = one move at a time           */
 int cemc_set_batch(cemc_handle *h, int b);
+/* All kernel variants (spin / batch (B,C) / one move at a time) give the same
+ * trajectory bit for bit; on long runs the fastest one is measured on segments
+ * of the run itself.  cemc_get_variant: 0 spin, 1..4 batch (16,2) (16,1) (8,1)
+ * (4,1), 5 mc_kernel, -1 not tuned yet.                                        */
+int cemc_set_autotune(cemc_handle *h, int on);
+int cemc_get_variant(cemc_handle *h, int *sgc, int *canonical);
 /* CTAs (SMs) of one thread-block cluster that cooperate on ONE chain in the batch
  * kernel: 0 = auto (2 when 2 x replicas still fit the GPU in one wave), 1, 2   */
 int cemc_set_cluster(cemc_handle *h, int c);

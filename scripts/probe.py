@@ -64,6 +64,16 @@ if __name__ == "__main__":
             ms = timeit(gpu, gpu.run_sgc, n)
             print("C3-lattice sgc ternary batch=%d cluster=%d: %.1f M moves/s (%.0f ns/move/chain)" % (bt, th, 64 * n / ms / 1e3, ms * 1e6 / n))
         st, acc = gpu.get_counters(); print("  accept rate", acc.sum() / st.sum())
+    if "auto" in which:
+        from cemc_b200 import workloads as wl
+        for name in ("C2", "C3S", "C3", "C1"):
+            w = wl.WORKLOADS[name](R=64) if name == "C1" else wl.WORKLOADS[name]()
+            gpu = wl.make_updater(w)
+            run = gpu.run_sgc if w.mode == "sgc" else gpu.run_canonical
+            n = 100000
+            run(n); gpu.synchronize()
+            ms = timeit(gpu, run, n, reps=2)
+            print("%s autotuned variant %s: %.1f M moves/s (%.0f ns/move/chain)" % (name, gpu.get_variant(), w.R * n / ms / 1e3, ms * 1e6 / n))
     if "c5" in which:
         from cemc_b200 import workloads as wl
         st = syn.fcc_settings(64, ["Al", "Mg"], ["nn", "2nn", "tri", "tet"])

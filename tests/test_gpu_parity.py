@@ -554,3 +554,23 @@ def test_cta_cluster_batch_kernel(cuda_device, cluster, mode):
         accs = gpu.get_accumulators()
         for r, c in enumerate(chains):
             assert np.array_equal(accs[r], c.acc)
+
+
+def test_autotuned_long_run_is_invariant(cuda_device):
+    """A long run is split into timed segments of different kernel variants by the
+    autotuner: the trajectory must equal the oracle's regardless of the choice."""
+    st, eci, symbols, ft = build(**TERNARY)
+    gpu, chains = make_pair(ft, [symbols] * 2, [0.03, 0.07], seed=71)
+    n = 70000
+    gpu.reset_accumulators()
+    gpu.run_canonical(n)
+    gpu.run_sgc(n)
+    gpu.synchronize()
+    assert min(gpu.get_variant()) >= 0
+    for c in chains:
+        c.run_canonical(n)
+        c.run_sgc(n)
+    assert_state_equal(gpu, chains)
+    accs = gpu.get_accumulators()
+    for r, c in enumerate(chains):
+        assert np.array_equal(accs[r], c.acc)
