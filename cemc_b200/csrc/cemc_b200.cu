@@ -906,9 +906,9 @@ static int launch_spin(cemc_handle *h, const RunArgs &a) {
   return -1;
 }
 
-template <int MODE, bool kTree, int B, bool kSmem, int C>
+template <int MODE, bool kTree, int B, bool kSmem, int C, bool kSpin>
 static int launch_batch_kc(cemc_handle *h, const RunArgs &a, size_t sm) {
-  auto kern = batch_kernel<MODE, kTree, B, kSmem, C>;
+  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, kSpin>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(h->R * C);
@@ -920,20 +920,20 @@ static int launch_batch_kc(cemc_handle *h, const RunArgs &a, size_t sm) {
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = C > 1 ? 1 : 0;
-  CU(cudaLaunchKernelEx(&cfg, kern, h->t, h->st, a, h->acc_stride));
+  CU(cudaLaunchKernelEx(&cfg, kern, h->t, h->st, a, h->acc_stride, h->spin));
   h->launches++;
   CU(cudaGetLastError());
   return 0;
 }
 
-template <int MODE, bool kTree, int B, int C>
+template <int MODE, bool kTree, int B, int C, bool kSpin = false>
 static int launch_batch_b(cemc_handle *h, const RunArgs &a) {
   size_t sm = batch_smem_layout<B, B * C>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, true);
   const bool in_smem = sm <= (size_t)h->max_smem_optin;
   if (!in_smem) sm = batch_smem_layout<B, B * C>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, false);
   if (sm > (size_t)h->max_smem_optin) return -1;
-  return in_smem ? launch_batch_kc<MODE, kTree, B, true, C>(h, a, sm)
-                 : launch_batch_kc<MODE, kTree, B, false, C>(h, a, sm);
+  return in_smem ? launch_batch_kc<MODE, kTree, B, true, C, kSpin>(h, a, sm)
+                 : launch_batch_kc<MODE, kTree, B, false, C, kSpin>(h, a, sm);
 }
 
 static RunArgs run_args(cemc_handle *h, long long n_steps) {
@@ -954,6 +954,14 @@ static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C) {
   if (h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
       2 * h->t.KP > 64) return -1;
   const bool tree = (h->order_mode == CEMC_ORDER_TREE) || h->integer_bf;
+  if (h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4) {
+    // binary +-1 basis: spin evaluation inside the batch kernel
+    if (B == 16 && C == 2) return launch_batch_b<MODE, true, 16, 2, true>(h, a);
+    if (B == 16 && C == 1) return launch_batch_b<MODE, true, 16, 1, true>(h, a);
+    if (B == 8 && C == 1) return launch_batch_b<MODE, true, 8, 1, true>(h, a);
+    if (B == 4 && C == 1) return launch_batch_b<MODE, true, 4, 1, true>(h, a);
+    return -1;
+  }
   if (B == 16 && C == 2) return tree ? launch_batch_b<MODE, true, 16, 2>(h, a) : launch_batch_b<MODE, false, 16, 2>(h, a);
   if (B == 16 && C == 1) return tree ? launch_batch_b<MODE, true, 16, 1>(h, a) : launch_batch_b<MODE, false, 16, 1>(h, a);
   if (B == 8 && C == 1) return tree ? launch_batch_b<MODE, true, 8, 1>(h, a) : launch_batch_b<MODE, false, 8, 1>(h, a);
@@ -979,6 +987,7 @@ static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
 }
 
 static bool variant_allowed(const cemc_handle *h, int v) {
+  if (v == 0 && h->batch > 0) return false;       // an explicit batch size asks for the batch kernel
   if (v >= 1 && v <= 4) {
     static const int Bs[5] = {0, 16, 16, 8, 4}, Cs[5] = {0, 2, 1, 1, 1};
     if (h->batch > 0 && h->batch != Bs[v]) return false;
@@ -993,24 +1002,25 @@ static bool variant_allowed(const cemc_handle *h, int v) {
 template <int MODE>
 static int run_tuned(cemc_handle *h, long long n_steps) {
   int &best = (MODE == MODE_SGC) ? h->tuned_sgc : h->tuned_can;
-  const long long seg = 4096;
+  const long long seg = 2048;
   long long done = 0;
-  if (best < 0 && h->autotune && h->trace_capacity == 0 && n_steps >= 16 * seg) {
+  if (best < 0 && h->autotune && h->trace_capacity == 0 && n_steps >= 8 * seg) {
     float best_ms = 1e30f;
     for (int v = 0; v < kNumVariants; v++) {
       if (!variant_allowed(h, v)) continue;
-      RunArgs a = run_args(h, seg);
-      CU(cudaEventRecord(h->ev0, h->stream));
-      const int rc = launch_variant<MODE>(h, a, v);
+      // untimed warm-up launch (first-use costs of the variant), then the timed segment
+      int rc = launch_variant<MODE>(h, run_args(h, seg / 4), v);
       if (rc == -1) continue;
+      if (rc) return rc;
+      CU(cudaEventRecord(h->ev0, h->stream));
+      rc = launch_variant<MODE>(h, run_args(h, seg), v);
       if (rc) return rc;
       CU(cudaEventRecord(h->ev1, h->stream));
       CU(cudaEventSynchronize(h->ev1));
       float ms = 0.f;
       CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-      done += seg;
+      done += seg + seg / 4;
       if (ms < best_ms) { best_ms = ms; best = v; }
-      if (v == 0) break;      // the spin kernel, when applicable, is the specialised path
     }
   }
   if (done >= n_steps) return 0;

@@ -33,6 +33,7 @@
 #include <cooperative_groups.h>
 
 #include "cemc_kernels.cuh"
+#include "cemc_spin_kernel.cuh"
 
 namespace cemc {
 
@@ -102,9 +103,11 @@ __device__ __forceinline__ int offs_of(const int (&offs)[9], int sp) {
 // it): it folds the decided moves of batch k into the Averager / SGCObserver sums
 // while the evaluation warps are already busy with batch k+1, which takes the
 // per-move observer arithmetic off the deciding warp.
-template <int MODE, bool kTree, int B, bool kStateSmem, int C>
-__global__ void __launch_bounds__((B + 1) * 32, 1)
-batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
+// kSpin: binary +-1 basis -- the evaluation of a move is the XOR / ballot / popcount
+// scheme of cemc_spin_kernel.cuh instead of fp64 products (same quotients, bit for bit).
+template <int MODE, bool kTree, int B, bool kStateSmem, int C, bool kSpin>
+__global__ void __launch_bounds__((B + 1) * 32, (kSpin && B <= 8) ? 2 : 1)
+batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTables sp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   namespace cg = cooperative_groups;
   constexpr bool kCanon = (MODE == MODE_CANONICAL);
@@ -228,6 +231,29 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
     etol = 1e-13 * dN * sa * 16.0 * a.screen_slack;
   }
 
+  // kSpin: this lane's sub-clusters (decoded once) and its ECI's ballot masks
+  int sca[4], scb[4], scc[4];
+  uint32_t smb[4], smc[4], smv[4], smask[4];
+  int s_coef = 0, s_msub = 1;
+  const int s_rounds = kSpin ? sp.n_rounds : 0;
+  if (kSpin) {
+    s_coef = sp.coef[lane]; s_msub = sp.msub[lane];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int qi = q * 32 + lane;
+      const bool valid = qi < sp.n_items;
+      const uint32_t w = valid ? sp.items[qi] : 0x00ffff00u;
+      sca[q] = (int)(w & 0xffu);
+      const uint32_t xb = (w >> 8) & 0xffu, xc = (w >> 16) & 0xffu;
+      scb[q] = xb != 0xffu ? (int)xb : sca[q];
+      scc[q] = xc != 0xffu ? (int)xc : sca[q];
+      smb[q] = xb != 0xffu ? 1u : 0u;
+      smc[q] = xc != 0xffu ? 1u : 0u;
+      smv[q] = valid ? 1u : 0u;
+      smask[q] = sp.masks[lane * 4 + q];
+    }
+  }
+
 #ifdef CEMC_PHASE_TIMING
   unsigned long long tph[16] = {0};
   long long tlast = clock64();
@@ -340,6 +366,47 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
         *reinterpret_cast<int4 *>(pp) = make_int4(site0, site1, new0, new1);
         *reinterpret_cast<int4 *>(pp + 4) = make_int4(old0, old1, slot0, slot1);
       }
+      if (kSpin) {
+        // ---- spin evaluation (cemc_spin_kernel.cuh): XOR of neighbour occupation bits,
+        // one ballot per 32 sub-clusters, exact integer numerators, exact division
+        const int sites[2] = {site0, site1};
+        const int olds[2] = {old0, old1}, news[2] = {new0, new1};
+#pragma unroll
+        for (int x = 0; x < 2; x++) {                     // gathered sites (conflict check)
+          const int q = lane + 32 * x;
+          if (q < NJ * KP) {
+            const int j = q >= KP, c = j ? q - KP : q;
+            gsx[x] = c < K ? __ldg(&t.trans[(size_t)sites[j] * K + c]) : sites[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+          const int32_t *row = t.trans + (size_t)sites[j] * K;
+          int cnt = 0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (q < s_rounds) {
+              const int na = __ldg(row + sca[q]), nb2 = __ldg(row + scb[q]), nc = __ldg(row + scc[q]);
+              uint32_t va = (uint32_t)s.occ[na], vb = (uint32_t)s.occ[nb2], vc = (uint32_t)s.occ[nc];
+              if (j == 1) {                    // change 1 sees change 0 applied (:845-852)
+                if (na == site0) va = (uint32_t)new0;
+                if (nb2 == site0) vb = (uint32_t)new0;
+                if (nc == site0) vc = (uint32_t)new0;
+              }
+              const uint32_t bit = (va ^ (vb & smb[q]) ^ (vc & smc[q])) & smv[q];
+              cnt += __popc(__ballot_sync(0xffffffffu, bit) & smask[q]);
+            }
+          }
+          const int dsig = 2 * sp.b0 * (olds[j] - news[j]);          // sigma_new - sigma_old
+          const int num = s_coef * dsig * (s_msub - 2 * cnt);
+          s0.sq[(b * 2 + j) * 32 + lane] = exact_div((double)num, f_den, f_rden);   // :402
+        }
+        if (!kCanon) s0.sq[(b * 2 + 1) * 32 + lane] = 0.0;
+        double de = f_kind > 0 ? eci_reg * (s0.sq[(b * 2 + 0) * 32 + lane] + s0.sq[(b * 2 + 1) * 32 + lane]) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
+        if (lane == 0) s0.dEa[b] = de * dN;
+      } else {
       // P1: gather
 #pragma unroll
       for (int x = 0; x < 2; x++) {
@@ -447,6 +514,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
         if (lane == 0) s0.dEa[b] = de * dN;
+      }
       }
     }
     csync();

@@ -42,9 +42,10 @@ if __name__ == "__main__":
         T = np.linspace(200, 1000, 16); mu = np.linspace(-1.1, -0.9, 16)
         kTs = np.repeat(T * KB, 16); mus = np.tile(mu, 16)
         ft, gpu = setup(10, ["Al", "Mg"], {"Al": 0.5, "Mg": 0.5}, 256, kTs, mus * 0.0)
+        gpu.set_autotune(False)
         for spin in (True, False):
           for bt in (batches if not spin else [0]):
-            gpu.set_spin_kernel(spin); gpu.set_batch(bt)
+            gpu.set_batch(bt)
             n = 50000
             ms = timeit(gpu, gpu.run_sgc, n)
             print("C2 sgc binary L=10 R=256 spin=%s batch=%d n=%d: %.2f ms -> %.1f M moves/s (%.0f ns/move/chain)" % (

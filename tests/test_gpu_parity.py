@@ -574,3 +574,33 @@ def test_autotuned_long_run_is_invariant(cuda_device):
     accs = gpu.get_accumulators()
     for r, c in enumerate(chains):
         assert np.array_equal(accs[r], c.acc)
+
+
+@pytest.mark.parametrize("batch,cluster", [(4, 1), (8, 1), (16, 1), (16, 2)])
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+def test_batch_kernel_spin_evaluation(cuda_device, batch, cluster, mode):
+    """Binary +-1 basis inside the batch kernel (XOR / ballot / popcount evaluation
+    per warp, screened in-order decisions): oracle trajectory for every batch size,
+    also on the 27-site cell and on config 1's six-family cluster set."""
+    cases = [(BINARY, 3), (dict(BINARY, L=3), 2),
+             (dict(BINARY, families=["nn", "2nn", "3nn", "tri", "iso", "tet"]), 2)]
+    for case, R in cases:
+        st, eci, symbols, ft = build(**case)
+        kTs = np.linspace(0.02, 0.2, R)
+        gpu, chains = make_pair(ft, [symbols] * R, kTs, seed=83)
+        gpu.set_batch(batch)
+        gpu.set_cluster(cluster)
+        n = 1500
+        gpu.set_trace(n)
+        gpu.reset_accumulators()
+        (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+        gpu.synchronize()
+        tr = gpu.get_trace(n)
+        for r, c in enumerate(chains):
+            o = c.run_sgc(n, trace=True) if mode == "sgc" else c.run_canonical(n, trace=True)
+            assert np.array_equal(tr[0][r], o[0]) and np.array_equal(tr[3][r], o[3])
+            assert np.array_equal(tr[4][r], o[4])
+        assert_state_equal(gpu, chains)
+        accs = gpu.get_accumulators()
+        for r, c in enumerate(chains):
+            assert np.array_equal(accs[r], c.acc)
