@@ -165,6 +165,8 @@ def gpu_arm(args):
     torch.cuda.set_stream(stream)
     gpu = wl.make_updater(w, device=local_rank, replica_offset=offset,
                           stream=stream.cuda_stream, seed=1234)
+    if args.variant >= 0:
+        gpu.set_variant(args.variant, args.variant)      # profiling runs: no autotuning
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
     def barrier():
@@ -275,6 +277,8 @@ def gpu_arm(args):
                 "cache": "L2 flushed (256 MiB write) between timed iterations; per-replica state "
                          "is shared-memory resident by design",
                 "parallelism": "replicas sharded over %d GPU(s), no data-path collective" % world,
+                "kernel_variant": "%d (0 spin, 1-4 batch (16,2)/(16,1)/(8,1)/(4,1), 5 one move at a "
+                                  "time; autotuned unless --variant)" % gpu.get_variant()[0],
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
@@ -362,6 +366,9 @@ def main():
                     help="moves per chain per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other_workloads block")
+    ap.add_argument("--variant", type=int, default=-1,
+                    help="pin the kernel variant (cemc_set_variant) instead of autotuning; used "
+                         "for ncu runs, whose per-launch overhead defeats the autotuner's timing")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

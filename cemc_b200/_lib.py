@@ -63,6 +63,7 @@ SIGNATURES = {
     "cemc_set_cluster": [_H, C.c_int],
     "cemc_set_autotune": [_H, C.c_int],
     "cemc_get_variant": [_H, _i32p, _i32p],
+    "cemc_set_variant": [_H, C.c_int, C.c_int],
     "cemc_set_spin_kernel": [_H, C.c_int],
     "cemc_set_screen_slack": [_H, C.c_double],
     "cemc_debug_phase_cycles": [_H, _u64p],

@@ -712,6 +712,14 @@ int cemc_set_autotune(cemc_handle *h, int on) {
   return 0;
 }
 
+int cemc_set_variant(cemc_handle *h, int sgc, int canonical) {
+  if (!h) return fail("null handle");
+  if (sgc < -1 || sgc >= 6 || canonical < -1 || canonical >= 6) return fail("no such kernel variant");
+  h->tuned_sgc = sgc;
+  h->tuned_can = canonical;
+  return 0;
+}
+
 int cemc_get_variant(cemc_handle *h, int *sgc, int *canonical) {
   if (!h) return fail("null handle");
   if (sgc) *sgc = h->tuned_sgc;

@@ -150,6 +150,9 @@ class BatchedCEUpdater(object):
     def set_autotune(self, on: bool):
         _lib.check(self.lib.cemc_set_autotune(self._h, int(bool(on))))
 
+    def set_variant(self, sgc: int = -1, canonical: int = -1):
+        _lib.check(self.lib.cemc_set_variant(self._h, int(sgc), int(canonical)))
+
     def get_variant(self):
         a, b = C.c_int32(-1), C.c_int32(-1)
         _lib.check(self.lib.cemc_get_variant(self._h, C.byref(a), C.byref(b)))

@@ -125,6 +125,9 @@ int cemc_set_batch(cemc_handle *h, int b);
  * (4,1), 5 mc_kernel, -1 not tuned yet.                                        */
 int cemc_set_autotune(cemc_handle *h, int on);
 int cemc_get_variant(cemc_handle *h, int *sgc, int *canonical);
+/* pin the variant per sampler (-1 = let the autotuner decide); inapplicable variants
+ * fall back to the default preference order                                     */
+int cemc_set_variant(cemc_handle *h, int sgc, int canonical);
 /* CTAs (SMs) of one thread-block cluster that cooperate on ONE chain in the batch
  * kernel: 0 = auto (2 when 2 x replicas still fit the GPU in one wave), 1, 2   */
 int cemc_set_cluster(cemc_handle *h, int c);
