@@ -74,7 +74,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(bf, double, t.D * t.S);
   CEMC_TAKE(items, unsigned long long, t.n_items_total);
   CEMC_TAKE(task_sum, int2, t.n_tasks_total);
-  CEMC_TAKE(ring, uint4, 32 * 2);
+  CEMC_TAKE(ring, uint4, 128 * 2);
   CEMC_TAKE(prop, int32_t, BT * 8);
   CEMC_TAKE(cmask, int32_t, BT);
   CEMC_TAKE(ctl, int32_t, 8);
@@ -254,53 +254,59 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     }
   }
 
+  // ---- proposal ring: 128 records, produced 32 at a time by the observer warp of every
+  // CTA while the evaluation warps work (montecarlo.py:890-908, sgc_montecarlo.py:62-76)
+  auto produce32 = [&](long long first) {
+    const unsigned long long stp = step0 + (unsigned long long)first + lane;
+    uint32_t c0 = (uint32_t)stp, c1 = (uint32_t)(stp >> 32), c2 = rep_global, c3 = 0;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    uint4 rec0;
+    double u;
+    if (!kCanon) {
+      const uint32_t ia = __umulhi(c0, (uint32_t)t.n_active);       // sgc_montecarlo.py:69
+      rec0 = make_uint4(ia, c1, 0u, 0u);
+      u = u53(c2, c3);
+    } else {                                                         // montecarlo.py:899-907
+      uint32_t d0 = (uint32_t)stp, d1 = (uint32_t)(stp >> 32), d2 = rep_global, d3 = 1;
+      philox4x32_10(d0, d1, d2, d3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      const int ia = (int)__umulhi(c0, (uint32_t)n_present);
+      int ib = (int)__umulhi(c1, (uint32_t)(n_present - 1)); ib += (ib >= ia);
+      int sa = 0, sb = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { if (q == ia) sa = present[q]; if (q == ib) sb = present[q]; }
+      const int oa0 = offs_of(offs, sa), oa1 = offs_of(offs, sa + 1);
+      const int ob0 = offs_of(offs, sb), ob1 = offs_of(offs, sb + 1);
+      const int slot0 = oa0 + (int)__umulhi(c2, (uint32_t)(oa1 - oa0));
+      const int slot1 = ob0 + (int)__umulhi(c3, (uint32_t)(ob1 - ob0));
+      rec0 = make_uint4((uint32_t)slot0, (uint32_t)slot1, (uint32_t)sb, (uint32_t)sa);
+      u = u53(d0, d1);
+    }
+    // Metropolis threshold: u <= exp(-dE/kT)  <=>  dE <= -kT ln u   (screen only)
+    const double L = -kT * log(u);
+    const int slot = (int)((first + lane) & 127);
+    s.ring[slot * 2] = rec0;
+    s.ring[slot * 2 + 1] = make_uint4((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u),
+                                      (uint32_t)__double2loint(L), (uint32_t)__double2hiint(L));
+  };
+  long long fill_end = 0;              // records of steps [sdone, fill_end) are in the ring
+  if (is_obs) { produce32(0); produce32(32); produce32(64); }
+  fill_end = 96;
+  csync();
+
 #ifdef CEMC_PHASE_TIMING
   unsigned long long tph[16] = {0};
   long long tlast = clock64();
 #endif
   long long sdone = 0;                 // moves decided so far
-  long long rbase = -(1LL << 40);      // first step held by the ring
 
   while (sdone < a.n_steps) {
     const int nb = (int)((a.n_steps - sdone) < BT ? (a.n_steps - sdone) : BT);
-    // ---- ring refill: proposals of steps [rbase, rbase + 32) ---------------------
-    if (sdone + nb > rbase + 32) {
-      rbase = sdone;
-      if (lwarp == 0) {                          // every CTA keeps its own copy of the ring
-        const unsigned long long stp = step0 + (unsigned long long)rbase + lane;
-        uint32_t c0 = (uint32_t)stp, c1 = (uint32_t)(stp >> 32), c2 = rep_global, c3 = 0;
-        philox4x32_10(c0, c1, c2, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-        uint4 rec0;
-        double u;
-        if (!kCanon) {
-          const uint32_t ia = __umulhi(c0, (uint32_t)t.n_active);       // sgc_montecarlo.py:69
-          rec0 = make_uint4(ia, c1, 0u, 0u);
-          u = u53(c2, c3);
-        } else {                                                         // montecarlo.py:899-907
-          uint32_t d0 = (uint32_t)stp, d1 = (uint32_t)(stp >> 32), d2 = rep_global, d3 = 1;
-          philox4x32_10(d0, d1, d2, d3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-          const int ia = (int)__umulhi(c0, (uint32_t)n_present);
-          int ib = (int)__umulhi(c1, (uint32_t)(n_present - 1)); ib += (ib >= ia);
-          int sa = 0, sb = 0;
-#pragma unroll
-          for (int q = 0; q < 8; q++) { if (q == ia) sa = present[q]; if (q == ib) sb = present[q]; }
-          const int oa0 = offs_of(offs, sa), oa1 = offs_of(offs, sa + 1);
-          const int ob0 = offs_of(offs, sb), ob1 = offs_of(offs, sb + 1);
-          const int slot0 = oa0 + (int)__umulhi(c2, (uint32_t)(oa1 - oa0));
-          const int slot1 = ob0 + (int)__umulhi(c3, (uint32_t)(ob1 - ob0));
-          rec0 = make_uint4((uint32_t)slot0, (uint32_t)slot1, (uint32_t)sb, (uint32_t)sa);
-          u = u53(d0, d1);
-        }
-        // Metropolis threshold: u <= exp(-dE/kT)  <=>  dE <= -kT ln u   (screen only)
-        const double L = -kT * log(u);
-        s.ring[lane * 2] = rec0;
-        s.ring[lane * 2 + 1] = make_uint4((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u),
-                                          (uint32_t)__double2loint(L), (uint32_t)__double2hiint(L));
-      }
-      __syncthreads();
-    }
     CEMC_TICK(0);
 
+    // ---- observer warp: next 32 proposal records, then the observer sums -----------------
+    const bool refill = (fill_end - sdone) <= 64;
+    if (is_obs && refill) produce32(fill_end);        // visible after the E1 barrier
+    if (refill) fill_end += 32;
     // ---- observer warp: Averager / SGCObserver sums of the previous batch ---------------
     // (montecarlo.py:811-814, mc_observers.py:264-270), in move order, while the
     // evaluation warps work on the next batch
@@ -338,7 +344,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check); host: NJ*KP <= 64
     if (warp < nb) {
       const int b = warp;
-      const uint4 rec0 = s.ring[(int)(sdone + b - rbase) * 2];
+      const uint4 rec0 = s.ring[(int)((sdone + b) & 127) * 2];
       int site0, site1 = -1, new0, new1 = 0, old0, old1 = 0, slot0 = -1, slot1 = -1;
       if (!kCanon) {
         site0 = t.active ? t.active[rec0.x] : (int)rec0.x;
@@ -543,7 +549,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     // where the reference's operation order allows.  A move whose screen is
     // inconclusive (|dE - L| inside the band) is decided with the exact expression.
     if (warp == 0) {
-      const uint4 rec1 = s.ring[(int)(sdone + (lane < nb ? lane : 0) - rbase) * 2 + 1];
+      const uint4 rec1 = s.ring[(int)((sdone + (lane < nb ? lane : 0)) & 127) * 2 + 1];
       const double u_l = __hiloint2double((int)rec1.y, (int)rec1.x);
       const double L_l = __hiloint2double((int)rec1.w, (int)rec1.z);
       const double dE_l = s.dEa[lane < nb ? lane : 0];
