@@ -357,6 +357,7 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   if (t.VS > (int)CEMC_ITEM_MASK) return fail("too many (basis function, column) pairs for the item encoding");
   const int RB = D * t.KP;
   std::vector<unsigned long long> items;
+  std::vector<uint4> items4;
   std::vector<uint16_t> item_slot;
   std::vector<int32_t> item_base(tb->n_symm + 1, 0), task_base(tb->n_symm + 1, 0);
   std::vector<int2> task_sum;
@@ -408,6 +409,16 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
           if (slot >= (1 << 14)) return fail("cluster program too large (product slots)");
           w |= (unsigned long long)slot << 50;
           items.push_back(w);
+          {   // byte offsets into V for the batch kernel: x = off0|off1<<16, y = off2|off3<<16,
+              // z = slot | kref<<16, w = offset of the NEW value of the changed site
+            uint32_t off[4];
+            for (int k = 0; k < 4; k++) off[k] = (uint32_t)((w >> (CEMC_ITEM_BITS * k)) & CEMC_ITEM_MASK) * 8u;
+            uint4 it;
+            it.x = off[0] | (off[1] << 16); it.y = off[2] | (off[3] << 16);
+            it.z = (uint32_t)slot | ((uint32_t)kref << 16);
+            it.w = off[kref] + (uint32_t)D * 8u;
+            items4.push_back(it);
+          }
           item_slot.push_back((uint16_t)slot++);
         }
       }
@@ -490,6 +501,7 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   if ((rc = dupload(h, &t.symm_of_site, symm))) return rc;
   if ((rc = dupload(h, &t.bf, bf))) return rc;
   if ((rc = dupload(h, &t.items, items))) return rc;
+  if ((rc = dupload(h, &t.items4, items4))) return rc;
   if ((rc = dupload(h, &t.item_slot, item_slot))) return rc;
   if ((rc = dupload(h, &t.item_base, item_base))) return rc;
   if ((rc = dupload(h, &t.task_base, task_base))) return rc;

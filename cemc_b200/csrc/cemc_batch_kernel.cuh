@@ -39,7 +39,7 @@ namespace cemc {
 
 struct BatchSmem {
   double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *Pm, *Ch, *obE;
-  unsigned long long *items;
+  uint4 *items;
   int2 *task_sum;
   uint4 *ring;              // [32][2]: proposal; uniform + Metropolis threshold
   int32_t *prop;            // [B][8] decoded proposal
@@ -72,7 +72,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(Ch, double, BT * 32);
   CEMC_TAKE(obE, double, BT);
   CEMC_TAKE(bf, double, t.D * t.S);
-  CEMC_TAKE(items, unsigned long long, t.n_items_total);
+  CEMC_TAKE(items, uint4, t.n_items_total);
   CEMC_TAKE(task_sum, int2, t.n_tasks_total);
   CEMC_TAKE(ring, uint4, 128 * 2);
   CEMC_TAKE(prop, int32_t, BT * 8);
@@ -156,7 +156,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 
   // ---- stage ----------------------------------------------------------------
   for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
-  for (int i = tid; i < t.n_items_total; i += nthr) s.items[i] = t.items[i];
+  for (int i = tid; i < t.n_items_total; i += nthr) s.items[i] = t.items4[i];
   for (int i = tid; i < t.n_tasks_total; i += nthr) s.task_sum[i] = t.task_sum[i];
   for (int i = tid; i < B * NJ * VS; i += nthr) s.V[i] = 1.0;      // V[K] is the constant 1.0
   if (kStateSmem) {
@@ -442,19 +442,24 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       double *POb = s.PO + lwarp * NJ * max_slots, *PNb = s.PN + lwarp * NJ * max_slots;
       for (int q = lane; q < NJ * n_items; q += 32) {
         const int j = q >= n_items;
-        const unsigned long long w = s.items[j ? q - n_items : q];
-        const double *Vj = Vb + j * VS;
-        const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-        const int i0 = lo & CEMC_ITEM_MASK, i1 = (lo >> 12) & CEMC_ITEM_MASK;
-        const int i2 = (uint32_t)(w >> 24) & CEMC_ITEM_MASK, i3 = (hi >> 4) & CEMC_ITEM_MASK;
-        const int kref = (hi >> 16) & 3;
-        const int slot = (int)(hi >> 18) + j * max_slots;
-        const double f0 = Vj[i0], f1 = Vj[i1], f2 = Vj[i2], f3 = Vj[i3];
-        const int iref = kref == 0 ? i0 : kref == 1 ? i1 : kref == 2 ? i2 : i3;
-        const double fr = Vj[iref + D];
-        const double tO = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), f2), f3);      // :271-281
-        const double tN = __dmul_rn(__dmul_rn(__dmul_rn(kref == 0 ? fr : f0, kref == 1 ? fr : f1),
-                                              kref == 2 ? fr : f2), kref == 3 ? fr : f3);
+        const uint4 it = s.items[j ? q - n_items : q];
+        const char *Vj = reinterpret_cast<const char *>(Vb + j * VS);
+        const double f0 = *reinterpret_cast<const double *>(Vj + (it.x & 0xffffu));
+        const double f1 = *reinterpret_cast<const double *>(Vj + (it.x >> 16));
+        const double f2 = *reinterpret_cast<const double *>(Vj + (it.y & 0xffffu));
+        const double f3 = *reinterpret_cast<const double *>(Vj + (it.y >> 16));
+        const double fr = *reinterpret_cast<const double *>(Vj + it.w);
+        const int slot = (int)(it.z & 0xffffu) + j * max_slots;
+        // left-to-right products (:271-281) for the old and the new species of the changed
+        // site; the position of the changed site is (mostly) warp-uniform
+        const double tO = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), f2), f3);
+        double tN;
+        switch (it.z >> 16) {
+          case 0: tN = __dmul_rn(__dmul_rn(__dmul_rn(fr, f1), f2), f3); break;
+          case 1: tN = __dmul_rn(__dmul_rn(__dmul_rn(f0, fr), f2), f3); break;
+          case 2: tN = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), fr), f3); break;
+          default: tN = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), f2), fr); break;
+        }
         POb[slot] = tO;
         PNb[slot] = tN;
       }

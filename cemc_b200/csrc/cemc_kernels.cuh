@@ -66,6 +66,7 @@ struct DeviceTables {    // device pointers, shared by all replicas
   const int32_t *symm_of_site; // [N]
   const double *bf;            // [D][S]
   const unsigned long long *items;  // [n_items_total]
+  const uint4 *items4;         // [n_items_total] same items, pre-decoded byte offsets (batch kernel)
   const uint16_t *item_slot;   // [n_items_total] product slot (padded, per group)
   const int32_t *item_base;    // [n_symm+1]
   const int32_t *task_base;    // [n_symm+1]
