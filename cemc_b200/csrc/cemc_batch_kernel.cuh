@@ -440,28 +440,45 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       __syncwarp();
       // P2a: products
       double *POb = s.PO + lwarp * NJ * max_slots, *PNb = s.PN + lwarp * NJ * max_slots;
-      for (int q = lane; q < NJ * n_items; q += 32) {
-        const int j = q >= n_items;
-        const uint4 it = s.items[j ? q - n_items : q];
-        const char *Vj = reinterpret_cast<const char *>(Vb + j * VS);
-        const double f0 = *reinterpret_cast<const double *>(Vj + (it.x & 0xffffu));
-        const double f1 = *reinterpret_cast<const double *>(Vj + (it.x >> 16));
-        const double f2 = *reinterpret_cast<const double *>(Vj + (it.y & 0xffffu));
-        const double f3 = *reinterpret_cast<const double *>(Vj + (it.y >> 16));
-        const double fr = *reinterpret_cast<const double *>(Vj + it.w);
-        const int slot = (int)(it.z & 0xffffu) + j * max_slots;
-        // left-to-right products (:271-281) for the old and the new species of the changed
-        // site; the position of the changed site is (mostly) warp-uniform
-        const double tO = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), f2), f3);
-        double tN;
-        switch (it.z >> 16) {
-          case 0: tN = __dmul_rn(__dmul_rn(__dmul_rn(fr, f1), f2), f3); break;
-          case 1: tN = __dmul_rn(__dmul_rn(__dmul_rn(f0, fr), f2), f3); break;
-          case 2: tN = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), fr), f3); break;
-          default: tN = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), f2), fr); break;
+      {
+        // one product pair per sub-cluster; two items in flight per lane (ILP: the warp
+        // has few siblings on its scheduler, so latency must be covered inside the warp)
+        auto item_products = [&](int q, double &tO, double &tN, int &slot) {
+          const int j = q >= n_items;
+          const uint4 it = s.items[j ? q - n_items : q];
+          const char *Vj = reinterpret_cast<const char *>(Vb + j * VS);
+          const double f0 = *reinterpret_cast<const double *>(Vj + (it.x & 0xffffu));
+          const double f1 = *reinterpret_cast<const double *>(Vj + (it.x >> 16));
+          const double f2 = *reinterpret_cast<const double *>(Vj + (it.y & 0xffffu));
+          const double f3 = *reinterpret_cast<const double *>(Vj + (it.y >> 16));
+          const double fr = *reinterpret_cast<const double *>(Vj + it.w);
+          slot = (int)(it.z & 0xffffu) + j * max_slots;
+          // left-to-right products (:271-281) for the old and the new species of the
+          // changed site; its position in the cluster is (mostly) warp-uniform
+          tO = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), f2), f3);
+          switch (it.z >> 16) {
+            case 0: tN = __dmul_rn(__dmul_rn(__dmul_rn(fr, f1), f2), f3); break;
+            case 1: tN = __dmul_rn(__dmul_rn(__dmul_rn(f0, fr), f2), f3); break;
+            case 2: tN = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), fr), f3); break;
+            default: tN = __dmul_rn(__dmul_rn(__dmul_rn(f0, f1), f2), fr); break;
+          }
+        };
+        const int n_all = NJ * n_items;
+        int q = lane;
+        for (; q + 32 < n_all; q += 64) {
+          double tO0, tN0, tO1, tN1;
+          int sl0, sl1;
+          item_products(q, tO0, tN0, sl0);
+          item_products(q + 32, tO1, tN1, sl1);
+          POb[sl0] = tO0; PNb[sl0] = tN0;
+          POb[sl1] = tO1; PNb[sl1] = tN1;
         }
-        POb[slot] = tO;
-        PNb[slot] = tN;
+        if (q < n_all) {
+          double tO0, tN0;
+          int sl0;
+          item_products(q, tO0, tN0, sl0);
+          POb[sl0] = tO0; PNb[sl0] = tN0;
+        }
       }
       __syncwarp();
       // P2b: sums
