@@ -14,13 +14,15 @@ from .tables import CemcTablesStruct
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CEMC_B200_LIB") or os.path.join(_HERE, "_cemc_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", "cemc_b200.cu"),
-           os.path.join(_HERE, "csrc", "cemc_kernels.cuh"),
-           os.path.join(_HERE, "csrc", "cemc_spin_kernel.cuh"),
-           os.path.join(_HERE, "csrc", "cemc_batch_kernel.cuh"),
-           os.path.join(os.path.dirname(_HERE), "include", "cemc_b200.h")]
+_CSRC = os.path.join(_HERE, "csrc")
+# translation units (compiled in parallel, linked into one library) and their headers
+UNITS = ["cemc_b200.cu", "cemc_batch_product.cu", "cemc_batch_spin.cu", "cemc_batch_tab.cu"]
+HEADERS = ["cemc_kernels.cuh", "cemc_spin_kernel.cuh", "cemc_batch_kernel.cuh",
+           "cemc_batch_launch.cuh"]
+SOURCES = [os.path.join(_CSRC, f) for f in UNITS + HEADERS] + \
+    [os.path.join(os.path.dirname(_HERE), "include", "cemc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-              "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-fmad=false"]
+              "-std=c++17", "-Xcompiler", "-fPIC", "-fmad=false"]
 
 _lib = None
 
@@ -29,17 +31,29 @@ class CemcError(RuntimeError):
     pass
 
 
-def build_ext(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA extension for sm_100a (nvcc cross-compiles w/o GPU)."""
+def build_ext(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """Compile the CUDA extension for sm_100a (nvcc cross-compiles w/o GPU):
+    one object per translation unit, in parallel, then one shared library."""
+    out = out or LIB_PATH
     newest = max(os.path.getmtime(s) for s in SOURCES)
-    if not force and os.path.exists(LIB_PATH) and \
-            os.path.getmtime(LIB_PATH) >= newest:
-        return LIB_PATH
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, SOURCES[0]]
-    subprocess.check_call(cmd)
-    return LIB_PATH
+    tag = os.path.splitext(os.path.basename(out))[0]
+    objdir = os.path.join(_CSRC, "_build", tag)
+    os.makedirs(objdir, exist_ok=True)
+    flags = NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+    procs, objs = [], []
+    for u in UNITS:
+        obj = os.path.join(objdir, u.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append((u, subprocess.Popen([nvcc] + flags + ["-c", "-o", obj, os.path.join(_CSRC, u)])))
+    failed = [u for u, p in procs if p.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for " + ", ".join(failed))
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-o", out] + objs)
+    return out
 
 
 _u64p = C.POINTER(C.c_uint64)
@@ -65,6 +79,8 @@ SIGNATURES = {
     "cemc_get_variant": [_H, _i32p, _i32p],
     "cemc_set_variant": [_H, C.c_int, C.c_int],
     "cemc_set_spin_kernel": [_H, C.c_int],
+    "cemc_set_table_eval": [_H, C.c_int],
+    "cemc_get_batch_eval": [_H, _i32p],
     "cemc_set_screen_slack": [_H, C.c_double],
     "cemc_debug_phase_cycles": [_H, _u64p],
     "cemc_selftest_division": [_H, C.c_uint64, C.c_int, C.c_int, _u64p],

@@ -16,7 +16,7 @@
 #include "../../include/cemc_b200.h"
 #include "cemc_kernels.cuh"
 #include "cemc_spin_kernel.cuh"
-#include "cemc_batch_kernel.cuh"
+#include "cemc_batch_launch.cuh"
 
 using namespace cemc;
 
@@ -83,6 +83,10 @@ struct cemc_handle {
   int batch = 0;                      // moves evaluated speculatively per batch (0 = auto)
   bool spin_ok = false;               // binary +-1 basis: warp-per-replica spin kernel usable
   SpinTables spin{};
+  bool tab_ok = false;                // product tables fit: table evaluation in the batch kernel
+  bool no_tab = false;                // testing: keep the fp64 product evaluation
+  TabTables tab{};
+  unsigned long long *d_phase = nullptr;   // CEMC_PHASE_TIMING builds
 };
 
 // ---------------------------------------------------------------------------
@@ -485,6 +489,79 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
     h->spin.b0 = b0;
   }
 
+  // ---- product tables of the batch kernel's table evaluation (TabTables) --------
+  // Per family one table [code][decoration]: code = sum_k occ_k S^k over the sorted
+  // positions, entry = the left-to-right product of ce_updater.cpp:271-281 for those
+  // occupations, multiplied in the reference's order (plain IEEE double products: the
+  // bits the reference computes).  Decorations are the fastest index, so the lanes of
+  // one family (one lane per decoration) read one contiguous row.
+  std::vector<uint2> tb_desc;
+  std::vector<int4> tb_task;
+  std::vector<double> tb_tab;
+  {
+    bool ok = (tb->n_symm == 1 && n_eci <= 32 && K <= 31 && S <= 9);
+    auto power = [&](int e) { int v = 1; for (int q = 0; q < e; q++) v *= S; return v; };
+    std::vector<std::vector<std::vector<int>>> fam_decos(tb->n_fam);     // distinct decorations per family
+    std::vector<std::pair<int, int>> task_fd;                            // task -> (family, decoration index)
+    for (int i = 0; i < n_eci && ok; i++) {
+      if (tb->eci_kind[i] != CEMC_ECI_CLUSTER) continue;
+      const int fam = tb->term_fam[i];
+      if (fam < 0) continue;
+      const int n = tb->fam_size[fam];
+      for (int e = tb->term_deco_off[i]; e < tb->term_deco_off[i + 1]; e++) {
+        std::vector<int> key;
+        for (int k = 0; k < n; k++) key.push_back(tb->deco[4 * e + k]);
+        auto &fd = fam_decos[fam];
+        int idx = (int)(std::find(fd.begin(), fd.end(), key) - fd.begin());
+        if (idx == (int)fd.size()) fd.push_back(key);
+        task_fd.push_back(std::make_pair(fam, idx));
+      }
+    }
+    std::vector<int> sub_base(tb->n_fam, 0), tab_base(tb->n_fam, 0);
+    for (int fam = 0; fam < tb->n_fam && ok; fam++) {
+      const int nd = (int)fam_decos[fam].size();
+      if (!nd) continue;
+      const int n = tb->fam_size[fam], M = tb->fam_nsub[fam];
+      const int32_t *pos = tb->fam_pos + tb->fam_pos_off[fam];
+      const int n_codes = power(n);
+      if (nd > 255 || (n_codes + 1) * nd * 8 > 65536) { ok = false; break; }
+      sub_base[fam] = (int)tb_desc.size();
+      for (int m = 0; m < M; m++) {
+        uint32_t cols = (uint32_t)nd << 24, wts = 0; int nn = 0;
+        for (int k = 0; k < n; k++) {
+          const int p = pos[m * n + k];
+          if (p == CEMC_POS_REF) wts |= (uint32_t)power(k) << 24;
+          else { cols |= (uint32_t)p << (8 * nn); wts |= (uint32_t)power(k) << (8 * nn); nn++; }
+        }
+        tb_desc.push_back(make_uint2(cols, wts));
+      }
+      // padding to a multiple of 8 sub-clusters: weights 0 mark the entry, x = byte offset of
+      // the table's all-zero row (adding +0.0 never changes a sum that started at +0.0)
+      while (tb_desc.size() % 8) tb_desc.push_back(make_uint2((uint32_t)(n_codes * nd * 8), 0u));
+      tab_base[fam] = (int)tb_tab.size();
+      for (int code = 0; code < n_codes; code++)
+        for (int e = 0; e < nd; e++) {
+          double v = 1.0;
+          int c = code;
+          for (int k = 0; k < n; k++, c /= S) {
+            volatile double prod = v * tb->bf[(size_t)fam_decos[fam][e][k] * S + (c % S)];   // :279, one rounding per factor
+            v = prod;
+          }
+          tb_tab.push_back(v);
+        }
+      for (int e = 0; e < nd; e++) tb_tab.push_back(0.0);          // the zero row
+    }
+    for (auto &fd : task_fd)
+      tb_task.push_back(make_int4((tab_base[fd.first] + fd.second) * 8, sub_base[fd.first], (tb->fam_nsub[fd.first] + 7) & ~7, 0));
+    if (tb_desc.size() > 128 || tb_tab.size() * 8 > 96 * 1024 || tb_task.empty()) ok = false;
+    if (ok && (int)tb_task.size() != (int)task_sum.size()) ok = false;      // same task numbering as fin_i
+    h->tab_ok = ok;
+    h->tab.n_sub = (int)tb_desc.size();
+    h->tab.n_rounds = ((int)tb_desc.size() + 31) / 32;
+    h->tab.n_tab = (int)tb_tab.size();
+    tb_desc.resize((size_t)std::max(1, h->tab.n_rounds) * 32, make_uint2(0u, 0u));   // never read by a task
+  }
+
   std::vector<int32_t> trans(tb->trans, tb->trans + (size_t)N * K);
   std::vector<int32_t> symm(tb->symm_of_site, tb->symm_of_site + N);
   std::vector<double> bf(tb->bf, tb->bf + (size_t)D * S);
@@ -515,6 +592,14 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
     if ((rc = dupload(h, &h->spin.coef, sp_coef))) return rc;
     if ((rc = dupload(h, &h->spin.msub, sp_msub))) return rc;
   }
+  if (h->tab_ok) {
+    if ((rc = dupload(h, &h->tab.desc, tb_desc))) return rc;
+    if ((rc = dupload(h, &h->tab.task, tb_task))) return rc;
+    if ((rc = dupload(h, &h->tab.tab, tb_tab))) return rc;
+  }
+#ifdef CEMC_PHASE_TIMING
+  if ((rc = dalloc(h, &h->d_phase, (size_t)n_replicas * 24))) return rc;
+#endif
   if (t.n_active != N) { if ((rc = dupload(h, &t.active, active))) return rc; }
   else t.active = nullptr;
   t.uniform_group = (tb->n_symm == 1 && t.n_active == N) ? 1 : 0;
@@ -710,7 +795,7 @@ int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8) {
 #ifdef CEMC_PHASE_TIMING
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaMemcpyFromSymbol(out8, g_phase_cycles, 16 * sizeof(uint64_t)));
+  CU(cudaMemcpy(out8, h->d_phase, (size_t)h->R * 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return 0;
 #else
   return fail("library built without -DCEMC_PHASE_TIMING");
@@ -751,6 +836,21 @@ int cemc_set_spin_kernel(cemc_handle *h, int on) {
   if (!h) return fail("null handle");
   h->no_spin = (on == 0);
   h->tuned_sgc = h->tuned_can = -1;
+  return 0;
+}
+
+int cemc_set_table_eval(cemc_handle *h, int on) {
+  if (!h) return fail("null handle");
+  h->no_tab = (on == 0);
+  h->tuned_sgc = h->tuned_can = -1;
+  return 0;
+}
+
+int cemc_get_batch_eval(cemc_handle *h, int *ev) {
+  if (!h || !ev) return fail("null argument");
+  if (h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4) *ev = EV_SPIN;
+  else if (h->tab_ok && !h->no_tab) *ev = EV_TAB;
+  else *ev = EV_PRODUCT;
   return 0;
 }
 
@@ -926,41 +1026,12 @@ static int launch_spin(cemc_handle *h, const RunArgs &a) {
   return -1;
 }
 
-template <int MODE, bool kTree, int B, bool kSmem, int C, bool kSpin>
-static int launch_batch_kc(cemc_handle *h, const RunArgs &a, size_t sm) {
-  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, kSpin>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(h->R * C);
-  cfg.blockDim = dim3((B + 1) * 32);
-  cfg.dynamicSmemBytes = sm;
-  cfg.stream = h->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = C > 1 ? 1 : 0;
-  CU(cudaLaunchKernelEx(&cfg, kern, h->t, h->st, a, h->acc_stride, h->spin));
-  h->launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-template <int MODE, bool kTree, int B, int C, bool kSpin = false>
-static int launch_batch_b(cemc_handle *h, const RunArgs &a) {
-  size_t sm = batch_smem_layout<B, B * C>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, true);
-  const bool in_smem = sm <= (size_t)h->max_smem_optin;
-  if (!in_smem) sm = batch_smem_layout<B, B * C>(nullptr, nullptr, h->t, MODE == MODE_CANONICAL, false);
-  if (sm > (size_t)h->max_smem_optin) return -1;
-  return in_smem ? launch_batch_kc<MODE, kTree, B, true, C, kSpin>(h, a, sm)
-                 : launch_batch_kc<MODE, kTree, B, false, C, kSpin>(h, a, sm);
-}
-
 static RunArgs run_args(cemc_handle *h, long long n_steps) {
   RunArgs a{};
   a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset;
   a.observe = 1;
   a.screen_slack = h->screen_slack;
+  a.phase = h->d_phase;
   if (h->trace_capacity > 0) {
     a.tr_sites = h->tr_sites; a.tr_news = h->tr_news; a.tr_u = h->tr_u; a.tr_acc = h->tr_acc;
     a.tr_e = h->tr_e; a.tr_capacity = h->trace_capacity;
@@ -973,20 +1044,21 @@ template <int MODE>
 static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C) {
   if (h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
       2 * h->t.KP > 64) return -1;
-  const bool tree = (h->order_mode == CEMC_ORDER_TREE) || h->integer_bf;
-  if (h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4) {
-    // binary +-1 basis: spin evaluation inside the batch kernel
-    if (B == 16 && C == 2) return launch_batch_b<MODE, true, 16, 2, true>(h, a);
-    if (B == 16 && C == 1) return launch_batch_b<MODE, true, 16, 1, true>(h, a);
-    if (B == 8 && C == 1) return launch_batch_b<MODE, true, 8, 1, true>(h, a);
-    if (B == 4 && C == 1) return launch_batch_b<MODE, true, 4, 1, true>(h, a);
-    return -1;
-  }
-  if (B == 16 && C == 2) return tree ? launch_batch_b<MODE, true, 16, 2>(h, a) : launch_batch_b<MODE, false, 16, 2>(h, a);
-  if (B == 16 && C == 1) return tree ? launch_batch_b<MODE, true, 16, 1>(h, a) : launch_batch_b<MODE, false, 16, 1>(h, a);
-  if (B == 8 && C == 1) return tree ? launch_batch_b<MODE, true, 8, 1>(h, a) : launch_batch_b<MODE, false, 8, 1>(h, a);
-  if (B == 4 && C == 1) return tree ? launch_batch_b<MODE, true, 4, 1>(h, a) : launch_batch_b<MODE, false, 4, 1>(h, a);
-  return -1;
+  BatchLaunch L{};
+  L.mode = MODE; L.B = B; L.C = C; L.R = h->R; L.max_smem_optin = h->max_smem_optin;
+  L.tree = ((h->order_mode == CEMC_ORDER_TREE) || h->integer_bf) ? 1 : 0;
+  L.stream = h->stream; L.t = h->t; L.st = h->st; L.a = a; L.acc_stride = h->acc_stride;
+  L.sp = h->spin; L.tb = h->tab;
+  int rc;
+  if (h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4)
+    rc = batch_launch_spin(L);          // binary +-1 basis: spin evaluation
+  else if (h->tab_ok && !h->no_tab)
+    rc = batch_launch_tab(L);           // product tables
+  else
+    rc = batch_launch_product(L);       // fp64 products
+  if (rc == 0) h->launches++;
+  if (rc >= 1000) return fail(std::string("batch kernel launch: ") + cudaGetErrorString((cudaError_t)(rc - 1000)), 100);
+  return rc;
 }
 
 // Kernel variants of one sampler.  All of them produce the same trajectory bit for

@@ -37,10 +37,32 @@
 
 namespace cemc {
 
+// Table evaluation (EV_TAB).  With S species and clusters of n <= 4 sites, the
+// left-to-right product of spin_product_one_atom (ce_updater.cpp:271-281) of one
+// sub-cluster under one decoration takes one of S^n values.  They are tabulated once
+// per (family, decoration) -- with the reference's own multiplication order, so every entry
+// is the bit pattern the reference computes -- and a move is evaluated by (1) packing
+// the occupations of each sub-cluster into a base-S code (once per sub-cluster, shared
+// by all decorations, old and new species of the changed site side by side) and (2)
+// one lane per (ECI, decoration) summing table entries in the reference's sub-cluster
+// order.  No products, no per-decoration gathers: ~3x fewer instructions per move.
+struct TabTables {
+  int n_sub;          // sub-clusters of one changed site, families back to back, each padded to 8
+  int n_rounds;       // ceil(n_sub / 32), <= 4
+  int n_tab;          // doubles in `tab`
+  const uint2 *desc;  // [n_rounds*32] x: col0 | col1<<8 | col2<<16 | n_deco<<24; y: w0 | w1<<8 | w2<<16 | wref<<24 (w = S^position)
+  const int4 *task;   // [n_tasks] {byte offset of the task's column in its family's table, first sub-cluster, M, 0}
+  const double *tab;  // [n_tab] per family [code][decoration] product tables
+};
+
+enum BatchEval : int { EV_PRODUCT = 0, EV_SPIN = 1, EV_TAB = 2 };
+
 struct BatchSmem {
-  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *Pm, *Ch, *obE;
+  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *Pm, *Ch, *obE, *tab, *pub;
   uint4 *items;
   int2 *task_sum;
+  int4 *ttask;
+  uint32_t *codes;          // [B][NJ][n_sub] old code*8 | new code*8 << 16
   uint4 *ring;              // [32][2]: proposal; uniform + Metropolis threshold
   int32_t *prop;            // [B][8] decoded proposal
   int32_t *cmask;           // [B] bit k: move b reads a site that move k changes
@@ -53,7 +75,8 @@ struct BatchSmem {
 template <int B, int BT = B>
 __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char *base,
                                                     const DeviceTables &t, bool canonical,
-                                                    bool state_in_smem = true) {
+                                                    bool state_in_smem = true,
+                                                    const TabTables *tb = nullptr) {
   size_t o = 0;
 #define CEMC_TAKE(field, type, count)                                   \
   do {                                                                  \
@@ -62,21 +85,27 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
     o += sizeof(type) * at_least_1((int)(count));                       \
   } while (0)
   const int nj = canonical ? 2 : 1;
-  CEMC_TAKE(V, double, B * nj * t.VS);
-  CEMC_TAKE(PO, double, B * nj * t.max_slots);
-  CEMC_TAKE(PN, double, B * nj * t.max_slots);
+  CEMC_TAKE(V, double, tb ? 0 : B * nj * t.VS);
+  CEMC_TAKE(PO, double, tb ? 0 : B * nj * t.max_slots);
+  CEMC_TAKE(PN, double, tb ? 0 : B * nj * t.max_slots);
   CEMC_TAKE(diff, double, B * nj * t.max_tasks);
-  CEMC_TAKE(sq, double, BT * 2 * 32);
+  CEMC_TAKE(tab, double, tb ? tb->n_tab : 0);
+  CEMC_TAKE(ttask, int4, tb ? t.n_tasks_total : 0);
+  o = align_up(o, 16);                     // code words are read four at a time
+  CEMC_TAKE(codes, uint32_t, tb ? B * nj * tb->n_sub : 0);
+  CEMC_TAKE(sq, double, 2 * BT * 2 * 32);      // double buffered: the bookkeeper reads batch k during batch k+1
+  CEMC_TAKE(pub, double, 34);
   CEMC_TAKE(dEa, double, BT);
   CEMC_TAKE(Pm, double, BT * 33);
   CEMC_TAKE(Ch, double, BT * 32);
   CEMC_TAKE(obE, double, BT);
   CEMC_TAKE(bf, double, t.D * t.S);
-  CEMC_TAKE(items, uint4, t.n_items_total);
-  CEMC_TAKE(task_sum, int2, t.n_tasks_total);
+  CEMC_TAKE(items, uint4, tb ? 0 : t.n_items_total);
+  CEMC_TAKE(task_sum, int2, tb ? 0 : t.n_tasks_total);
   CEMC_TAKE(ring, uint4, 128 * 2);
-  CEMC_TAKE(prop, int32_t, BT * 8);
+  CEMC_TAKE(prop, int32_t, 2 * BT * 8);
   CEMC_TAKE(cmask, int32_t, BT);
+  o = align_up(o, 8);
   CEMC_TAKE(ctl, int32_t, 8);
   if (state_in_smem) {
     if (canonical) CEMC_TAKE(list, int32_t, t.N);
@@ -105,11 +134,12 @@ __device__ __forceinline__ int offs_of(const int (&offs)[9], int sp) {
 // per-move observer arithmetic off the deciding warp.
 // kSpin: binary +-1 basis -- the evaluation of a move is the XOR / ballot / popcount
 // scheme of cemc_spin_kernel.cuh instead of fp64 products (same quotients, bit for bit).
-template <int MODE, bool kTree, int B, bool kStateSmem, int C, bool kSpin>
-__global__ void __launch_bounds__((B + 1) * 32, (kSpin && B <= 8) ? 2 : 1)
-batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTables sp) {
+template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV>
+__global__ void __launch_bounds__((B + 1) * 32, (EV != EV_PRODUCT && B <= 8) ? 2 : 1)
+batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTables sp, TabTables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   namespace cg = cooperative_groups;
+  constexpr bool kSpin = (EV == EV_SPIN), kTab = (EV == EV_TAB);
   constexpr bool kCanon = (MODE == MODE_CANONICAL);
   constexpr int NJ = kCanon ? 2 : 1;
   constexpr int BT = B * C;                      // moves per batch over the whole cluster
@@ -131,7 +161,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   int32_t *g_list = st.list + (size_t)r * N;
   int32_t *g_loc = st.loc + (size_t)r * N;
   BatchSmem s;
-  batch_smem_layout<B, BT>(&s, smem_raw, t, kCanon, kStateSmem);
+  batch_smem_layout<B, BT>(&s, smem_raw, t, kCanon, kStateSmem, kTab ? &tb : nullptr);
   if (!kStateSmem) { s.occ = g_occ; s.list = g_list; }
   // CTA 0's copies of the arrays the deciding warp reads (DSMEM when C > 1)
   BatchSmem s0 = s;
@@ -156,9 +186,14 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 
   // ---- stage ----------------------------------------------------------------
   for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
-  for (int i = tid; i < t.n_items_total; i += nthr) s.items[i] = t.items4[i];
-  for (int i = tid; i < t.n_tasks_total; i += nthr) s.task_sum[i] = t.task_sum[i];
-  for (int i = tid; i < B * NJ * VS; i += nthr) s.V[i] = 1.0;      // V[K] is the constant 1.0
+  if (!kTab) {
+    for (int i = tid; i < t.n_items_total; i += nthr) s.items[i] = t.items4[i];
+    for (int i = tid; i < t.n_tasks_total; i += nthr) s.task_sum[i] = t.task_sum[i];
+    for (int i = tid; i < B * NJ * VS; i += nthr) s.V[i] = 1.0;      // V[K] is the constant 1.0
+  } else {
+    for (int i = tid; i < tb.n_tab; i += nthr) s.tab[i] = tb.tab[i];
+    for (int i = tid; i < t.n_tasks_total; i += nthr) s.ttask[i] = tb.task[i];
+  }
   if (kStateSmem) {
     for (int i = tid; i < N; i += nthr) s.occ[i] = g_occ[i];
     if (kCanon) for (int i = tid; i < N; i += nthr) s.list[i] = g_list[i];
@@ -207,7 +242,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     if (my_singlet >= 0) { aS0 = ag[3 + 3 * my_singlet]; aS1 = ag[4 + 3 * my_singlet]; aS2 = ag[5 + 3 * my_singlet]; }
     aE0 = ag[0]; aE1 = ag[1]; aE2 = ag[2];
   }
-  int ob_pending = 0;                  // decided moves of the previous batch still to observe
+  int bk_nd = 0, par = 0;              // bookkeeper: decided moves of the previous batch; batch parity
+  uint32_t bk_am = 0u;
+  long long bk_base = 0;
   double e_cur = st.e_cur[r];
   const double kT = st.kT[r];
   const double rkT = __ddiv_rn(1.0, kT);
@@ -254,6 +291,18 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     }
   }
 
+  // kTab: this lane's sub-cluster descriptors (columns of the other sites, code weights)
+  uint32_t tdx[4], tdy[4];
+  const int t_rounds = kTab ? tb.n_rounds : 0;
+  const int n_sub = kTab ? tb.n_sub : 0;
+  if (kTab) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint2 d = q < t_rounds ? tb.desc[q * 32 + lane] : make_uint2(0u, 0u);
+      tdx[q] = d.x; tdy[q] = d.y;
+    }
+  }
+
   // ---- proposal ring: 128 records, produced 32 at a time by the observer warp of every
   // CTA while the evaluation warps work (montecarlo.py:890-908, sgc_montecarlo.py:62-76)
   auto produce32 = [&](long long first) {
@@ -281,65 +330,177 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       rec0 = make_uint4((uint32_t)slot0, (uint32_t)slot1, (uint32_t)sb, (uint32_t)sa);
       u = u53(d0, d1);
     }
-    // Metropolis threshold: u <= exp(-dE/kT)  <=>  dE <= -kT ln u   (screen only)
-    const double L = -kT * log(u);
+    // Metropolis threshold: u <= exp(-dE/kT)  <=>  dE <= -kT ln u.  Screen only, so a
+    // single-precision logarithm will do: |error| <= kT (6e-8 + 1.2e-7 |ln u|) is covered
+    // by the band of the screen, inconclusive moves take the exact expression.
+    const double L = -kT * (double)logf((float)u);
     const int slot = (int)((first + lane) & 127);
     s.ring[slot * 2] = rec0;
     s.ring[slot * 2 + 1] = make_uint4((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u),
                                       (uint32_t)__double2loint(L), (uint32_t)__double2hiint(L));
   };
+#ifdef CEMC_PHASE_TIMING
+  unsigned long long tph[24] = {0};
+  long long tlast = clock64();
+#endif
+  // ---- bookkeeper (observer warp of CTA 0): the exact bookkeeping of a decided batch, in the
+  // reference's order, off the critical path (it runs while the evaluation warps work on the
+  // next batch): CF increments per accepted move (:404), ordered energy dot products
+  // (:236-242, one lane per move), trace records, Averager / SGCObserver sums
+  // (montecarlo.py:811-814, mc_observers.py:264-270).  The deciding warp only needs the CF
+  // vector and the energy for an inconclusive screen; they are published in s.pub.
+  auto bookkeep = [&](int nd, uint32_t accmask, long long base, int pp) {
+#ifdef CEMC_PHASE_TIMING
+    long long tb0 = clock64();
+#define CEMC_OTICK(slot) do { const long long n_ = clock64(); if (lane == 0) tph[slot] += (unsigned long long)(n_ - tb0); tb0 = n_; } while (0)
+#else
+#define CEMC_OTICK(slot) do { } while (0)
+#endif
+    const double *sqp = s.sq + pp * (BT * 64);
+    double c = cf_reg;
+    {
+      // fully unrolled over the batch: compile-time addresses and mask bits, loads of a
+      // group of G moves up front; the only serial chain is the DADDs of accepted moves
+      constexpr int G = (BT % 5 == 0) ? 5 : (BT % 7 == 0) ? 7 : 3;
+      static_assert(BT % G == 0, "group size must divide the batch");
+#pragma unroll
+      for (int b0 = 0; b0 < BT; b0 += G) {
+        if (b0 < nd) {
+          double qa[G], qb[G];
+#pragma unroll
+          for (int x = 0; x < G; x++) {
+            qa[x] = sqp[(b0 + x) * 64 + lane];
+            qb[x] = kCanon ? sqp[(b0 + x) * 64 + 32 + lane] : 0.0;
+          }
+#pragma unroll
+          for (int x = 0; x < G; x++) {
+            if (accmask & (1u << (b0 + x))) {                  // warp-uniform
+              if (f_kind > 0) {                                // kinds 0 / -1: copied (:360,:382)
+                c = __dadd_rn(c, qa[x]);                       // :404
+                if (kCanon) c = __dadd_rn(c, qb[x]);
+              }
+              s.Pm[(b0 + x) * 33 + lane] = __dmul_rn(eci_reg, c);
+            }
+            s.Ch[(b0 + x) * 32 + lane] = c;                    // entries >= nd are never read
+          }
+        }
+      }
+    }
+    __syncwarp();
+    CEMC_OTICK(16);
+    // exact energies of the accepted moves, one lane per move (ordered dot, :236-242)
+    const bool my_acc = lane < nd && ((accmask >> lane) & 1u);
+    double E_l = 0.0;
+    if (my_acc) {
+      const double *pm = s.Pm + lane * 33;
+      double e = 0.0;
+      int i = 0;
+      for (; i + 7 < n_eci; i += 8) {
+        double v[8];
+#pragma unroll
+        for (int x = 0; x < 8; x++) v[x] = pm[i + x];
+#pragma unroll
+        for (int x = 0; x < 8; x++) e = __dadd_rn(e, v[x]);
+      }
+      for (; i < n_eci; i++) e = __dadd_rn(e, pm[i]);
+      E_l = __dmul_rn(e, dN);
+    }
+    // energy after move b = energy of the last accepted move <= b (else the old one)
+    double E_after;
+    {
+      const uint32_t upto = accmask & (lane >= 31 ? 0xffffffffu : ((2u << lane) - 1u));
+      const int src = upto ? 31 - __clz(upto) : 0;
+      const double Es = __shfl_sync(0xffffffffu, E_l, src);
+      E_after = upto ? Es : e_cur;
+    }
+    if (accmask) {
+      const int last = 31 - __clz(accmask);
+      e_cur = __shfl_sync(0xffffffffu, E_l, last);
+      cf_reg = c;
+      s.pub[lane] = c;
+      if (lane == 0) s.pub[32] = e_cur;
+    }
+    if (lane < nd) s.obE[lane] = E_after;
+    if (tracing && lane < nd && base + lane < a.tr_capacity) {
+      const int4 pa = *reinterpret_cast<const int4 *>(s.prop + pp * (BT * 8) + lane * 8);
+      const uint4 rec1 = s.ring[(int)((base + lane) & 127) * 2 + 1];
+      const size_t q = (size_t)r * a.tr_capacity + (size_t)(base + lane);
+      if (a.tr_sites) { a.tr_sites[2 * q] = pa.x; a.tr_sites[2 * q + 1] = pa.y; }
+      if (a.tr_news) { a.tr_news[2 * q] = (int8_t)pa.z; a.tr_news[2 * q + 1] = (int8_t)pa.w; }
+      if (a.tr_u) a.tr_u[q] = __hiloint2double((int)rec1.y, (int)rec1.x);
+      if (a.tr_acc) a.tr_acc[q] = my_acc ? 1 : 0;
+      if (a.tr_e) a.tr_e[q] = E_after;
+    }
+    __syncwarp();
+    CEMC_OTICK(17);
+    if (!observe) return;
+    if (ref_is_one) {            // Averager reference value 1: value / ref is the value itself
+      int b = 0;
+      for (; b + 3 < nd; b += 4) {
+        double Eb[4], cb[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) { Eb[x] = s.obE[b + x]; cb[x] = s.Ch[(b + x) * 32 + lane]; }
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          aE0 = __dadd_rn(aE0, 1.0);
+          aE1 = __dadd_rn(aE1, Eb[x]);
+          aE2 = __dadd_rn(aE2, __dmul_rn(Eb[x], Eb[x]));
+          aS0 = __dadd_rn(aS0, cb[x]);
+          aS1 = __dadd_rn(aS1, __dmul_rn(cb[x], cb[x]));
+          aS2 = __dadd_rn(aS2, __dmul_rn(cb[x], Eb[x]));
+        }
+      }
+      for (; b < nd; b++) {
+        const double Eb = s.obE[b], cb = s.Ch[b * 32 + lane];
+        aE0 = __dadd_rn(aE0, 1.0);
+        aE1 = __dadd_rn(aE1, Eb);
+        aE2 = __dadd_rn(aE2, __dmul_rn(Eb, Eb));
+        aS0 = __dadd_rn(aS0, cb);
+        aS1 = __dadd_rn(aS1, __dmul_rn(cb, cb));
+        aS2 = __dadd_rn(aS2, __dmul_rn(cb, Eb));
+      }
+    } else {
+      for (int b = 0; b < nd; b++) {
+        const double Eb = s.obE[b], cb = s.Ch[b * 32 + lane];
+        const double e2 = __dmul_rn(Eb, Eb);
+        aE0 = __dadd_rn(aE0, 1.0);
+        aE1 = __dadd_rn(aE1, exact_div(Eb, ref, rref));
+        aE2 = __dadd_rn(aE2, exact_div(e2, ref, rref));
+        aS0 = __dadd_rn(aS0, cb);
+        aS1 = __dadd_rn(aS1, __dmul_rn(cb, cb));
+        aS2 = __dadd_rn(aS2, __dmul_rn(cb, Eb));
+      }
+    }
+    CEMC_OTICK(18);
+  };
+
   long long fill_end = 0;              // records of steps [sdone, fill_end) are in the ring
   if (is_obs) { produce32(0); produce32(32); produce32(64); }
+  if (is_obs && crank == 0) { s.pub[lane] = cf_reg; if (lane == 0) s.pub[32] = e_cur; }
   fill_end = 96;
   csync();
 
-#ifdef CEMC_PHASE_TIMING
-  unsigned long long tph[16] = {0};
-  long long tlast = clock64();
-#endif
   long long sdone = 0;                 // moves decided so far
 
   while (sdone < a.n_steps) {
     const int nb = (int)((a.n_steps - sdone) < BT ? (a.n_steps - sdone) : BT);
     CEMC_TICK(0);
 
+#ifdef CEMC_PHASE_TIMING
+    const long long tob0 = clock64();
+#endif
     // ---- observer warp: next 32 proposal records, then the observer sums -----------------
     const bool refill = (fill_end - sdone) <= 64;
     if (is_obs && refill) produce32(fill_end);        // visible after the E1 barrier
+#ifdef CEMC_PHASE_TIMING
+    if (is_obs && lane == 0) tph[19] += (unsigned long long)(clock64() - tob0);
+#endif
     if (refill) fill_end += 32;
-    // ---- observer warp: Averager / SGCObserver sums of the previous batch ---------------
-    // (montecarlo.py:811-814, mc_observers.py:264-270), in move order, while the
-    // evaluation warps work on the next batch
-    if (is_obs && crank == 0 && observe && ob_pending > 0) {
-      int b = 0;
-      for (; b + 3 < ob_pending; b += 4) {
-        double Eb[4], cb[4];
-#pragma unroll
-        for (int x = 0; x < 4; x++) { Eb[x] = s.obE[b + x]; cb[x] = s.Ch[(b + x) * 32 + lane]; }
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-          const double e2 = __dmul_rn(Eb[x], Eb[x]);
-          aE0 = __dadd_rn(aE0, 1.0);
-          aE1 = __dadd_rn(aE1, ref_is_one ? Eb[x] : exact_div(Eb[x], ref, rref));
-          aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
-          aS0 = __dadd_rn(aS0, cb[x]);
-          aS1 = __dadd_rn(aS1, __dmul_rn(cb[x], cb[x]));
-          aS2 = __dadd_rn(aS2, __dmul_rn(cb[x], Eb[x]));
-        }
-      }
-      for (; b < ob_pending; b++) {
-        const double Eb = s.obE[b];
-        const double cb = s.Ch[b * 32 + lane];
-        const double e2 = __dmul_rn(Eb, Eb);
-        aE0 = __dadd_rn(aE0, 1.0);
-        aE1 = __dadd_rn(aE1, ref_is_one ? Eb : exact_div(Eb, ref, rref));
-        aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
-        aS0 = __dadd_rn(aS0, cb);
-        aS1 = __dadd_rn(aS1, __dmul_rn(cb, cb));
-        aS2 = __dadd_rn(aS2, __dmul_rn(cb, Eb));
-      }
-    }
-    ob_pending = 0;
+    // ---- bookkeeper: exact CF vector, energies, trace and observer sums of the previous batch
+    if (is_obs && crank == 0 && bk_nd > 0) bookkeep(bk_nd, bk_am, bk_base, par ^ 1);
+#ifdef CEMC_PHASE_TIMING
+    const long long tob1 = clock64();
+#endif
     // ---- E1: warp b evaluates move sdone + b against the current state --------------
     int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check); host: NJ*KP <= 64
     if (warp < nb) {
@@ -365,10 +526,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         old0 = new1; old1 = new0;
       }
       double *Vb = s.V + lwarp * NJ * VS;
-      if (lane < C) {                            // every CTA gets the proposal (conflict masks)
-        int32_t *pp = prop_of[0] + b * 8;
-#pragma unroll
-        for (int q = 1; q < C; q++) if (lane == q) pp = prop_of[q] + b * 8;
+      double *sqb = s0.sq + par * (BT * 64) + b * 64;   // this move's per-ECI quotients [2][32]
+      if (lane == 0) {                           // the deciding warp commits from this record
+        int32_t *pp = s0.prop + par * (BT * 8) + b * 8;
         *reinterpret_cast<int4 *>(pp) = make_int4(site0, site1, new0, new1);
         *reinterpret_cast<int4 *>(pp + 4) = make_int4(old0, old1, slot0, slot1);
       }
@@ -378,13 +538,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         const int sites[2] = {site0, site1};
         const int olds[2] = {old0, old1}, news[2] = {new0, new1};
 #pragma unroll
-        for (int x = 0; x < 2; x++) {                     // gathered sites (conflict check)
-          const int q = lane + 32 * x;
-          if (q < NJ * KP) {
-            const int j = q >= KP, c = j ? q - KP : q;
-            gsx[x] = c < K ? __ldg(&t.trans[(size_t)sites[j] * K + c]) : sites[j];
-          }
-        }
+        for (int j = 0; j < NJ; j++)                      // gathered sites (conflict check)
+          if (lane < KP) gsx[j] = lane < K ? __ldg(&t.trans[(size_t)sites[j] * K + lane]) : sites[j];
 #pragma unroll
         for (int j = 0; j < NJ; j++) {
           const int32_t *row = t.trans + (size_t)sites[j] * K;
@@ -405,20 +560,132 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           }
           const int dsig = 2 * sp.b0 * (olds[j] - news[j]);          // sigma_new - sigma_old
           const int num = s_coef * dsig * (s_msub - 2 * cnt);
-          s0.sq[(b * 2 + j) * 32 + lane] = exact_div((double)num, f_den, f_rden);   // :402
+          sqb[j * 32 + lane] = exact_div((double)num, f_den, f_rden);   // :402
         }
-        if (!kCanon) s0.sq[(b * 2 + 1) * 32 + lane] = 0.0;
-        double de = f_kind > 0 ? eci_reg * (s0.sq[(b * 2 + 0) * 32 + lane] + s0.sq[(b * 2 + 1) * 32 + lane]) : 0.0;
+        if (!kCanon) sqb[32 + lane] = 0.0;
+        double de = f_kind > 0 ? eci_reg * (sqb[lane] + sqb[32 + lane]) : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
         if (lane == 0) s0.dEa[b] = de * dN;
+      } else if (kTab) {
+        CEMC_TICK(5);
+        // ---- table evaluation: neighbour occupations stay in registers (lane c = column c),
+        // sub-cluster codes by shuffles, sums over sub-clusters from the product tables
+        const int sites[2] = {site0, site1};
+        const int olds[2] = {old0, old1}, news[2] = {new0, new1};
+        uint32_t *cw = s.codes + lwarp * NJ * n_sub;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+          int v = 0;
+          if (lane < K) {
+            const int nbs = __ldg(&t.trans[(size_t)sites[j] * K + lane]);        // :264
+            gsx[j] = nbs;
+            v = s.occ[nbs];
+            if (j && nbs == site0) v = new0;      // change 1 sees change 0 applied (:845-852)
+          } else if (lane == K) gsx[j] = sites[j];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (q < t_rounds) {
+              const int va = __shfl_sync(0xffffffffu, v, (int)(tdx[q] & 0xffu));
+              const int vb = __shfl_sync(0xffffffffu, v, (int)((tdx[q] >> 8) & 0xffu));
+              const int vc = __shfl_sync(0xffffffffu, v, (int)((tdx[q] >> 16) & 0xffu));
+              const uint32_t rest = (uint32_t)va * (tdy[q] & 0xffu) + (uint32_t)vb * ((tdy[q] >> 8) & 0xffu) +
+                                    (uint32_t)vc * ((tdy[q] >> 16) & 0xffu);
+              const uint32_t wr = tdy[q] >> 24, nd = tdx[q] >> 24;    // nd: decorations per table row
+              const uint32_t cO = (rest + (uint32_t)olds[j] * wr) * nd, cN = (rest + (uint32_t)news[j] * wr) * nd;
+              uint32_t word = (cO << 3) | (cN << 19);
+              if (tdy[q] == 0u) { const uint32_t z = tdx[q] & 0xffffu; word = z | (z << 16); }   // padding: the table's zero row
+              if (q * 32 + lane < n_sub) cw[j * n_sub + q * 32 + lane] = word;
+            }
+          }
+        }
+        __syncwarp();
+        CEMC_TICK(6);
+        // sums over the sub-clusters, reference order (:246-282) or 4-way interleaved (TREE);
+        // lane = (ECI, decoration), both changed sites side by side
+        double *db = s.diff + lwarp * NJ * max_tasks;
+        for (int tk = lane; tk < n_tasks; tk += 32) {
+          const int4 tt = s.ttask[tk];
+          const char *tbl = reinterpret_cast<const char *>(s.tab) + tt.x;
+          const uint32_t *cp = cw + tt.y;
+          auto TV = [&](uint32_t off) { return *reinterpret_cast<const double *>(tbl + off); };
+          if (!kTree) {
+            double spO[NJ], spN[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; j++) { spO[j] = 0.0; spN[j] = 0.0; }
+#pragma unroll 1
+            for (int m = 0; m < tt.z; m += 8) {         // M is padded to a multiple of 8 with zero entries
+              uint4 w[NJ][2];
+#pragma unroll
+              for (int j = 0; j < NJ; j++) {
+                w[j][0] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m);
+                w[j][1] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m + 4);
+              }
+              double vo[NJ][8], vn[NJ][8];
+#pragma unroll
+              for (int j = 0; j < NJ; j++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                  vo[j][4 * h + 0] = TV(w[j][h].x & 0xffffu); vn[j][4 * h + 0] = TV(w[j][h].x >> 16);
+                  vo[j][4 * h + 1] = TV(w[j][h].y & 0xffffu); vn[j][4 * h + 1] = TV(w[j][h].y >> 16);
+                  vo[j][4 * h + 2] = TV(w[j][h].z & 0xffffu); vn[j][4 * h + 2] = TV(w[j][h].z >> 16);
+                  vo[j][4 * h + 3] = TV(w[j][h].w & 0xffffu); vn[j][4 * h + 3] = TV(w[j][h].w >> 16);
+                }
+#pragma unroll
+              for (int x = 0; x < 8; x++)
+#pragma unroll
+                for (int j = 0; j < NJ; j++) { spO[j] = __dadd_rn(spO[j], vo[j][x]); spN[j] = __dadd_rn(spN[j], vn[j][x]); }
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; j++) db[j * max_tasks + tk] = __dsub_rn(spN[j], spO[j]);     // :397
+          } else {
+#pragma unroll
+            for (int j = 0; j < NJ; j++) {
+              double o[4] = {0.0, 0.0, 0.0, 0.0}, n[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+              for (int m = 0; m < tt.z; m += 4) {
+                const uint4 w = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m);
+                o[0] = __dadd_rn(o[0], TV(w.x & 0xffffu)); n[0] = __dadd_rn(n[0], TV(w.x >> 16));
+                o[1] = __dadd_rn(o[1], TV(w.y & 0xffffu)); n[1] = __dadd_rn(n[1], TV(w.y >> 16));
+                o[2] = __dadd_rn(o[2], TV(w.z & 0xffffu)); n[2] = __dadd_rn(n[2], TV(w.z >> 16));
+                o[3] = __dadd_rn(o[3], TV(w.w & 0xffffu)); n[3] = __dadd_rn(n[3], TV(w.w >> 16));
+              }
+              db[j * max_tasks + tk] = __dsub_rn(__dadd_rn(__dadd_rn(n[0], n[1]), __dadd_rn(n[2], n[3])),
+                                                 __dadd_rn(__dadd_rn(o[0], o[1]), __dadd_rn(o[2], o[3])));
+            }
+          }
+        }
+        __syncwarp();
+        CEMC_TICK(7);
+        // per-ECI quotients (:393-402): lane i = ECI i, both changed sites
+        {
+          double num0 = 0.0, num1 = 0.0;
+          if (f_kind == 1) {                                  // :366-371
+            num0 = __dsub_rn(s.bf[f_d * S + new0], s.bf[f_d * S + old0]);
+            if (kCanon) num1 = __dsub_rn(s.bf[f_d * S + new1], s.bf[f_d * S + old1]);
+          } else if (f_kind == 2) {
+            for (int q = 0; q < f_nd; q++) {                  // :397
+              num0 = __dadd_rn(num0, db[f_t0 + q]);
+              if (kCanon) num1 = __dadd_rn(num1, db[max_tasks + f_t0 + q]);
+            }
+            num0 = __dmul_rn(num0, f_scale);                  // :400
+            num1 = __dmul_rn(num1, f_scale);
+          }
+          const double qa = exact_div(num0, f_den, f_rden);                     // :402
+          const double qb = kCanon ? exact_div(num1, f_den, f_rden) : 0.0;
+          sqb[lane] = qa;
+          sqb[32 + lane] = qb;
+          double de = f_kind > 0 ? eci_reg * (qa + qb) : 0.0;   // screen only
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
+          if (lane == 0) s0.dEa[b] = de * dN;
+        }
       } else {
       // P1: gather
 #pragma unroll
-      for (int x = 0; x < 2; x++) {
-        const int q = lane + 32 * x;
-        if (q < NJ * KP) {
-          const int j = q >= KP, c = j ? q - KP : q;
+      for (int x = 0; x < NJ; x++) {
+        if (lane < KP) {
+          const int j = x, c = lane;
           double *Vj = Vb + j * VS;
           const int sj = j ? site1 : site0;
           if (c < K) {
@@ -534,8 +801,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         }
         const double qa = exact_div(num0, f_den, f_rden);                     // :402
         const double qb = kCanon ? exact_div(num1, f_den, f_rden) : 0.0;
-        s0.sq[(b * 2 + 0) * 32 + lane] = qa;
-        s0.sq[(b * 2 + 1) * 32 + lane] = qb;
+        sqb[lane] = qa;
+        sqb[32 + lane] = qb;
         // state-independent energy change of this move, N * sum_i eci_i (q0_i + q1_i):
         // only used to SCREEN the Metropolis test (any summation order will do)
         double de = f_kind > 0 ? eci_reg * (qa + qb) : 0.0;
@@ -544,22 +811,65 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         if (lane == 0) s0.dEa[b] = de * dN;
       }
       }
-    }
-    csync();
-    CEMC_TICK(1);
-
-    // ---- E2: which earlier moves of the batch would invalidate this evaluation? -------
-    if (warp < nb) {
-      uint32_t m = 0;
-      for (int k = 0; k < warp; k++) {
-        const int sk0 = s.prop[k * 8], sk1 = s.prop[k * 8 + 1];       // sk1 = -1 for SGC
-        const bool hit = (gsx[0] == sk0) | (gsx[1] == sk0) | (kCanon & ((gsx[0] == sk1) | (gsx[1] == sk1)));
-        if (__ballot_sync(0xffffffffu, hit)) m |= 1u << k;
+      CEMC_TICK(12);
+      // ---- which earlier moves of the batch would invalidate this evaluation?  Lane k
+      // holds the site(s) move k changes if accepted (state independent for SGC; for swaps
+      // the current list entries: had an accepted move changed them, move k would be
+      // invalid itself and the batch would end before it); every gathered site of this
+      // move is broadcast once and compared by all lanes.
+      {
+        int sk0 = -2, sk1 = -2;
+        if (lane < b) {
+          const uint4 rk = s.ring[(int)((sdone + lane) & 127) * 2];
+          if (!kCanon) sk0 = t.active ? t.active[rk.x] : (int)rk.x;
+          else { sk0 = s.list[rk.x]; sk1 = s.list[rk.y]; }
+        }
+        // gsx[j]: lanes 0..K hold the K neighbours and the changed site itself.  The other
+        // 32 - KP lanes take the sk values of a few moves per round and one MATCH finds the
+        // lanes holding equal values: a hit is an sk lane matching a gathered-site lane.
+        uint32_t m = 0;
+        const int slots = 32 - KP;
+        if (slots >= 8) {
+          const int h = kCanon ? slots / 2 : slots;          // moves per round
+          const uint32_t gmask = (1u << KP) - 1u;
+          for (int mv0 = 0; mv0 < b; mv0 += h) {
+            const int q = lane - KP;                           // slot of this lane
+            const int mv = mv0 + (kCanon && q >= h ? q - h : q);
+            const bool is_sk = q >= 0 && q < (kCanon ? 2 * h : h) && mv < b;
+            const int a0 = __shfl_sync(0xffffffffu, sk0, is_sk ? mv : 0);
+            const int a1 = kCanon ? __shfl_sync(0xffffffffu, sk1, is_sk ? mv : 0) : 0;
+            const int val = (kCanon && q >= h) ? a1 : a0;
+            uint32_t hb = 0;
+#pragma unroll
+            for (int j = 0; j < NJ; j++) {
+              const int x = lane < KP ? gsx[j] : (is_sk ? val : -3 - lane);
+              const uint32_t mm = __match_any_sync(0xffffffffu, x);
+              hb |= __ballot_sync(0xffffffffu, is_sk && (mm & gmask) != 0u);
+            }
+            hb >>= KP;
+            if (kCanon) hb = (hb | (hb >> h)) & ((1u << h) - 1u);
+            m |= hb << mv0;
+          }
+        } else {
+          bool hit = false;
+#pragma unroll
+          for (int j = 0; j < NJ; j++)
+            for (int q = 0; q < KP; q++) {
+              const int g = __shfl_sync(0xffffffffu, gsx[j], q);
+              hit |= (g == sk0) | (kCanon & (g == sk1));
+            }
+          m = __ballot_sync(0xffffffffu, hit);
+        }
+        if (lane == 0) s0.cmask[b] = (int32_t)m;
       }
-      if (lane == 0) s0.cmask[warp] = (int32_t)m;
+      CEMC_TICK(13);
     }
     csync();
-    CEMC_TICK(2);
+#ifdef CEMC_PHASE_TIMING
+    if (*reinterpret_cast<volatile int32_t *>(s.ctl + 7) == 0x7fffffff) tlast = 0;   // wait for the barrier release
+    if (is_obs && crank == 0 && lane == 0) { tph[14] += (unsigned long long)(tob1 - tob0); tph[15] += (unsigned long long)(clock64() - tob1); }
+#endif
+    CEMC_TICK(1);
 
     // ---- D: warp 0 decides the moves strictly in order ---------------------------------
     // The Metropolis outcome of a move depends on the chain state only through
@@ -575,29 +885,29 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       const double u_l = __hiloint2double((int)rec1.y, (int)rec1.x);
       const double L_l = __hiloint2double((int)rec1.w, (int)rec1.z);
       const double dE_l = s.dEa[lane < nb ? lane : 0];
-      const double band = 1e-9 * a.screen_slack * fmax(fabs(dE_l), fabs(L_l)) + etol;
+      const double band = a.screen_slack * (4e-7 * (kT + fabs(L_l)) + 1e-9 * fabs(dE_l)) + etol;
       const bool t_acc = lane < nb && (dE_l < L_l - band);
       const bool t_bdr = lane < nb && !t_acc && !(dE_l > L_l + band);
       const uint32_t tmask = __ballot_sync(0xffffffffu, t_acc);
       const uint32_t bmask = __ballot_sync(0xffffffffu, t_bdr);
       const uint32_t cm_l = lane < nb ? (uint32_t)s.cmask[lane] : 0u;
       uint32_t tm = tmask;
-      double c = cf_reg;                 // CF of this lane's ECI, after the moves decided so far
-      double E_l = 0.0;                  // lane b: energy after move b (if accepted)
       if (bmask & 1u) {
         // move 0 is inconclusive: exact path (rare) -- ordered dot (named_array.cpp:27-31)
-        // and the reference expression (montecarlo.py:951-956) on the current state
-        double cn = c;
+        // and the reference expression (montecarlo.py:951-956) on the current state, which
+        // the bookkeeper published after the previous batch
+        double cn = s.pub[lane];
+        const double e_old = s.pub[32];
         if (f_kind > 0) {
-          cn = __dadd_rn(cn, s.sq[lane]);
-          if (kCanon) cn = __dadd_rn(cn, s.sq[32 + lane]);
+          cn = __dadd_rn(cn, s.sq[par * (BT * 64) + lane]);
+          if (kCanon) cn = __dadd_rn(cn, s.sq[par * (BT * 64) + 32 + lane]);
         }
         const double p = __dmul_rn(eci_reg, cn);
         double e_new = 0.0;
         for (int i = 0; i < n_eci4; i++) e_new = __dadd_rn(e_new, __shfl_sync(0xffffffffu, p, i));
         e_new = __dmul_rn(e_new, dN);
         const double ub = __shfl_sync(0xffffffffu, u_l, 0);
-        if (metropolis(e_new, e_cur, ub, kT, rkT)) tm |= 1u; else tm &= ~1u;
+        if (metropolis(e_new, e_old, ub, kT, rkT)) tm |= 1u; else tm &= ~1u;
       }
       // In-order semantics without a loop: all moves before the first invalid one are
       // decided by their screen bit, so move b is invalid iff one of the moves it
@@ -608,70 +918,14 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       const uint32_t stops = __ballot_sync(0xffffffffu, stop_here);
       const int ndone = stops ? (__ffs(stops) - 1) : nb;
       const uint32_t accmask = tm & (ndone >= 32 ? 0xffffffffu : ((1u << ndone) - 1u));
-      // CF vector through the accepted moves, in order (:404); products for the dots
-      {
-        uint32_t rem = accmask;
-        int bn = rem ? __ffs(rem) - 1 : 0;
-        double qa = s.sq[(bn * 2 + 0) * 32 + lane], qb = kCanon ? s.sq[(bn * 2 + 1) * 32 + lane] : 0.0;
-        int bprev = 0;
-        while (rem) {
-          const int bc = bn;
-          rem &= rem - 1;
-          const double qa_c = qa, qb_c = qb;
-          if (rem) {                                         // prefetch the next accepted move
-            bn = __ffs(rem) - 1;
-            qa = s.sq[(bn * 2 + 0) * 32 + lane];
-            if (kCanon) qb = s.sq[(bn * 2 + 1) * 32 + lane];
-          }
-          for (int x = bprev; x < bc; x++) s.Ch[x * 32 + lane] = c;     // rejected moves keep c
-          if (f_kind > 0) {                                  // kinds 0 / -1: copied (:360,:382)
-            c = __dadd_rn(c, qa_c);                          // :404
-            if (kCanon) c = __dadd_rn(c, qb_c);
-          }
-          s.Pm[bc * 33 + lane] = __dmul_rn(eci_reg, c);
-          s.Ch[bc * 32 + lane] = c;
-          bprev = bc + 1;
-        }
-        for (int x = bprev; x < ndone; x++) s.Ch[x * 32 + lane] = c;
-      }
-      __syncwarp();
-      // exact energies of the accepted moves, one lane per move (ordered dot, :236-242)
+      n_acc += __popc(accmask);
       const bool my_acc = lane < ndone && ((accmask >> lane) & 1u);
-      if (my_acc) {
-        const double *pm = s.Pm + lane * 33;
-        double e = 0.0;
-        int i = 0;
-        for (; i + 7 < n_eci; i += 8) {
-          double v[8];
-#pragma unroll
-          for (int x = 0; x < 8; x++) v[x] = pm[i + x];
-#pragma unroll
-          for (int x = 0; x < 8; x++) e = __dadd_rn(e, v[x]);
-        }
-        for (; i < n_eci; i++) e = __dadd_rn(e, pm[i]);
-        E_l = __dmul_rn(e, dN);
-      }
-      // energy after move b = energy of the last accepted move <= b (else the old one)
-      double E_after;
-      {
-        const uint32_t upto = accmask & (lane >= 31 ? 0xffffffffu : ((2u << lane) - 1u));
-        const int src = upto ? 31 - __clz(upto) : 0;
-        const double Es = __shfl_sync(0xffffffffu, E_l, src);
-        E_after = upto ? Es : e_cur;
-      }
-      if (accmask) {
-        const int last = 31 - __clz(accmask);
-        e_cur = __shfl_sync(0xffffffffu, E_l, last);
-        cf_reg = c;
-        n_acc += __popc(accmask);
-      }
-      if (lane < ndone) s.obE[lane] = E_after;      // the observer warp folds these in during the next E1
       // commits of the decided moves: lane b applies move b (accepted moves of one
       // batch never share a site, so the order among them is irrelevant)
       if (lane < ndone) {
-        const int4 pa = *reinterpret_cast<const int4 *>(s.prop + lane * 8);
-        const int4 pb = *reinterpret_cast<const int4 *>(s.prop + lane * 8 + 4);
         if (my_acc) {
+          const int4 pa = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8);
+          const int4 pb = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8 + 4);
 #pragma unroll
           for (int q = 0; q < (kStateSmem ? C : 1); q++) {       // every CTA's copy of the state
             occ_of[q][pa.x] = (int8_t)pa.z;
@@ -682,81 +936,49 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           }
           if (kCanon) { g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z); }
         }
-        if (tracing && sdone + lane < a.tr_capacity) {
-          const size_t q = (size_t)r * a.tr_capacity + (size_t)(sdone + lane);
-          if (a.tr_sites) { a.tr_sites[2 * q] = pa.x; a.tr_sites[2 * q + 1] = pa.y; }
-          if (a.tr_news) { a.tr_news[2 * q] = (int8_t)pa.z; a.tr_news[2 * q + 1] = (int8_t)pa.w; }
-          if (a.tr_u) a.tr_u[q] = u_l;
-          if (a.tr_acc) a.tr_acc[q] = my_acc ? 1 : 0;
-          if (a.tr_e) a.tr_e[q] = E_after;
-        }
       }
       if (!kStateSmem) { if (C > 1) __threadfence(); else __threadfence_block(); }
       if (lane < C) {
         int32_t *cp = ctl_of[0];
 #pragma unroll
         for (int q = 1; q < C; q++) if (lane == q) cp = ctl_of[q];
-        cp[0] = ndone;
+        *reinterpret_cast<int2 *>(cp) = make_int2(ndone, (int)accmask);
       }
       CEMC_TICK(3);
 #ifdef CEMC_PHASE_TIMING
-      if (tid == 0) { tph[8] += 1; tph[9] += ndone; }
+      if (tid == 0) { tph[8] += 1; tph[9] += ndone; tph[10] += __popc(accmask); tph[11] += (stops ? 1 : 0); }
 #endif
     }
     csync();
-    sdone += s.ctl[0];
-    ob_pending = s.ctl[0];
-    csync();
+#ifdef CEMC_PHASE_TIMING
+    if (*reinterpret_cast<volatile int32_t *>(s.ctl + 7) == 0x7fffffff) tlast = 0;
+#endif
+    {   // rewritten only after the next barrier: no second barrier needed
+      const int2 ct = *reinterpret_cast<const int2 *>(s.ctl);
+      bk_nd = ct.x; bk_am = (uint32_t)ct.y; bk_base = sdone;
+      sdone += ct.x;
+      par ^= 1;
+    }
     CEMC_TICK(4);
   }
-  // ---- observer warp: Averager / SGCObserver sums of the previous batch ---------------
-  // (montecarlo.py:811-814, mc_observers.py:264-270), in move order, while the
-  // evaluation warps work on the next batch
-  if (is_obs && crank == 0 && observe && ob_pending > 0) {
-    int b = 0;
-    for (; b + 3 < ob_pending; b += 4) {
-      double Eb[4], cb[4];
-#pragma unroll
-      for (int x = 0; x < 4; x++) { Eb[x] = s.obE[b + x]; cb[x] = s.Ch[(b + x) * 32 + lane]; }
-#pragma unroll
-      for (int x = 0; x < 4; x++) {
-        const double e2 = __dmul_rn(Eb[x], Eb[x]);
-        aE0 = __dadd_rn(aE0, 1.0);
-        aE1 = __dadd_rn(aE1, ref_is_one ? Eb[x] : exact_div(Eb[x], ref, rref));
-        aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
-        aS0 = __dadd_rn(aS0, cb[x]);
-        aS1 = __dadd_rn(aS1, __dmul_rn(cb[x], cb[x]));
-        aS2 = __dadd_rn(aS2, __dmul_rn(cb[x], Eb[x]));
-      }
-    }
-    for (; b < ob_pending; b++) {
-      const double Eb = s.obE[b];
-      const double cb = s.Ch[b * 32 + lane];
-      const double e2 = __dmul_rn(Eb, Eb);
-      aE0 = __dadd_rn(aE0, 1.0);
-      aE1 = __dadd_rn(aE1, ref_is_one ? Eb : exact_div(Eb, ref, rref));
-      aE2 = __dadd_rn(aE2, ref_is_one ? e2 : exact_div(e2, ref, rref));
-      aS0 = __dadd_rn(aS0, cb);
-      aS1 = __dadd_rn(aS1, __dmul_rn(cb, cb));
-      aS2 = __dadd_rn(aS2, __dmul_rn(cb, Eb));
-    }
-  }
-
+  if (is_obs && crank == 0 && bk_nd > 0) bookkeep(bk_nd, bk_am, bk_base, par ^ 1);
 
 #ifdef CEMC_PHASE_TIMING
-  if (tid == 0 && r == 0)
-    for (int i = 0; i < 16; i++) g_phase_cycles[i] = tph[i];
+  if (tid == 0 && crank == 0 && a.phase)
+    for (int i = 0; i < 14; i++) a.phase[(size_t)r * 24 + i] = tph[i];
+  if (is_obs && lane == 0 && crank == 0 && a.phase)
+    for (int i = 14; i < 24; i++) a.phase[(size_t)r * 24 + i] = tph[i];
 #endif
   // ---- write back ------------------------------------------------------------
   if (is_obs && crank == 0) {
     double *aw = st.acc + (size_t)r * acc_stride;
     if (lane == 0) { aw[0] = aE0; aw[1] = aE1; aw[2] = aE2; }
     if (my_singlet >= 0) { aw[3 + 3 * my_singlet] = aS0; aw[4 + 3 * my_singlet] = aS1; aw[5 + 3 * my_singlet] = aS2; }
+    if (lane < n_eci) st.cf[(size_t)r * n_eci + lane] = cf_reg;
+    if (lane == 0) st.e_cur[r] = e_cur;
   }
   if (warp == 0) {
-    if (lane < n_eci) st.cf[(size_t)r * n_eci + lane] = cf_reg;
     if (lane == 0) {
-      st.e_cur[r] = e_cur;
       st.step[r] = step0 + (unsigned long long)a.n_steps;
       st.accepted[r] += n_acc;
     }

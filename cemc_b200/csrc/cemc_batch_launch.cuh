@@ -1,0 +1,88 @@
+// cemc_batch_launch.cuh -- host-side launcher of batch_kernel, shared by the three
+// translation units that instantiate it (one per evaluation scheme: fp64 products,
+// binary spin, product tables), so that they compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "cemc_batch_kernel.cuh"
+
+namespace cemc {
+
+struct BatchLaunch {
+  int mode;               // MODE_SGC | MODE_CANONICAL
+  int tree;               // TREE summation order
+  int B, C;               // moves per CTA, CTAs per chain
+  int R;                  // replicas
+  int max_smem_optin;
+  cudaStream_t stream;
+  DeviceTables t;
+  ReplicaState st;
+  RunArgs a;
+  int acc_stride;
+  SpinTables sp;
+  TabTables tb;
+};
+
+// -1: not applicable (does not fit); 0: launched; > 0: cudaError_t + 1000
+int batch_launch_product(const BatchLaunch &L);
+int batch_launch_spin(const BatchLaunch &L);
+int batch_launch_tab(const BatchLaunch &L);
+
+template <int MODE, bool kTree, int B, bool kSmem, int C, int EV>
+static int batch_launch_kc(const BatchLaunch &L, size_t sm) {
+  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return 1000 + (int)e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(L.R * C);
+  cfg.blockDim = dim3((B + 1) * 32);
+  cfg.dynamicSmemBytes = sm;
+  cfg.stream = L.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = C > 1 ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, L.t, L.st, L.a, L.acc_stride, L.sp, L.tb);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : 1000 + (int)e;
+}
+
+template <int MODE, bool kTree, int B, int C, int EV>
+static int batch_launch_b(const BatchLaunch &L) {
+  const TabTables *tb = EV == EV_TAB ? &L.tb : nullptr;
+  size_t sm = batch_smem_layout<B, B * C>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, tb);
+  const bool in_smem = sm <= (size_t)L.max_smem_optin;
+  if (!in_smem) sm = batch_smem_layout<B, B * C>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, false, tb);
+  if (sm > (size_t)L.max_smem_optin) return -1;
+  return in_smem ? batch_launch_kc<MODE, kTree, B, true, C, EV>(L, sm)
+                 : batch_launch_kc<MODE, kTree, B, false, C, EV>(L, sm);
+}
+
+template <int MODE, bool kTree, int EV>
+static int batch_launch_bc(const BatchLaunch &L) {
+  // L.B counts the warps of a CTA: B - 1 evaluation warps (moves per batch) + the observer
+  // warp; power-of-two CTAs get the full register budget (512 threads x 128 registers)
+  if (L.B == 16 && L.C == 2) return batch_launch_b<MODE, kTree, 15, 2, EV>(L);
+  if (L.B == 16 && L.C == 1) return batch_launch_b<MODE, kTree, 15, 1, EV>(L);
+  if (L.B == 8 && L.C == 1) return batch_launch_b<MODE, kTree, 7, 1, EV>(L);
+  if (L.B == 4 && L.C == 1) return batch_launch_b<MODE, kTree, 3, 1, EV>(L);
+  return -1;
+}
+
+// kBothOrders = false: only the TREE instantiation exists (binary +-1 basis: every
+// order gives the same bits, the host always asks for TREE)
+template <int EV, bool kBothOrders>
+static int batch_launch_ev(const BatchLaunch &L) {
+  if (L.mode == MODE_SGC) {
+    if constexpr (kBothOrders) { if (!L.tree) return batch_launch_bc<MODE_SGC, false, EV>(L); }
+    return batch_launch_bc<MODE_SGC, true, EV>(L);
+  }
+  if (L.mode == MODE_CANONICAL) {
+    if constexpr (kBothOrders) { if (!L.tree) return batch_launch_bc<MODE_CANONICAL, false, EV>(L); }
+    return batch_launch_bc<MODE_CANONICAL, true, EV>(L);
+  }
+  return -1;
+}
+
+}  // namespace cemc

@@ -40,7 +40,6 @@ namespace cemc {
 // -DCEMC_PHASE_TIMING: per-phase clock64() accounting of warp 0 (debug builds only;
 // scripts/phase_timing.py).  Slots: 0 refill 1 P0 2 P1 3 P2a 4 P2b 5 P3 6 end barrier
 #ifdef CEMC_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[16];
 #define CEMC_TICK(slot)                                              \
   do {                                                               \
     const long long now_ = clock64();                                \
@@ -119,6 +118,7 @@ struct RunArgs {
   uint8_t *tr_acc;
   double *tr_e;
   long long tr_capacity;
+  unsigned long long *phase;   // [R][24] per-phase cycle counts (CEMC_PHASE_TIMING builds), may be null
 };
 
 // ---------------------------------------------------------------------------
@@ -660,8 +660,8 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
     }
   }
 #ifdef CEMC_PHASE_TIMING
-  if (tid == 0 && r == 0)
-    for (int i = 0; i < 16; i++) g_phase_cycles[i] = tph[i];
+  if (tid == 0 && a.phase)
+    for (int i = 0; i < 16; i++) a.phase[(size_t)r * 24 + i] = tph[i];
 #endif
 
   // ---- write back --------------------------------------------------------
@@ -691,7 +691,7 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
 }
 
 // cemc_selftest_division: exact_div against IEEE division on random operands
-__global__ void exact_div_selftest_kernel(unsigned long long seed, int iters, const double *dens,
+static __global__ void exact_div_selftest_kernel(unsigned long long seed, int iters, const double *dens,
                                           int n_dens, unsigned long long *mismatches) {
   const unsigned long long gid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   unsigned long long bad = 0;

@@ -150,6 +150,16 @@ class BatchedCEUpdater(object):
     def set_autotune(self, on: bool):
         _lib.check(self.lib.cemc_set_autotune(self._h, int(bool(on))))
 
+    def set_table_eval(self, on: bool):
+        """Testing hook: product tables (default) vs fp64 products in the batch kernel."""
+        _lib.check(self.lib.cemc_set_table_eval(self._h, 1 if on else 0))
+
+    def get_batch_eval(self) -> int:
+        """0 fp64 products, 1 binary spin, 2 product tables."""
+        v = C.c_int32(-1)
+        _lib.check(self.lib.cemc_get_batch_eval(self._h, C.byref(v)))
+        return v.value
+
     def set_variant(self, sgc: int = -1, canonical: int = -1):
         _lib.check(self.lib.cemc_set_variant(self._h, int(sgc), int(canonical)))
 

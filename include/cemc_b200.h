@@ -133,12 +133,18 @@ int cemc_set_variant(cemc_handle *h, int sgc, int canonical);
 int cemc_set_cluster(cemc_handle *h, int c);
 /* testing hook: 0 = do not use the binary spin kernel (cemc_spin_kernel.cuh)   */
 int cemc_set_spin_kernel(cemc_handle *h, int on);
+/* testing hook: 0 = keep the fp64 product evaluation in the batch kernel instead of
+ * the product tables (cemc_batch_kernel.cuh, EV_TAB); both give the same bits      */
+int cemc_set_table_eval(cemc_handle *h, int on);
+/* evaluation scheme the batch kernel uses for this system: 0 fp64 products, 1 binary
+ * spin (XOR / popcount), 2 product tables                                          */
+int cemc_get_batch_eval(cemc_handle *h, int *ev);
 /* testing hook: widen the band in which the batch kernel's Metropolis screen
  * defers to the exact expression (factor >= 1; 1e30 = always exact)           */
 int cemc_set_screen_slack(cemc_handle *h, double factor);
-/* debug builds (-DCEMC_PHASE_TIMING) only: clock64() cycles warp 0 of replica 0
+/* debug builds (-DCEMC_PHASE_TIMING) only: clock64() cycles warp 0 of every replica
  * spent per kernel phase in the last launch                                   */
-int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out16 /*[16]*/);
+int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out /*[n_replicas][24]*/);
 int cemc_selftest_division(cemc_handle *h, uint64_t seed, int n_blocks, int iters,
                            uint64_t *mismatches);
 /* threads per CTA (= per replica): 0 = auto, else a multiple of 32 in [32,256] */

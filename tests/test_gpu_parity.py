@@ -449,9 +449,10 @@ def test_sgc_restricted_species(cuda_device):
     assert_state_equal(gpu, chains)
 
 
+@pytest.mark.parametrize("table_eval", [True, False])
 @pytest.mark.parametrize("batch", [-1, 4, 8, 16])
 @pytest.mark.parametrize("mode", ["sgc", "canonical"])
-def test_speculative_batch_kernel(cuda_device, batch, mode):
+def test_speculative_batch_kernel(cuda_device, batch, mode, table_eval):
     """Speculative batch evaluation (cemc_batch_kernel.cuh) keeps the chain
     exactly sequential: every batch size gives the oracle's trajectory, also on
     a tiny cell where moves of one batch collide all the time."""
@@ -460,6 +461,7 @@ def test_speculative_batch_kernel(cuda_device, batch, mode):
         kTs = np.linspace(0.02, 0.2, R)
         gpu, chains = make_pair(ft, [symbols] * R, kTs, seed=41)
         gpu.set_batch(batch)
+        gpu.set_table_eval(table_eval)      # product tables vs fp64 products: same bits
         n = 1500
         gpu.set_trace(n)
         gpu.reset_accumulators()
@@ -528,9 +530,10 @@ def test_large_cell_global_state(cuda_device, species, conc):
     np.testing.assert_allclose(gpu.get_cf()[0], oc.cf, rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("table_eval", [True, False])
 @pytest.mark.parametrize("cluster", [1, 2])
 @pytest.mark.parametrize("mode", ["sgc", "canonical"])
-def test_cta_cluster_batch_kernel(cuda_device, cluster, mode):
+def test_cta_cluster_batch_kernel(cuda_device, cluster, mode, table_eval):
     """Two CTAs of a thread-block cluster cooperating on one chain (DSMEM exchange
     of proposals / quotients / conflict masks, commits to both copies of the
     state): same trajectory as the oracle, for state in shared memory (4^3, 3^3)
@@ -540,6 +543,7 @@ def test_cta_cluster_batch_kernel(cuda_device, cluster, mode):
         kTs = np.linspace(0.02, 0.2, R)
         gpu, chains = make_pair(ft, [symbols] * R, kTs, seed=61)
         gpu.set_cluster(cluster)
+        gpu.set_table_eval(table_eval)
         n = 1200
         gpu.set_trace(n)
         gpu.reset_accumulators()
@@ -604,3 +608,43 @@ def test_batch_kernel_spin_evaluation(cuda_device, batch, cluster, mode):
         accs = gpu.get_accumulators()
         for r, c in enumerate(chains):
             assert np.array_equal(accs[r], c.acc)
+
+
+@pytest.mark.parametrize("order", ["reference", "tree"])
+@pytest.mark.parametrize("batch,cluster", [(4, 1), (8, 1), (16, 1), (16, 2)])
+def test_table_evaluation_quaternary(cuda_device, batch, cluster, order):
+    """Product-table evaluation of the batch kernel on a four-species system (three
+    basis functions, S^n-entry tables per decoration) and, with quadruplets, the
+    fall-back to fp64 products when the tables would not fit: oracle trajectory
+    either way, in the reference's summation order and in TREE order."""
+    from cemc_b200.updater import ORDER_TREE
+    species = ["Al", "Cu", "Mg", "Si"]
+    conc = {"Al": 0.4, "Cu": 0.2, "Mg": 0.2, "Si": 0.2}
+    for families, ev in ((["nn", "2nn", "tri"], 2), (["nn", "tet"], 0)):
+        st, eci, symbols, ft = build(4, species, families, conc)
+        assert ft.n_eci <= 32
+        kTs = [0.03, 0.09]
+        gpu, chains = make_pair(ft, [symbols] * 2, kTs, seed=97)
+        assert gpu.get_batch_eval() == ev
+        gpu.set_batch(batch)
+        gpu.set_cluster(cluster)
+        if order == "tree":
+            gpu.set_order_mode(ORDER_TREE)
+        n = 1000
+        gpu.set_trace(n)
+        gpu.reset_accumulators()
+        gpu.run_sgc(n)
+        gpu.run_canonical(n)
+        gpu.synchronize()
+        tr = gpu.get_trace(n)
+        for r, c in enumerate(chains):
+            c.run_sgc(n)
+            o = c.run_canonical(n, trace=True)
+            assert np.array_equal(tr[3][r], o[3])            # accept/reject sequence
+            if order == "reference":
+                assert np.array_equal(tr[4][r], o[4])
+        if order == "reference":
+            assert_state_equal(gpu, chains)
+        else:
+            assert np.array_equal(gpu.get_occupancy(), np.stack([c.occ for c in chains]))
+            np.testing.assert_allclose(gpu.get_cf(), np.stack([c.cf for c in chains]), rtol=1e-10, atol=1e-13)
