@@ -44,12 +44,12 @@ UNIT = "moves/s"
 # CPU arm: the reference's compiled CEUpdater (or the oracle port) on host cores
 def _cpu_worker(args):
     """One chain on one core; returns (moves, seconds, kind)."""
-    replica, n_moves, warm = args
+    replica, n_moves, warm, which = args
     sys.path.insert(0, ROOT)
     from cemc_b200 import workloads as wl
     from oracle import ref_driver
     from oracle.ce_oracle import OracleChain
-    w = wl.c2_almg_sgc_sweep(R=1, replica_offset=replica)
+    w = wl.WORKLOADS[which](R=1, replica_offset=replica)
     ft = w.tables
     eci_vec = w.eci_matrix[0]
     oc = OracleChain(ft, w.occ[0], kT=w.kT[0], seed=1234, replica=replica, eci=eci_vec)
@@ -58,7 +58,13 @@ def _cpu_worker(args):
         # updater does every energy evaluation (its Python-side accept rule)
         cf0 = {k: float(v) for k, v in zip(ft.eci_names, oc.cf)}
         eci = {k: float(v) for k, v in zip(ft.eci_names, eci_vec)}
-        rc = ref_driver.RefChain(w.settings, ft.symbols_of(w.occ[0]), eci, cf0, kT=w.kT[0])
+        st = w.settings
+        if st.trans_matrix_columns is not None:
+            # the reference reads a dense ndarray or a list of dicts, not our compact form
+            from cemc_b200 import synthetic as syn
+            kw = st.kwargs
+            st = syn.fcc_settings(kw["size"][0], kw["species"], kw["families"], trans_matrix_format="list")
+        rc = ref_driver.RefChain(st, ft.symbols_of(w.occ[0]), eci, cf0, kT=w.kT[0])
         tr = oc.run_sgc(warm + n_moves, trace=True)
         rc.replay(ft.species, tr[0][:warm], tr[1][:warm], tr[2][:warm])
         t0 = time.perf_counter()
@@ -72,20 +78,20 @@ def _cpu_worker(args):
     return n_moves * 10, time.perf_counter() - t0, "port"
 
 
-def cpu_measure(n_moves_per_chain, n_procs=None, warm=500):
+def cpu_measure(n_moves_per_chain, n_procs=None, warm=500, which="C2"):
     n_procs = n_procs or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(n_procs) as pool:
-        res = pool.map(_cpu_worker, [(r, n_moves_per_chain, warm) for r in range(n_procs)])
+        res = pool.map(_cpu_worker, [(r, n_moves_per_chain, warm, which) for r in range(n_procs)])
     wall = time.perf_counter() - t0
     # chains run concurrently, one per core: aggregate = sum of per-chain rates
     rate = sum(m / dt for m, dt, _ in res)
     kind = res[0][2]
     return dict(value=rate, unit=UNIT, cores=n_procs, kind=kind,
                 sample="%d SGC trial moves on each of %d concurrent chains (one per host core) "
-                       "of the C2 workload, %s; wall %.1f s incl. setup" % (
-                           res[0][0], n_procs,
+                       "of the %s workload, %s; wall %.1f s incl. setup" % (
+                           res[0][0], n_procs, which,
                            "reference C++ CEUpdater driven through its Cython PyCEUpdater"
                            if kind == "reference" else "C oracle port", wall))
 
@@ -152,8 +158,11 @@ def gpu_arm(args):
 
     # CPU baseline first (rank 0, N=1 only), before this process touches CUDA
     cpu = None
+    cpu_c3s = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_measure(args.cpu_moves)
+        if not args.no_extra:
+            cpu_c3s = cpu_measure(args.cpu_moves // 4, which="C3S")
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -278,7 +287,8 @@ def gpu_arm(args):
                          "is shared-memory resident by design",
                 "parallelism": "replicas sharded over %d GPU(s), no data-path collective" % world,
                 "kernel_variant": "%d (0 spin, 1-4 batch (16,2)/(16,1)/(8,1)/(4,1), 5 one move at a "
-                                  "time; autotuned unless --variant)" % gpu.get_variant()[0],
+                                  "time, 6-7 batch (8,1)/(16,1) with two moves per warp; autotuned "
+                                  "unless --variant)" % gpu.get_variant()[0],
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
@@ -293,6 +303,8 @@ def gpu_arm(args):
             line["cpu_baseline"] = cpu
         if world == 1 and not args.no_extra:
             line["other_workloads"] = extra_workloads(local_rank)
+            if cpu_c3s is not None:     # the north-star target line: 64-replica Al-Mg-Si SGC sweep
+                line["other_workloads"]["C3S"]["cpu_baseline"] = cpu_c3s
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

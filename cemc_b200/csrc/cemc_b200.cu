@@ -32,7 +32,12 @@ static int fail(const std::string &m, int code = 1) { g_err = m; return code; }
 
 template <class T>
 static cudaError_t upload(T **dst, const T *src, size_t n) {
-  cudaError_t e = cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T));
+  // padded to a multiple of 16 bytes (zero filled): the kernels stage the tables with
+  // TMA bulk copies (cp.async.bulk), whose sizes are multiples of 16 bytes
+  const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 15) / 16 * 16;
+  cudaError_t e = cudaMalloc((void **)dst, bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(*dst, 0, bytes);
   if (e != cudaSuccess) return e;
   if (n) e = cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
   return e;
@@ -809,9 +814,11 @@ int cemc_set_autotune(cemc_handle *h, int on) {
   return 0;
 }
 
+static const int kNumVariants = 8;   // see launch_variant
+
 int cemc_set_variant(cemc_handle *h, int sgc, int canonical) {
   if (!h) return fail("null handle");
-  if (sgc < -1 || sgc >= 6 || canonical < -1 || canonical >= 6) return fail("no such kernel variant");
+  if (sgc < -1 || sgc >= kNumVariants || canonical < -1 || canonical >= kNumVariants) return fail("no such kernel variant");
   h->tuned_sgc = sgc;
   h->tuned_can = canonical;
   return 0;
@@ -1041,11 +1048,11 @@ static RunArgs run_args(cemc_handle *h, long long n_steps) {
 
 // speculative batch kernel with B moves per CTA and C CTAs per chain; -1 when not applicable
 template <int MODE>
-static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C) {
+static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 1) {
   if (h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
       2 * h->t.KP > 64) return -1;
   BatchLaunch L{};
-  L.mode = MODE; L.B = B; L.C = C; L.R = h->R; L.max_smem_optin = h->max_smem_optin;
+  L.mode = MODE; L.B = B; L.C = C; L.M = M; L.R = h->R; L.max_smem_optin = h->max_smem_optin;
   L.tree = ((h->order_mode == CEMC_ORDER_TREE) || h->integer_bf) ? 1 : 0;
   L.stream = h->stream; L.t = h->t; L.st = h->st; L.a = a; L.acc_stride = h->acc_stride;
   L.sp = h->spin; L.tb = h->tab;
@@ -1063,8 +1070,8 @@ static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C) {
 
 // Kernel variants of one sampler.  All of them produce the same trajectory bit for
 // bit, so the choice is a pure performance knob: 0 spin, 1..4 batch (B,C) =
-// (16,2) (16,1) (8,1) (4,1), 5 one move at a time (mc_kernel, always applicable).
-static const int kNumVariants = 6;
+// (16,2) (16,1) (8,1) (4,1), 5 one move at a time (mc_kernel, always applicable),
+// 6..7 batch (8,1) / (16,1) with two moves per evaluation warp.
 
 template <int MODE>
 static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
@@ -1074,14 +1081,16 @@ static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
     case 2: return launch_batch<MODE>(h, a, 16, 1);
     case 3: return launch_batch<MODE>(h, a, 8, 1);
     case 4: return launch_batch<MODE>(h, a, 4, 1);
+    case 6: return launch_batch<MODE>(h, a, 8, 1, 2);
+    case 7: return launch_batch<MODE>(h, a, 16, 1, 2);
     default: return launch_mc<MODE>(h, a, 0, h->R);
   }
 }
 
 static bool variant_allowed(const cemc_handle *h, int v) {
   if (v == 0 && h->batch > 0) return false;       // an explicit batch size asks for the batch kernel
-  if (v >= 1 && v <= 4) {
-    static const int Bs[5] = {0, 16, 16, 8, 4}, Cs[5] = {0, 2, 1, 1, 1};
+  if ((v >= 1 && v <= 4) || v >= 6) {
+    static const int Bs[8] = {0, 16, 16, 8, 4, 0, 8, 16}, Cs[8] = {0, 2, 1, 1, 1, 0, 1, 1};
     if (h->batch > 0 && h->batch != Bs[v]) return false;
     if (h->cluster > 0 && h->cluster != Cs[v]) return false;
   }

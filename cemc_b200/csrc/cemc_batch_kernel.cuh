@@ -69,6 +69,7 @@ struct BatchSmem {
   int32_t *ctl;             // control words
   int32_t *list;
   int8_t *occ;
+  uint64_t *mbar;           // mbarrier of the TMA staging copies
 };
 
 // B = moves evaluated by this CTA, BT = moves per batch over the whole cluster
@@ -84,13 +85,20 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
     if (s) s->field = reinterpret_cast<type *>(base + o);               \
     o += sizeof(type) * at_least_1((int)(count));                       \
   } while (0)
+  // destinations of TMA bulk copies: 16-byte aligned, size rounded up to 16 bytes
+#define CEMC_TAKE16(field, type, count)                                 \
+  do {                                                                  \
+    o = align_up(o, 16);                                                \
+    if (s) s->field = reinterpret_cast<type *>(base + o);               \
+    o += align_up(sizeof(type) * at_least_1((int)(count)), 16);         \
+  } while (0)
   const int nj = canonical ? 2 : 1;
   CEMC_TAKE(V, double, tb ? 0 : B * nj * t.VS);
   CEMC_TAKE(PO, double, tb ? 0 : B * nj * t.max_slots);
   CEMC_TAKE(PN, double, tb ? 0 : B * nj * t.max_slots);
   CEMC_TAKE(diff, double, B * nj * t.max_tasks);
-  CEMC_TAKE(tab, double, tb ? tb->n_tab : 0);
-  CEMC_TAKE(ttask, int4, tb ? t.n_tasks_total : 0);
+  CEMC_TAKE16(tab, double, tb ? tb->n_tab : 0);
+  CEMC_TAKE16(ttask, int4, tb ? t.n_tasks_total : 0);
   o = align_up(o, 16);                     // code words are read four at a time
   CEMC_TAKE(codes, uint32_t, tb ? B * nj * tb->n_sub : 0);
   CEMC_TAKE(sq, double, 2 * BT * 2 * 32);      // double buffered: the bookkeeper reads batch k during batch k+1
@@ -100,19 +108,19 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(Ch, double, BT * 32);
   CEMC_TAKE(obE, double, BT);
   CEMC_TAKE(bf, double, t.D * t.S);
-  CEMC_TAKE(items, uint4, tb ? 0 : t.n_items_total);
-  CEMC_TAKE(task_sum, int2, tb ? 0 : t.n_tasks_total);
+  CEMC_TAKE16(items, uint4, tb ? 0 : t.n_items_total);
+  CEMC_TAKE16(task_sum, int2, tb ? 0 : t.n_tasks_total);
   CEMC_TAKE(ring, uint4, 128 * 2);
   CEMC_TAKE(prop, int32_t, 2 * BT * 8);
   CEMC_TAKE(cmask, int32_t, BT);
   o = align_up(o, 8);
   CEMC_TAKE(ctl, int32_t, 8);
+  CEMC_TAKE(mbar, uint64_t, 1);
   if (state_in_smem) {
-    if (canonical) CEMC_TAKE(list, int32_t, t.N);
-    o = align_up(o, 16);
-    if (s) s->occ = reinterpret_cast<int8_t *>(base + o);
-    o += align_up((size_t)t.N, 16);
+    if (canonical) CEMC_TAKE16(list, int32_t, t.N);
+    CEMC_TAKE16(occ, int8_t, t.N);
   }
+#undef CEMC_TAKE16
 #undef CEMC_TAKE
   return align_up(o, 16);
 }
@@ -134,7 +142,10 @@ __device__ __forceinline__ int offs_of(const int (&offs)[9], int sp) {
 // per-move observer arithmetic off the deciding warp.
 // kSpin: binary +-1 basis -- the evaluation of a move is the XOR / ballot / popcount
 // scheme of cemc_spin_kernel.cuh instead of fp64 products (same quotients, bit for bit).
-template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV>
+// M: moves per evaluation warp and batch (one after the other): M = 2 doubles the batch at the
+// same number of warps / registers, so the per-batch costs (two barriers, the decision pass)
+// are shared by twice as many moves; the price is more speculation lost on hot chains.
+template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV, int M = 1>
 __global__ void __launch_bounds__((B + 1) * 32, (EV != EV_PRODUCT && B <= 8) ? 2 : 1)
 batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTables sp, TabTables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -142,7 +153,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   constexpr bool kSpin = (EV == EV_SPIN), kTab = (EV == EV_TAB);
   constexpr bool kCanon = (MODE == MODE_CANONICAL);
   constexpr int NJ = kCanon ? 2 : 1;
-  constexpr int BT = B * C;                      // moves per batch over the whole cluster
+  constexpr int BW = B * C;                      // evaluation warps of the chain
+  constexpr int BT = BW * M;                     // moves per batch over the whole cluster
   static_assert(BT <= 32, "one decision lane per move");
   const int crank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int r = blockIdx.x / C;
@@ -184,19 +196,34 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     occ_of[0] = s.occ; list_of[0] = s.list; prop_of[0] = s.prop; ctl_of[0] = s.ctl;
   }
 
-  // ---- stage ----------------------------------------------------------------
-  for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
-  if (!kTab) {
-    for (int i = tid; i < t.n_items_total; i += nthr) s.items[i] = t.items4[i];
-    for (int i = tid; i < t.n_tasks_total; i += nthr) s.task_sum[i] = t.task_sum[i];
-    for (int i = tid; i < B * NJ * VS; i += nthr) s.V[i] = 1.0;      // V[K] is the constant 1.0
-  } else {
-    for (int i = tid; i < tb.n_tab; i += nthr) s.tab[i] = tb.tab[i];
-    for (int i = tid; i < t.n_tasks_total; i += nthr) s.ttask[i] = tb.task[i];
+  // ---- stage: the TMA engine copies the read-only tables -- and the replica's occupations /
+  // site lists when their global addresses are 16-byte aligned -- into shared memory
+  // (cp.async.bulk -> mbarrier transaction bytes); the threads only fill what has no
+  // global image (V) or is misaligned
+  const bool occ_tma = kStateSmem && tma_aligned(g_occ, (size_t)N);
+  const bool list_tma = kStateSmem && kCanon && tma_aligned(g_list, (size_t)N * 4);
+  if (tid == 0) mbar_init(s.mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t b_tab = kTab ? (uint32_t)align_up((size_t)tb.n_tab * 8, 16) : 0u;
+    const uint32_t b_ttask = kTab ? (uint32_t)t.n_tasks_total * 16u : 0u;
+    const uint32_t b_items = kTab ? 0u : (uint32_t)t.n_items_total * 16u;
+    const uint32_t b_tsum = kTab ? 0u : (uint32_t)align_up((size_t)t.n_tasks_total * 8, 16);
+    const uint32_t b_occ = occ_tma ? (uint32_t)N : 0u, b_list = list_tma ? (uint32_t)N * 4u : 0u;
+    mbar_expect_tx(s.mbar, b_tab + b_ttask + b_items + b_tsum + b_occ + b_list);
+    if (b_tab) tma_bulk_g2s(s.tab, tb.tab, b_tab, s.mbar);
+    if (b_ttask) tma_bulk_g2s(s.ttask, tb.task, b_ttask, s.mbar);
+    if (b_items) tma_bulk_g2s(s.items, t.items4, b_items, s.mbar);
+    if (b_tsum) tma_bulk_g2s(s.task_sum, t.task_sum, b_tsum, s.mbar);
+    if (b_occ) tma_bulk_g2s(s.occ, g_occ, b_occ, s.mbar);
+    if (b_list) tma_bulk_g2s(s.list, g_list, b_list, s.mbar);
   }
+  for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
+  if (!kTab)
+    for (int i = tid; i < B * NJ * VS; i += nthr) s.V[i] = 1.0;      // V[K] is the constant 1.0
   if (kStateSmem) {
-    for (int i = tid; i < N; i += nthr) s.occ[i] = g_occ[i];
-    if (kCanon) for (int i = tid; i < N; i += nthr) s.list[i] = g_list[i];
+    if (!occ_tma) for (int i = tid; i < N; i += nthr) s.occ[i] = g_occ[i];
+    if (kCanon && !list_tma) for (int i = tid; i < N; i += nthr) s.list[i] = g_list[i];
   }
   // canonical: species present and their list ranges (constant during a launch)
   int n_present = 0, present[8], offs[9];
@@ -214,10 +241,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int q = 0; q < 8; q++) if (q == n_present) present[q] = sp;
         n_present++;
       }
-    if (n_present < 2) {                       // TooFewElementsError, montecarlo.py:310
-      if (tid == 0) st.status[r] = 2;
-      return;
-    }
+  }
+  mbar_wait(s.mbar, 0);                        // every staged byte has landed
+  if (kCanon && n_present < 2) {               // TooFewElementsError, montecarlo.py:310
+    if (tid == 0) st.status[r] = 2;
+    return;
   }
   csync();
 
@@ -394,15 +422,16 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     if (my_acc) {
       const double *pm = s.Pm + lane * 33;
       double e = 0.0;
-      int i = 0;
-      for (; i + 7 < n_eci; i += 8) {
-        double v[8];
+      // groups of four, loads up front: the entries of lanes >= n_eci are +0.0 products
+      // (eci = cf = 0), and adding +0.0 leaves every partial sum bit for bit (the sum
+      // starts at +0.0, so it is never -0.0)
+      for (int i = 0; i < n_eci4; i += 4) {
+        double v[4];
 #pragma unroll
-        for (int x = 0; x < 8; x++) v[x] = pm[i + x];
+        for (int x = 0; x < 4; x++) v[x] = pm[i + x];
 #pragma unroll
-        for (int x = 0; x < 8; x++) e = __dadd_rn(e, v[x]);
+        for (int x = 0; x < 4; x++) e = __dadd_rn(e, v[x]);
       }
-      for (; i < n_eci; i++) e = __dadd_rn(e, pm[i]);
       E_l = __dmul_rn(e, dN);
     }
     // energy after move b = energy of the last accepted move <= b (else the old one)
@@ -502,9 +531,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     const long long tob1 = clock64();
 #endif
     // ---- E1: warp b evaluates move sdone + b against the current state --------------
-    int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check); host: NJ*KP <= 64
-    if (warp < nb) {
-      const int b = warp;
+#pragma unroll 1
+    for (int mi = 0; mi < M; mi++) {
+      const int b = warp + mi * BW;             // warp w evaluates moves w, w + BW, ...
+      if (b >= nb) break;
+      int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check); host: NJ*KP <= 64
       const uint4 rec0 = s.ring[(int)((sdone + b) & 127) * 2];
       int site0, site1 = -1, new0, new1 = 0, old0, old1 = 0, slot0 = -1, slot1 = -1;
       if (!kCanon) {
@@ -824,31 +855,22 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           if (!kCanon) sk0 = t.active ? t.active[rk.x] : (int)rk.x;
           else { sk0 = s.list[rk.x]; sk1 = s.list[rk.y]; }
         }
-        // gsx[j]: lanes 0..K hold the K neighbours and the changed site itself.  The other
-        // 32 - KP lanes take the sk values of a few moves per round and one MATCH finds the
-        // lanes holding equal values: a hit is an sk lane matching a gathered-site lane.
+        // gsx[j]: lanes 0..K hold the K neighbours and the changed site itself.  With few
+        // earlier moves, the site(s) of each one are broadcast and compared by the lanes holding
+        // gathered sites (one vote per move); with many, every gathered site is broadcast and
+        // compared by the lanes holding the moves.  Both are short independent shuffle / compare
+        // / vote sequences (MATCH.ANY over 32 distinct values costs ~400 cycles on sm_100).
         uint32_t m = 0;
-        const int slots = 32 - KP;
-        if (slots >= 8) {
-          const int h = kCanon ? slots / 2 : slots;          // moves per round
-          const uint32_t gmask = (1u << KP) - 1u;
-          for (int mv0 = 0; mv0 < b; mv0 += h) {
-            const int q = lane - KP;                           // slot of this lane
-            const int mv = mv0 + (kCanon && q >= h ? q - h : q);
-            const bool is_sk = q >= 0 && q < (kCanon ? 2 * h : h) && mv < b;
-            const int a0 = __shfl_sync(0xffffffffu, sk0, is_sk ? mv : 0);
-            const int a1 = kCanon ? __shfl_sync(0xffffffffu, sk1, is_sk ? mv : 0) : 0;
-            const int val = (kCanon && q >= h) ? a1 : a0;
-            uint32_t hb = 0;
-#pragma unroll
-            for (int j = 0; j < NJ; j++) {
-              const int x = lane < KP ? gsx[j] : (is_sk ? val : -3 - lane);
-              const uint32_t mm = __match_any_sync(0xffffffffu, x);
-              hb |= __ballot_sync(0xffffffffu, is_sk && (mm & gmask) != 0u);
+        if (b <= KP) {
+          for (int k = 0; k < b; k++) {
+            const int a0 = __shfl_sync(0xffffffffu, sk0, k);
+            bool hit = (gsx[0] == a0);
+            if (NJ == 2) hit |= (gsx[1] == a0);
+            if (kCanon) {
+              const int a1 = __shfl_sync(0xffffffffu, sk1, k);
+              hit |= (gsx[0] == a1) | (gsx[1] == a1);
             }
-            hb >>= KP;
-            if (kCanon) hb = (hb | (hb >> h)) & ((1u << h) - 1u);
-            m |= hb << mv0;
+            if (__any_sync(0xffffffffu, hit)) m |= 1u << k;
           }
         } else {
           bool hit = false;
@@ -863,6 +885,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         if (lane == 0) s0.cmask[b] = (int32_t)m;
       }
       CEMC_TICK(13);
+      if (M > 1) __syncwarp();                  // the warp's scratch is reused by its next move
     }
     csync();
 #ifdef CEMC_PHASE_TIMING

@@ -11,7 +11,7 @@ namespace cemc {
 struct BatchLaunch {
   int mode;               // MODE_SGC | MODE_CANONICAL
   int tree;               // TREE summation order
-  int B, C;               // moves per CTA, CTAs per chain
+  int B, C, M;            // warps per CTA, CTAs per chain, moves per evaluation warp
   int R;                  // replicas
   int max_smem_optin;
   cudaStream_t stream;
@@ -28,9 +28,9 @@ int batch_launch_product(const BatchLaunch &L);
 int batch_launch_spin(const BatchLaunch &L);
 int batch_launch_tab(const BatchLaunch &L);
 
-template <int MODE, bool kTree, int B, bool kSmem, int C, int EV>
+template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M>
 static int batch_launch_kc(const BatchLaunch &L, size_t sm) {
-  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV>;
+  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV, M>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return 1000 + (int)e;
   cudaLaunchConfig_t cfg{};
@@ -48,21 +48,30 @@ static int batch_launch_kc(const BatchLaunch &L, size_t sm) {
   return e == cudaSuccess ? 0 : 1000 + (int)e;
 }
 
-template <int MODE, bool kTree, int B, int C, int EV>
+template <int MODE, bool kTree, int B, int C, int EV, int M = 1>
 static int batch_launch_b(const BatchLaunch &L) {
   const TabTables *tb = EV == EV_TAB ? &L.tb : nullptr;
-  size_t sm = batch_smem_layout<B, B * C>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, tb);
+  size_t sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, tb);
   const bool in_smem = sm <= (size_t)L.max_smem_optin;
-  if (!in_smem) sm = batch_smem_layout<B, B * C>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, false, tb);
+  if (!in_smem) sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, false, tb);
   if (sm > (size_t)L.max_smem_optin) return -1;
-  return in_smem ? batch_launch_kc<MODE, kTree, B, true, C, EV>(L, sm)
-                 : batch_launch_kc<MODE, kTree, B, false, C, EV>(L, sm);
+  if constexpr (M > 1) {            // two moves per warp: shared-memory state only
+    return in_smem ? batch_launch_kc<MODE, kTree, B, true, C, EV, M>(L, sm) : -1;
+  } else {
+    return in_smem ? batch_launch_kc<MODE, kTree, B, true, C, EV, M>(L, sm)
+                   : batch_launch_kc<MODE, kTree, B, false, C, EV, M>(L, sm);
+  }
 }
 
 template <int MODE, bool kTree, int EV>
 static int batch_launch_bc(const BatchLaunch &L) {
   // L.B counts the warps of a CTA: B - 1 evaluation warps (moves per batch) + the observer
   // warp; power-of-two CTAs get the full register budget (512 threads x 128 registers)
+  if (L.M == 2) {
+    if (L.B == 16 && L.C == 1) return batch_launch_b<MODE, kTree, 15, 1, EV, 2>(L);
+    if (L.B == 8 && L.C == 1) return batch_launch_b<MODE, kTree, 7, 1, EV, 2>(L);
+    return -1;
+  }
   if (L.B == 16 && L.C == 2) return batch_launch_b<MODE, kTree, 15, 2, EV>(L);
   if (L.B == 16 && L.C == 1) return batch_launch_b<MODE, kTree, 15, 1, EV>(L);
   if (L.B == 8 && L.C == 1) return batch_launch_b<MODE, kTree, 7, 1, EV>(L);

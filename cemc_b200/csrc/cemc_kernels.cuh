@@ -171,6 +171,34 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP): the copy engine stages the read-only
+// tables (and, when 16-byte aligned, the occupations / site lists of the replica) from HBM
+// into shared memory; completion is signalled on an mbarrier by transaction bytes, so no
+// thread spends issue slots on the staging loop.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bytes: multiple of 16; dst / src 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ bool tma_aligned(const void *p, size_t bytes) {
+  return ((reinterpret_cast<uintptr_t>(p) | bytes) & 15u) == 0 && bytes > 0;
+}
+
 struct Smem {            // carved from dynamic shared memory
   double *cf, *cfn, *eci, *prod, *V, *PO, *PN, *diff, *bf, *acc;
   double2 *fin_d;

@@ -648,3 +648,35 @@ def test_table_evaluation_quaternary(cuda_device, batch, cluster, order):
         else:
             assert np.array_equal(gpu.get_occupancy(), np.stack([c.occ for c in chains]))
             np.testing.assert_allclose(gpu.get_cf(), np.stack([c.cf for c in chains]), rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("variant", [6, 7])
+@pytest.mark.parametrize("system", ["binary", "ternary_tab", "ternary_product"])
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+def test_two_moves_per_warp_variants(cuda_device, variant, system, mode):
+    """Kernel variants 6 / 7: every evaluation warp of the batch kernel takes two moves of
+    a batch (14 / 30 moves per batch).  Same trajectory, trace, observer sums as the oracle
+    for the three evaluation schemes, also on the 27-site cell (constant collisions)."""
+    base = BINARY if system == "binary" else TERNARY
+    for case, R in ((base, 3), (dict(base, L=3), 2)):
+        st, eci, symbols, ft = build(**case)
+        kTs = np.linspace(0.02, 0.2, R)
+        gpu, chains = make_pair(ft, [symbols] * R, kTs, seed=131)
+        if system != "binary":
+            gpu.set_table_eval(system == "ternary_tab")
+        gpu.set_variant(variant, variant)
+        n = 1500
+        gpu.set_trace(n)
+        gpu.reset_accumulators()
+        (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+        gpu.synchronize()
+        assert gpu.get_variant() == (variant, variant)
+        tr = gpu.get_trace(n)
+        for r, c in enumerate(chains):
+            o = c.run_sgc(n, trace=True) if mode == "sgc" else c.run_canonical(n, trace=True)
+            assert np.array_equal(tr[0][r], o[0]) and np.array_equal(tr[3][r], o[3])
+            assert np.array_equal(tr[4][r], o[4])
+        assert_state_equal(gpu, chains)
+        accs = gpu.get_accumulators()
+        for r, c in enumerate(chains):
+            assert np.array_equal(accs[r], c.acc)
