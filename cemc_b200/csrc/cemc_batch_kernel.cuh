@@ -531,6 +531,141 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     const long long tob1 = clock64();
 #endif
     // ---- E1: warp b evaluates move sdone + b against the current state --------------
+    // ---- which earlier moves of the batch would invalidate an evaluation?  Lane k holds the
+    // site(s) move k changes if accepted (state independent for SGC; for swaps the current
+    // list entries: had an accepted move changed them, move k would be invalid itself and
+    // the batch would end before it)
+    auto changed_sites = [&](int bmax, int &sk0, int &sk1) {
+      sk0 = -2; sk1 = -2;
+      if (lane < bmax) {
+        const uint4 rk = s.ring[(int)((sdone + lane) & 127) * 2];
+        if (!kCanon) sk0 = t.active ? t.active[rk.x] : (int)rk.x;
+        else { sk0 = s.list[rk.x]; sk1 = s.list[rk.y]; }
+      }
+    };
+    // gsx[j]: lanes 0..K hold the K neighbours and the changed site itself.  With few
+    // earlier moves, the site(s) of each one are broadcast and compared by the lanes holding
+    // gathered sites (one vote per move); with many, every gathered site is broadcast and
+    // compared by the lanes holding the moves.  Both are short independent shuffle / compare
+    // / vote sequences (MATCH.ANY over 32 distinct values costs ~400 cycles on sm_100).
+    auto conflict_mask = [&](int b, const int (&gsx)[2], int sk0, int sk1) -> uint32_t {
+      uint32_t m = 0;
+      if (b <= KP) {
+        for (int k = 0; k < b; k++) {
+          const int a0 = __shfl_sync(0xffffffffu, sk0, k);
+          bool hit = (gsx[0] == a0);
+          if (NJ == 2) hit |= (gsx[1] == a0);
+          if (kCanon) {
+            const int a1 = __shfl_sync(0xffffffffu, sk1, k);
+            hit |= (gsx[0] == a1) | (gsx[1] == a1);
+          }
+          if (__any_sync(0xffffffffu, hit)) m |= 1u << k;
+        }
+      } else {
+        bool hit = false;
+#pragma unroll
+        for (int j = 0; j < NJ; j++)
+          for (int q = 0; q < KP; q++) {
+            const int g = __shfl_sync(0xffffffffu, gsx[j], q);
+            hit |= (g == sk0) | (kCanon & (g == sk1));
+          }
+        m = __ballot_sync(0xffffffffu, hit) & (b >= 32 ? 0xffffffffu : ((1u << b) - 1u));
+      }
+      return m;
+    };
+
+    if constexpr (kSpin) {
+      // ---- spin evaluation (cemc_spin_kernel.cuh), the M moves of this warp side by side
+      // (independent instruction streams: the warp has few siblings on its scheduler, so
+      // latency must be covered inside the warp).  Lane c gathers column c of the changed
+      // site's translation-matrix row and its occupation; ONE ballot turns the K occupations
+      // into a bit mask, every lane forms the parity of its sub-cluster(s) from that mask,
+      // one ballot per 32 sub-clusters packs the parities, ECI lanes take popc(ballot & mask),
+      // the exact integer numerator n (sigma_new - sigma_old)(M_sub - 2 popc), one exact
+      // division.  Moves past the end of the run are evaluated too (their records exist in
+      // the ring; nobody reads the results): no divergence between the M streams.
+      if (!is_obs) {
+        int site[M][2], oldv[M][2], newv[M][2], gs[M][2];
+        double qv[M][2];
+#pragma unroll
+        for (int mi = 0; mi < M; mi++) {
+          const int b = warp + mi * BW;           // warp w evaluates moves w, w + BW, ...
+          const uint4 rec0 = s.ring[(int)((sdone + b) & 127) * 2];
+          int slot0 = -1, slot1 = -1;
+          site[mi][1] = -1; oldv[mi][1] = 0; newv[mi][1] = 0;
+          if (!kCanon) {                          // sgc_montecarlo.py:69-75 (all species allowed)
+            site[mi][0] = t.active ? t.active[rec0.x] : (int)rec0.x;
+            oldv[mi][0] = s.occ[site[mi][0]];
+            int rr = (int)__umulhi(rec0.y, (uint32_t)(S - 1)); rr += (rr >= oldv[mi][0]);
+            newv[mi][0] = rr;
+          } else {
+            slot0 = (int)rec0.x; slot1 = (int)rec0.y; newv[mi][0] = (int)rec0.z; newv[mi][1] = (int)rec0.w;
+            site[mi][0] = s.list[slot0]; site[mi][1] = s.list[slot1];
+            oldv[mi][0] = newv[mi][1]; oldv[mi][1] = newv[mi][0];
+          }
+          if (lane == 0) {                         // the deciding warp commits from this record
+            int32_t *pp = s0.prop + par * (BT * 8) + b * 8;
+            *reinterpret_cast<int4 *>(pp) = make_int4(site[mi][0], site[mi][1], newv[mi][0], newv[mi][1]);
+            *reinterpret_cast<int4 *>(pp + 4) = make_int4(oldv[mi][0], oldv[mi][1], slot0, slot1);
+          }
+        }
+#pragma unroll
+        for (int mi = 0; mi < M; mi++) {
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            gs[mi][j] = -1; qv[mi][j] = 0.0;
+            if (j < NJ) {
+              uint32_t v = 0;
+              if (lane < K) {
+                const int nbs = __ldg(&t.trans[(size_t)site[mi][j] * K + lane]);      // :264
+                gs[mi][j] = nbs;
+                v = (uint32_t)s.occ[nbs];
+                if (j == 1 && nbs == site[mi][0]) v = (uint32_t)newv[mi][0];   // change 1 sees change 0 applied (:845-852)
+              } else if (lane == K) gs[mi][j] = site[mi][j];
+              const uint32_t ob = __ballot_sync(0xffffffffu, (v & 1u) != 0u);
+              int cnt = 0;
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                if (q < s_rounds) {
+                  const uint32_t bit = ((ob >> sca[q]) ^ ((ob >> scb[q]) & smb[q]) ^ ((ob >> scc[q]) & smc[q])) & smv[q];
+                  cnt += __popc(__ballot_sync(0xffffffffu, bit != 0u) & smask[q]);
+                }
+              }
+              const int dsig = 2 * sp.b0 * (oldv[mi][j] - newv[mi][j]);      // sigma_new - sigma_old
+              const int num = s_coef * dsig * (s_msub - 2 * cnt);
+              qv[mi][j] = exact_div((double)num, f_den, f_rden);             // :402
+            }
+          }
+        }
+#pragma unroll
+        for (int mi = 0; mi < M; mi++) {
+          const int b = warp + mi * BW;
+          double *sqb = s0.sq + par * (BT * 64) + b * 64;   // this move's per-ECI quotients [2][32]
+          sqb[lane] = qv[mi][0];
+          sqb[32 + lane] = qv[mi][1];
+        }
+        double de[M];
+#pragma unroll
+        for (int mi = 0; mi < M; mi++) de[mi] = f_kind > 0 ? eci_reg * (qv[mi][0] + qv[mi][1]) : 0.0;   // screen only
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int mi = 0; mi < M; mi++) de[mi] += __shfl_xor_sync(0xffffffffu, de[mi], o);
+#pragma unroll
+        for (int mi = 0; mi < M; mi++)
+          if (lane == 0) s0.dEa[warp + mi * BW] = de[mi] * dN;
+        CEMC_TICK(12);
+        int sk0, sk1;
+        changed_sites(warp + (M - 1) * BW, sk0, sk1);
+#pragma unroll
+        for (int mi = 0; mi < M; mi++) {
+          const int b = warp + mi * BW;
+          const uint32_t m = conflict_mask(b, gs[mi], sk0, sk1);
+          if (lane == 0) s0.cmask[b] = (int32_t)m;
+        }
+        CEMC_TICK(13);
+      }
+    } else {
 #pragma unroll 1
     for (int mi = 0; mi < M; mi++) {
       const int b = warp + mi * BW;             // warp w evaluates moves w, w + BW, ...
@@ -563,42 +698,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         *reinterpret_cast<int4 *>(pp) = make_int4(site0, site1, new0, new1);
         *reinterpret_cast<int4 *>(pp + 4) = make_int4(old0, old1, slot0, slot1);
       }
-      if (kSpin) {
-        // ---- spin evaluation (cemc_spin_kernel.cuh): XOR of neighbour occupation bits,
-        // one ballot per 32 sub-clusters, exact integer numerators, exact division
-        const int sites[2] = {site0, site1};
-        const int olds[2] = {old0, old1}, news[2] = {new0, new1};
-#pragma unroll
-        for (int j = 0; j < NJ; j++)                      // gathered sites (conflict check)
-          if (lane < KP) gsx[j] = lane < K ? __ldg(&t.trans[(size_t)sites[j] * K + lane]) : sites[j];
-#pragma unroll
-        for (int j = 0; j < NJ; j++) {
-          const int32_t *row = t.trans + (size_t)sites[j] * K;
-          int cnt = 0;
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            if (q < s_rounds) {
-              const int na = __ldg(row + sca[q]), nb2 = __ldg(row + scb[q]), nc = __ldg(row + scc[q]);
-              uint32_t va = (uint32_t)s.occ[na], vb = (uint32_t)s.occ[nb2], vc = (uint32_t)s.occ[nc];
-              if (j == 1) {                    // change 1 sees change 0 applied (:845-852)
-                if (na == site0) va = (uint32_t)new0;
-                if (nb2 == site0) vb = (uint32_t)new0;
-                if (nc == site0) vc = (uint32_t)new0;
-              }
-              const uint32_t bit = (va ^ (vb & smb[q]) ^ (vc & smc[q])) & smv[q];
-              cnt += __popc(__ballot_sync(0xffffffffu, bit) & smask[q]);
-            }
-          }
-          const int dsig = 2 * sp.b0 * (olds[j] - news[j]);          // sigma_new - sigma_old
-          const int num = s_coef * dsig * (s_msub - 2 * cnt);
-          sqb[j * 32 + lane] = exact_div((double)num, f_den, f_rden);   // :402
-        }
-        if (!kCanon) sqb[32 + lane] = 0.0;
-        double de = f_kind > 0 ? eci_reg * (sqb[lane] + sqb[32 + lane]) : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
-        if (lane == 0) s0.dEa[b] = de * dN;
-      } else if (kTab) {
+      if (kTab) {
         CEMC_TICK(5);
         // ---- table evaluation: neighbour occupations stay in registers (lane c = column c),
         // sub-cluster codes by shuffles, sums over sub-clusters from the product tables
@@ -843,49 +943,15 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       }
       }
       CEMC_TICK(12);
-      // ---- which earlier moves of the batch would invalidate this evaluation?  Lane k
-      // holds the site(s) move k changes if accepted (state independent for SGC; for swaps
-      // the current list entries: had an accepted move changed them, move k would be
-      // invalid itself and the batch would end before it); every gathered site of this
-      // move is broadcast once and compared by all lanes.
       {
-        int sk0 = -2, sk1 = -2;
-        if (lane < b) {
-          const uint4 rk = s.ring[(int)((sdone + lane) & 127) * 2];
-          if (!kCanon) sk0 = t.active ? t.active[rk.x] : (int)rk.x;
-          else { sk0 = s.list[rk.x]; sk1 = s.list[rk.y]; }
-        }
-        // gsx[j]: lanes 0..K hold the K neighbours and the changed site itself.  With few
-        // earlier moves, the site(s) of each one are broadcast and compared by the lanes holding
-        // gathered sites (one vote per move); with many, every gathered site is broadcast and
-        // compared by the lanes holding the moves.  Both are short independent shuffle / compare
-        // / vote sequences (MATCH.ANY over 32 distinct values costs ~400 cycles on sm_100).
-        uint32_t m = 0;
-        if (b <= KP) {
-          for (int k = 0; k < b; k++) {
-            const int a0 = __shfl_sync(0xffffffffu, sk0, k);
-            bool hit = (gsx[0] == a0);
-            if (NJ == 2) hit |= (gsx[1] == a0);
-            if (kCanon) {
-              const int a1 = __shfl_sync(0xffffffffu, sk1, k);
-              hit |= (gsx[0] == a1) | (gsx[1] == a1);
-            }
-            if (__any_sync(0xffffffffu, hit)) m |= 1u << k;
-          }
-        } else {
-          bool hit = false;
-#pragma unroll
-          for (int j = 0; j < NJ; j++)
-            for (int q = 0; q < KP; q++) {
-              const int g = __shfl_sync(0xffffffffu, gsx[j], q);
-              hit |= (g == sk0) | (kCanon & (g == sk1));
-            }
-          m = __ballot_sync(0xffffffffu, hit);
-        }
+        int sk0, sk1;
+        changed_sites(b, sk0, sk1);
+        const uint32_t m = conflict_mask(b, gsx, sk0, sk1);
         if (lane == 0) s0.cmask[b] = (int32_t)m;
       }
       CEMC_TICK(13);
       if (M > 1) __syncwarp();                  // the warp's scratch is reused by its next move
+    }
     }
     csync();
 #ifdef CEMC_PHASE_TIMING
