@@ -266,9 +266,7 @@ def gpu_arm(args):
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj.get("mc_kernel_sgc_dram_bytes_per_move", None)
-            if traffic is not None:
-                traffic = traffic * R * MOVES_PER_STEP
+            traffic = tj.get("batch_kernel_sgc_dram_bytes_per_launch", None)
         except (OSError, ValueError):
             pass
         h2d = w.occ.nbytes + w.eci_matrix.nbytes + w.kT.nbytes
