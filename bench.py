@@ -315,8 +315,8 @@ def extra_workloads(device):
     the north-star target line is the 64-replica Al-Mg-Si SGC sweep)."""
     from cemc_b200 import workloads as wl
     out = {}
-    for name, n in (("C3S", 40000), ("C3", 40000), ("C1", 40000)):
-        w = wl.WORKLOADS[name](R=64) if name != "C1" else wl.WORKLOADS[name](R=64)
+    for name, n in (("C3S", 40000), ("C3", 40000), ("C1", 40000), ("C5", 40000)):
+        w = wl.WORKLOADS[name](R=1) if name == "C5" else wl.WORKLOADS[name](R=64)
         gpu = wl.make_updater(w, device=device)
         run = gpu.run_sgc if w.mode == "sgc" else gpu.run_canonical
         run(n)
@@ -331,6 +331,44 @@ def extra_workloads(device):
                      "ns_per_move_per_chain": best * 1e6 / n,
                      "algorithmic_bytes_per_move": w.tables.algorithmic_bytes_per_move(w.sites_changed)}
         gpu.close()
+    out["C4"] = pt_workload(device)
+    return out
+
+
+def pt_workload(device, rounds=40):
+    """BASELINE config 4 on one GPU's shard: 64 temperatures of the ladder, fcc 12^3 ternary,
+    one exchange sweep (pt_exchange_kernel, on the device) every 1728 canonical moves."""
+    import torch
+    from cemc_b200 import workloads as wl
+    R = 64
+    w = wl.c4_parallel_tempering(R=R, n_total=R)
+    gpu = wl.make_updater(w, device=device)
+    dev = torch.device("cuda", device)
+    slots = torch.arange(R, dtype=torch.int32, device=dev)
+    kts = torch.from_numpy(np.ascontiguousarray(w.kT_of_slot)).to(dev)
+    n_acc = torch.zeros(1, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(dev)
+    sweep = w.tables.N
+
+    def cycle(k):
+        gpu.run_canonical(sweep)
+        gpu.pt_exchange(R, gpu.energy_dev_ptr(), slots.data_ptr(), kts.data_ptr(), k & 1, k,
+                        n_acc.data_ptr())
+
+    for k in range(12):         # includes the autotuner's segments
+        cycle(k)
+    gpu.synchronize()
+    gpu.timer_start()
+    for k in range(rounds):
+        cycle(100 + k)
+    ms = gpu.timer_stop()
+    gpu.synchronize()
+    out = {"workload": w.description.replace("512", str(R)) + ", %d replicas on this GPU, exchange every %d moves" % (R, sweep),
+           "moves_per_s": R * sweep * rounds / (ms * 1e-3),
+           "ns_per_move_per_chain": ms * 1e6 / (sweep * rounds),
+           "exchange_rounds_per_s": rounds / (ms * 1e-3),
+           "algorithmic_bytes_per_move": w.tables.algorithmic_bytes_per_move(2)}
+    gpu.close()
     return out
 
 

@@ -71,7 +71,8 @@ struct cemc_handle {
   uint8_t *tr_acc = nullptr; double *tr_e = nullptr;
   double *cf_partial = nullptr;         // [R][n_jobs]
   int32_t *pt_scratch = nullptr; int pt_scratch_n = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // cemc_timer_start / _stop
+  cudaEvent_t tv0 = nullptr, tv1 = nullptr;     // the autotuner's own pair
   // host copies needed by the API
   std::vector<int32_t> symm_of_site;
   std::vector<int8_t> allowed;
@@ -83,6 +84,9 @@ struct cemc_handle {
   double screen_slack = 1.0;          // testing: widen the Metropolis screening band
   bool autotune = true;               // pick the fastest kernel variant on long runs
   int tuned_sgc = -1, tuned_can = -1;  // variant chosen by the autotuner
+  // tuning across short launches: next variant to time, ms per move of the timed ones
+  int xt_next[2] = {0, 0};
+  float xt_ms[2][8];
   int cluster = 0;                    // CTAs per chain in the batch kernel (0 = auto, 1, 2)
   int n_sms = 148;
   int batch = 0;                      // moves evaluated speculatively per batch (0 = auto)
@@ -93,6 +97,11 @@ struct cemc_handle {
   TabTables tab{};
   unsigned long long *d_phase = nullptr;   // CEMC_PHASE_TIMING builds
 };
+
+static void reset_tuning(cemc_handle *h) {
+  h->tuned_sgc = h->tuned_can = -1;
+  h->xt_next[0] = h->xt_next[1] = 0;
+}
 
 // ---------------------------------------------------------------------------
 // small kernels
@@ -358,6 +367,8 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   CU(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
+  CU(cudaEventCreate(&h->tv0));
+  CU(cudaEventCreate(&h->tv1));
 
   // ---- build the cluster program ------------------------------------------
   DeviceTables &t = h->t;
@@ -658,6 +669,8 @@ int cemc_destroy(cemc_handle *h) {
   for (void *p : extra) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->tv0) cudaEventDestroy(h->tv0);
+  if (h->tv1) cudaEventDestroy(h->tv1);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -810,7 +823,7 @@ int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8) {
 int cemc_set_autotune(cemc_handle *h, int on) {
   if (!h) return fail("null handle");
   h->autotune = on != 0;
-  h->tuned_sgc = h->tuned_can = -1;
+  reset_tuning(h);
   return 0;
 }
 
@@ -834,7 +847,7 @@ int cemc_get_variant(cemc_handle *h, int *sgc, int *canonical) {
 int cemc_set_cluster(cemc_handle *h, int c) {
   if (!h) return fail("null handle");
   if (c < 0 || c > 2) return fail("cluster size must be 0 (auto), 1 or 2");
-  h->tuned_sgc = h->tuned_can = -1;
+  reset_tuning(h);
   h->cluster = c;
   return 0;
 }
@@ -842,14 +855,14 @@ int cemc_set_cluster(cemc_handle *h, int c) {
 int cemc_set_spin_kernel(cemc_handle *h, int on) {
   if (!h) return fail("null handle");
   h->no_spin = (on == 0);
-  h->tuned_sgc = h->tuned_can = -1;
+  reset_tuning(h);
   return 0;
 }
 
 int cemc_set_table_eval(cemc_handle *h, int on) {
   if (!h) return fail("null handle");
   h->no_tab = (on == 0);
-  h->tuned_sgc = h->tuned_can = -1;
+  reset_tuning(h);
   return 0;
 }
 
@@ -871,7 +884,7 @@ int cemc_set_screen_slack(cemc_handle *h, double factor) {
 int cemc_set_batch(cemc_handle *h, int b) {
   if (!h) return fail("null handle");
   if (!(b == -1 || b == 0 || b == 4 || b == 8 || b == 16)) return fail("batch must be -1 (off), 0 (auto), 4, 8 or 16");
-  h->tuned_sgc = h->tuned_can = -1;
+  reset_tuning(h);
   h->batch = b;
   return 0;
 }
@@ -879,7 +892,7 @@ int cemc_set_batch(cemc_handle *h, int b) {
 int cemc_set_generic_path(cemc_handle *h, int on) {
   if (!h) return fail("null handle");
   h->force_generic = on != 0;
-  h->tuned_sgc = h->tuned_can = -1;
+  reset_tuning(h);
   return 0;
 }
 
@@ -1113,15 +1126,45 @@ static int run_tuned(cemc_handle *h, long long n_steps) {
       int rc = launch_variant<MODE>(h, run_args(h, seg / 4), v);
       if (rc == -1) continue;
       if (rc) return rc;
-      CU(cudaEventRecord(h->ev0, h->stream));
+      CU(cudaEventRecord(h->tv0, h->stream));
       rc = launch_variant<MODE>(h, run_args(h, seg), v);
       if (rc) return rc;
-      CU(cudaEventRecord(h->ev1, h->stream));
-      CU(cudaEventSynchronize(h->ev1));
+      CU(cudaEventRecord(h->tv1, h->stream));
+      CU(cudaEventSynchronize(h->tv1));
       float ms = 0.f;
-      CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      CU(cudaEventElapsedTime(&ms, h->tv0, h->tv1));
       done += seg + seg / 4;
       if (ms < best_ms) { best_ms = ms; best = v; }
+    }
+  }
+  // short launches (e.g. the 1728-move legs between parallel-tempering exchanges): tune
+  // across calls -- every call runs one untested variant (a quarter of the moves untimed
+  // as warm-up, the rest timed); when all are timed the fastest is kept
+  if (best < 0 && done == 0 && h->autotune && h->trace_capacity == 0 && n_steps >= 256 && n_steps < 8 * seg) {
+    int &next = h->xt_next[MODE == MODE_SGC ? 0 : 1];
+    float *xms = h->xt_ms[MODE == MODE_SGC ? 0 : 1];
+    while (next < kNumVariants) {
+      const int v = next++;
+      xms[v] = 1e30f;
+      if (!variant_allowed(h, v)) continue;
+      const long long n1 = n_steps / 4;
+      int rc = launch_variant<MODE>(h, run_args(h, n1), v);
+      if (rc == -1) continue;
+      if (rc) return rc;
+      CU(cudaEventRecord(h->tv0, h->stream));
+      rc = launch_variant<MODE>(h, run_args(h, n_steps - n1), v);
+      if (rc) return rc;
+      CU(cudaEventRecord(h->tv1, h->stream));
+      CU(cudaEventSynchronize(h->tv1));
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, h->tv0, h->tv1));
+      xms[v] = ms / (float)(n_steps - n1);
+      done = n_steps;
+      break;
+    }
+    if (next >= kNumVariants) {
+      float bm = 1e30f;
+      for (int v = 0; v < kNumVariants; v++) if (xms[v] < bm) { bm = xms[v]; best = v; }
     }
   }
   if (done >= n_steps) return 0;

@@ -142,7 +142,9 @@ class ParallelTempering(object):
         self.gpu.synchronize()
         if self.world > 1:
             import torch.distributed as dist
-            e_loc = torch.from_numpy(self.gpu.get_energy()).to(d["dev"])
+            # the local energies never leave the device: wrap the updater's buffer
+            e_loc = torch.as_tensor(parallel.DeviceArrayF64(self.gpu.energy_dev_ptr(), self.gpu.R),
+                                    device=d["dev"])
             dist.all_gather_into_tensor(d["e_all"], e_loc)      # NCCL over NVLink
             e_ptr = d["e_all"].data_ptr()
         else:

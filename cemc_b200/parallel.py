@@ -71,3 +71,13 @@ def exchange_sweep(energies, slot_of_replica, kT_of_slot, direction, seed, rnd,
     new_slots = np.empty(n, dtype=np.int32)
     new_slots[rep_of_slot] = np.arange(n, dtype=np.int32)
     return new_slots, n_acc
+
+
+class DeviceArrayF64(object):
+    """A raw CUDA device pointer seen through ``__cuda_array_interface__`` so that
+    ``torch.as_tensor(obj, device=...)`` aliases it (no copy): the updater's
+    per-replica energies feed the NCCL all-gather of the exchange step directly."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr="<f8",
+                                             data=(int(ptr), False), version=2)

@@ -114,6 +114,18 @@ def c4_parallel_tempering(R=64, replica_offset=0, n_total=512, L=12):
     return w
 
 
+def c5_large_supercell(R=1, replica_offset=0, L=64):
+    """Config 5: fcc 64x64x64 binary (262 144 sites, 90/10), single-chain exact
+    canonical Metropolis (CTA cluster on one chain); R > 1 = seed ensemble."""
+    st = syn.fcc_settings(L, ["Al", "Mg"], syn.STANDARD_FAMILIES)
+    eci = syn.almg_ecis(st)
+    conc = {"Al": 0.9, "Mg": 0.1}
+    ft = FlatTables(st, eci, syn.random_symbols(st, conc, seed=0))
+    occ = _occ(st, ft, conc, R, 5000 + replica_offset, True)
+    return Workload("C5", st, eci, ft, occ, np.full(R, 600.0 * KB), None, "canonical", 2,
+                    "fcc %dx%dx%d binary canonical, %d chain(s), T=600 K" % (L, L, L, R))
+
+
 def make_updater(w: Workload, device=0, replica_offset=0, stream=None, seed=1234):
     """Upload a workload: returns a ready BatchedCEUpdater."""
     from .updater import BatchedCEUpdater
@@ -130,4 +142,4 @@ def make_updater(w: Workload, device=0, replica_offset=0, stream=None, seed=1234
 
 WORKLOADS = {"C1": c1_almg_canonical, "C2": c2_almg_sgc_sweep,
              "C3": c3_almgsi_canonical, "C3S": c3s_almgsi_sgc,
-             "C4": c4_parallel_tempering}
+             "C4": c4_parallel_tempering, "C5": c5_large_supercell}

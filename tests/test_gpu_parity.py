@@ -680,3 +680,25 @@ def test_two_moves_per_warp_variants(cuda_device, variant, system, mode):
         accs = gpu.get_accumulators()
         for r, c in enumerate(chains):
             assert np.array_equal(accs[r], c.acc)
+
+
+def test_short_launch_autotuning_is_invariant(cuda_device):
+    """Launches too short for the in-run autotuner (e.g. the legs between parallel-tempering
+    exchanges) are tuned across calls: every call times another kernel variant, then the
+    fastest is kept.  The trajectory must not depend on any of it."""
+    st, eci, symbols, ft = build(**TERNARY)
+    gpu, chains = make_pair(ft, [symbols] * 3, [0.03, 0.07, 0.15], seed=57)
+    gpu.reset_accumulators()
+    for _ in range(11):
+        gpu.run_canonical(300)
+        gpu.run_sgc(260)
+    gpu.synchronize()
+    assert min(gpu.get_variant()) >= 0           # both samplers settled on a variant
+    for c in chains:
+        for _ in range(11):
+            c.run_canonical(300)
+            c.run_sgc(260)
+    assert_state_equal(gpu, chains)
+    accs = gpu.get_accumulators()
+    for r, c in enumerate(chains):
+        assert np.array_equal(accs[r], c.acc)
