@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CEMC_B200_LIB") or os.path.join(_HERE, "_cemc_b200.so")
 _CSRC = os.path.join(_HERE, "csrc")
 # translation units (compiled in parallel, linked into one library) and their headers
-UNITS = ["cemc_b200.cu", "cemc_batch_product.cu", "cemc_batch_spin.cu", "cemc_batch_tab.cu"]
+UNITS = ["cemc_b200.cu", "cemc_batch_product.cu", "cemc_batch_spin.cu", "cemc_batch_tab.cu",
+         "cemc_batch_tab32.cu"]
 HEADERS = ["cemc_kernels.cuh", "cemc_spin_kernel.cuh", "cemc_batch_kernel.cuh",
            "cemc_batch_launch.cuh"]
 SOURCES = [os.path.join(_CSRC, f) for f in UNITS + HEADERS] + \
@@ -80,6 +81,7 @@ SIGNATURES = {
     "cemc_set_variant": [_H, C.c_int, C.c_int],
     "cemc_set_spin_kernel": [_H, C.c_int],
     "cemc_set_table_eval": [_H, C.c_int],
+    "cemc_set_precision": [_H, C.c_int],
     "cemc_get_batch_eval": [_H, _i32p],
     "cemc_set_screen_slack": [_H, C.c_double],
     "cemc_debug_phase_cycles": [_H, _u64p],

@@ -94,6 +94,7 @@ struct cemc_handle {
   SpinTables spin{};
   bool tab_ok = false;                // product tables fit: table evaluation in the batch kernel
   bool no_tab = false;                // testing: keep the fp64 product evaluation
+  bool fp32 = false;                  // cemc_set_precision(32): single-precision tables / sums
   TabTables tab{};
   unsigned long long *d_phase = nullptr;   // CEMC_PHASE_TIMING builds
 };
@@ -612,6 +613,8 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
     if ((rc = dupload(h, &h->tab.desc, tb_desc))) return rc;
     if ((rc = dupload(h, &h->tab.task, tb_task))) return rc;
     if ((rc = dupload(h, &h->tab.tab, tb_tab))) return rc;
+    std::vector<float> tb_tab32(tb_tab.begin(), tb_tab.end());      // each entry rounded once
+    if ((rc = dupload(h, &h->tab.tab32, tb_tab32))) return rc;
   }
 #ifdef CEMC_PHASE_TIMING
   if ((rc = dalloc(h, &h->d_phase, (size_t)n_replicas * 24))) return rc;
@@ -866,9 +869,21 @@ int cemc_set_table_eval(cemc_handle *h, int on) {
   return 0;
 }
 
+int cemc_set_precision(cemc_handle *h, int bits) {
+  if (!h) return fail("null handle");
+  if (bits != 32 && bits != 64) return fail("precision must be 32 or 64");
+  const bool spin = h->spin_ok && h->t.allowed_identity && h->spin.n_rounds <= 4;
+  if (bits == 32 && !spin && !h->tab_ok)
+    return fail("the fp32 variant needs the table evaluation (<= 32 ECIs, one symmetry group, tables in shared memory)");
+  h->fp32 = (bits == 32);
+  reset_tuning(h);
+  return 0;
+}
+
 int cemc_get_batch_eval(cemc_handle *h, int *ev) {
   if (!h || !ev) return fail("null argument");
   if (h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4) *ev = EV_SPIN;
+  else if (h->tab_ok && h->fp32) *ev = EV_TAB32;
   else if (h->tab_ok && !h->no_tab) *ev = EV_TAB;
   else *ev = EV_PRODUCT;
   return 0;
@@ -1072,6 +1087,8 @@ static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 
   int rc;
   if (h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4)
     rc = batch_launch_spin(L);          // binary +-1 basis: spin evaluation
+  else if (h->tab_ok && h->fp32)
+    rc = batch_launch_tab32(L);         // fp32 product tables (opt-in)
   else if (h->tab_ok && !h->no_tab)
     rc = batch_launch_tab(L);           // product tables
   else
@@ -1101,6 +1118,9 @@ static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
 }
 
 static bool variant_allowed(const cemc_handle *h, int v) {
+  // fp32 variant of a non-binary system: only the batch kernels evaluate in fp32; mixing in
+  // the fp64 kernels would make the result depend on the tuner's timing
+  if (h->fp32 && !h->spin_ok && (v == 0 || v == 5)) return false;
   if (v == 0 && h->batch > 0) return false;       // an explicit batch size asks for the batch kernel
   if ((v >= 1 && v <= 4) || v >= 6) {
     static const int Bs[8] = {0, 16, 16, 8, 4, 0, 8, 16}, Cs[8] = {0, 2, 1, 1, 1, 0, 1, 1};

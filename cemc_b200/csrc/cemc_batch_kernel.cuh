@@ -16,6 +16,11 @@
 //     committed state.  The Philox stream is keyed by the step index, so the
 //     restart changes nothing.
 //
+// EV_TAB32 (opt-in fp32 variant, cemc_set_precision): the tables and the sums over the
+// sub-clusters are single precision (half the shared-memory traffic, FADD instead of DADD
+// chains); quotients, CF vector, energies and observer sums stay fp64.  Same decisions as the
+// fp64 path unless |dE + kT ln u| is below fp32 rounding; CFs / energies within 1e-5 (tested).
+//
 // Results are bit-identical to the one-move-at-a-time kernels (tested): the
 // arithmetic of each phase is the same code path, operation for operation.
 // CTA clusters (template parameter C > 1): C CTAs of one thread-block cluster work on
@@ -31,6 +36,7 @@
 // in shared memory; everything else runs mc_kernel.
 #pragma once
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "cemc_kernels.cuh"
 #include "cemc_spin_kernel.cuh"
@@ -53,9 +59,10 @@ struct TabTables {
   const uint2 *desc;  // [n_rounds*32] x: col0 | col1<<8 | col2<<16 | n_deco<<24; y: w0 | w1<<8 | w2<<16 | wref<<24 (w = S^position)
   const int4 *task;   // [n_tasks] {byte offset of the task's column in its family's table, first sub-cluster, M, 0}
   const double *tab;  // [n_tab] per family [code][decoration] product tables
+  const float *tab32; // the same tables rounded to fp32 (EV_TAB32, the fp32 variant)
 };
 
-enum BatchEval : int { EV_PRODUCT = 0, EV_SPIN = 1, EV_TAB = 2 };
+enum BatchEval : int { EV_PRODUCT = 0, EV_SPIN = 1, EV_TAB = 2, EV_TAB32 = 3 };
 
 struct BatchSmem {
   double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *Pm, *Ch, *obE, *tab, *pub;
@@ -77,7 +84,8 @@ template <int B, int BT = B>
 __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char *base,
                                                     const DeviceTables &t, bool canonical,
                                                     bool state_in_smem = true,
-                                                    const TabTables *tb = nullptr) {
+                                                    const TabTables *tb = nullptr,
+                                                    bool tab_fp32 = false) {
   size_t o = 0;
 #define CEMC_TAKE(field, type, count)                                   \
   do {                                                                  \
@@ -97,7 +105,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(PO, double, tb ? 0 : B * nj * t.max_slots);
   CEMC_TAKE(PN, double, tb ? 0 : B * nj * t.max_slots);
   CEMC_TAKE(diff, double, B * nj * t.max_tasks);
-  CEMC_TAKE16(tab, double, tb ? tb->n_tab : 0);
+  CEMC_TAKE16(tab, double, tb ? (tab_fp32 ? (tb->n_tab + 1) / 2 : tb->n_tab) : 0);
   CEMC_TAKE16(ttask, int4, tb ? t.n_tasks_total : 0);
   o = align_up(o, 16);                     // code words are read four at a time
   CEMC_TAKE(codes, uint32_t, tb ? B * nj * tb->n_sub : 0);
@@ -133,6 +141,12 @@ __device__ __forceinline__ int offs_of(const int (&offs)[9], int sp) {
   return v;
 }
 
+// one rounding per operation in either precision (no contraction: -fmad=false and the intrinsics)
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+
 // One WARP evaluates one trial move; B warps = B moves per batch.
 // kStateSmem = false: occupations / site lists stay in global memory (L2): supercells
 // whose occupations do not fit in shared memory (64^3); the batch hides the latency.
@@ -150,7 +164,9 @@ __global__ void __launch_bounds__((B + 1) * 32, (EV != EV_PRODUCT && B <= 8) ? 2
 batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTables sp, TabTables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   namespace cg = cooperative_groups;
-  constexpr bool kSpin = (EV == EV_SPIN), kTab = (EV == EV_TAB);
+  constexpr bool kSpin = (EV == EV_SPIN), kTab32 = (EV == EV_TAB32), kTab = (EV == EV_TAB) || kTab32;
+  using TR = typename std::conditional<kTab32, float, double>::type;      // table / sub-cluster-sum type
+  constexpr int TSH = kTab32 ? 2 : 3;                                       // log2(sizeof(TR))
   constexpr bool kCanon = (MODE == MODE_CANONICAL);
   constexpr int NJ = kCanon ? 2 : 1;
   constexpr int BW = B * C;                      // evaluation warps of the chain
@@ -173,7 +189,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   int32_t *g_list = st.list + (size_t)r * N;
   int32_t *g_loc = st.loc + (size_t)r * N;
   BatchSmem s;
-  batch_smem_layout<B, BT>(&s, smem_raw, t, kCanon, kStateSmem, kTab ? &tb : nullptr);
+  batch_smem_layout<B, BT>(&s, smem_raw, t, kCanon, kStateSmem, kTab ? &tb : nullptr, kTab32);
   if (!kStateSmem) { s.occ = g_occ; s.list = g_list; }
   // CTA 0's copies of the arrays the deciding warp reads (DSMEM when C > 1)
   BatchSmem s0 = s;
@@ -205,13 +221,13 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   if (tid == 0) mbar_init(s.mbar, 1);
   __syncthreads();
   if (tid == 0) {
-    const uint32_t b_tab = kTab ? (uint32_t)align_up((size_t)tb.n_tab * 8, 16) : 0u;
+    const uint32_t b_tab = kTab ? (uint32_t)align_up((size_t)tb.n_tab * sizeof(TR), 16) : 0u;
     const uint32_t b_ttask = kTab ? (uint32_t)t.n_tasks_total * 16u : 0u;
     const uint32_t b_items = kTab ? 0u : (uint32_t)t.n_items_total * 16u;
     const uint32_t b_tsum = kTab ? 0u : (uint32_t)align_up((size_t)t.n_tasks_total * 8, 16);
     const uint32_t b_occ = occ_tma ? (uint32_t)N : 0u, b_list = list_tma ? (uint32_t)N * 4u : 0u;
     mbar_expect_tx(s.mbar, b_tab + b_ttask + b_items + b_tsum + b_occ + b_list);
-    if (b_tab) tma_bulk_g2s(s.tab, tb.tab, b_tab, s.mbar);
+    if (b_tab) tma_bulk_g2s(s.tab, kTab32 ? (const void *)tb.tab32 : (const void *)tb.tab, b_tab, s.mbar);
     if (b_ttask) tma_bulk_g2s(s.ttask, tb.task, b_ttask, s.mbar);
     if (b_items) tma_bulk_g2s(s.items, t.items4, b_items, s.mbar);
     if (b_tsum) tma_bulk_g2s(s.task_sum, t.task_sum, b_tsum, s.mbar);
@@ -724,8 +740,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                                     (uint32_t)vc * ((tdy[q] >> 16) & 0xffu);
               const uint32_t wr = tdy[q] >> 24, nd = tdx[q] >> 24;    // nd: decorations per table row
               const uint32_t cO = (rest + (uint32_t)olds[j] * wr) * nd, cN = (rest + (uint32_t)news[j] * wr) * nd;
-              uint32_t word = (cO << 3) | (cN << 19);
-              if (tdy[q] == 0u) { const uint32_t z = tdx[q] & 0xffffu; word = z | (z << 16); }   // padding: the table's zero row
+              uint32_t word = (cO << TSH) | (cN << (16 + TSH));
+              if (tdy[q] == 0u) { const uint32_t z = (tdx[q] & 0xffffu) >> (3 - TSH); word = z | (z << 16); }   // padding: the table's zero row
               if (q * 32 + lane < n_sub) cw[j * n_sub + q * 32 + lane] = word;
             }
           }
@@ -737,13 +753,13 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         double *db = s.diff + lwarp * NJ * max_tasks;
         for (int tk = lane; tk < n_tasks; tk += 32) {
           const int4 tt = s.ttask[tk];
-          const char *tbl = reinterpret_cast<const char *>(s.tab) + tt.x;
+          const char *tbl = reinterpret_cast<const char *>(s.tab) + (tt.x >> (3 - TSH));
           const uint32_t *cp = cw + tt.y;
-          auto TV = [&](uint32_t off) { return *reinterpret_cast<const double *>(tbl + off); };
+          auto TV = [&](uint32_t off) { return *reinterpret_cast<const TR *>(tbl + off); };
           if (!kTree) {
-            double spO[NJ], spN[NJ];
+            TR spO[NJ], spN[NJ];
 #pragma unroll
-            for (int j = 0; j < NJ; j++) { spO[j] = 0.0; spN[j] = 0.0; }
+            for (int j = 0; j < NJ; j++) { spO[j] = (TR)0; spN[j] = (TR)0; }
 #pragma unroll 1
             for (int m = 0; m < tt.z; m += 8) {         // M is padded to a multiple of 8 with zero entries
               uint4 w[NJ][2];
@@ -752,7 +768,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                 w[j][0] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m);
                 w[j][1] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m + 4);
               }
-              double vo[NJ][8], vn[NJ][8];
+              TR vo[NJ][8], vn[NJ][8];
 #pragma unroll
               for (int j = 0; j < NJ; j++)
 #pragma unroll
@@ -765,24 +781,24 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
               for (int x = 0; x < 8; x++)
 #pragma unroll
-                for (int j = 0; j < NJ; j++) { spO[j] = __dadd_rn(spO[j], vo[j][x]); spN[j] = __dadd_rn(spN[j], vn[j][x]); }
+                for (int j = 0; j < NJ; j++) { spO[j] = add_rn(spO[j], vo[j][x]); spN[j] = add_rn(spN[j], vn[j][x]); }
             }
 #pragma unroll
-            for (int j = 0; j < NJ; j++) db[j * max_tasks + tk] = __dsub_rn(spN[j], spO[j]);     // :397
+            for (int j = 0; j < NJ; j++) db[j * max_tasks + tk] = (double)sub_rn(spN[j], spO[j]);     // :397
           } else {
 #pragma unroll
             for (int j = 0; j < NJ; j++) {
-              double o[4] = {0.0, 0.0, 0.0, 0.0}, n[4] = {0.0, 0.0, 0.0, 0.0};
+              TR o[4] = {(TR)0, (TR)0, (TR)0, (TR)0}, n[4] = {(TR)0, (TR)0, (TR)0, (TR)0};
 #pragma unroll 1
               for (int m = 0; m < tt.z; m += 4) {
                 const uint4 w = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m);
-                o[0] = __dadd_rn(o[0], TV(w.x & 0xffffu)); n[0] = __dadd_rn(n[0], TV(w.x >> 16));
-                o[1] = __dadd_rn(o[1], TV(w.y & 0xffffu)); n[1] = __dadd_rn(n[1], TV(w.y >> 16));
-                o[2] = __dadd_rn(o[2], TV(w.z & 0xffffu)); n[2] = __dadd_rn(n[2], TV(w.z >> 16));
-                o[3] = __dadd_rn(o[3], TV(w.w & 0xffffu)); n[3] = __dadd_rn(n[3], TV(w.w >> 16));
+                o[0] = add_rn(o[0], TV(w.x & 0xffffu)); n[0] = add_rn(n[0], TV(w.x >> 16));
+                o[1] = add_rn(o[1], TV(w.y & 0xffffu)); n[1] = add_rn(n[1], TV(w.y >> 16));
+                o[2] = add_rn(o[2], TV(w.z & 0xffffu)); n[2] = add_rn(n[2], TV(w.z >> 16));
+                o[3] = add_rn(o[3], TV(w.w & 0xffffu)); n[3] = add_rn(n[3], TV(w.w >> 16));
               }
-              db[j * max_tasks + tk] = __dsub_rn(__dadd_rn(__dadd_rn(n[0], n[1]), __dadd_rn(n[2], n[3])),
-                                                 __dadd_rn(__dadd_rn(o[0], o[1]), __dadd_rn(o[2], o[3])));
+              db[j * max_tasks + tk] = (double)sub_rn(add_rn(add_rn(n[0], n[1]), add_rn(n[2], n[3])),
+                                                 add_rn(add_rn(o[0], o[1]), add_rn(o[2], o[3])));
             }
           }
         }

@@ -27,6 +27,7 @@ struct BatchLaunch {
 int batch_launch_product(const BatchLaunch &L);
 int batch_launch_spin(const BatchLaunch &L);
 int batch_launch_tab(const BatchLaunch &L);
+int batch_launch_tab32(const BatchLaunch &L);
 
 template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M>
 static int batch_launch_kc(const BatchLaunch &L, size_t sm) {
@@ -50,10 +51,11 @@ static int batch_launch_kc(const BatchLaunch &L, size_t sm) {
 
 template <int MODE, bool kTree, int B, int C, int EV, int M = 1>
 static int batch_launch_b(const BatchLaunch &L) {
-  const TabTables *tb = EV == EV_TAB ? &L.tb : nullptr;
-  size_t sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, tb);
+  const TabTables *tb = (EV == EV_TAB || EV == EV_TAB32) ? &L.tb : nullptr;
+  constexpr bool f32 = (EV == EV_TAB32);
+  size_t sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, tb, f32);
   const bool in_smem = sm <= (size_t)L.max_smem_optin;
-  if (!in_smem) sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, false, tb);
+  if (!in_smem) sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, false, tb, f32);
   if (sm > (size_t)L.max_smem_optin) return -1;
   if constexpr (M > 1) {            // two moves per warp: shared-memory state only
     return in_smem ? batch_launch_kc<MODE, kTree, B, true, C, EV, M>(L, sm) : -1;

@@ -154,6 +154,11 @@ class BatchedCEUpdater(object):
         """Testing hook: product tables (default) vs fp64 products in the batch kernel."""
         _lib.check(self.lib.cemc_set_table_eval(self._h, 1 if on else 0))
 
+    def set_precision(self, bits: int):
+        """64 (default, bit-identical to the reference) or 32: the fp32 variant
+        (single-precision product tables and sub-cluster sums, fp64 everything else)."""
+        _lib.check(self.lib.cemc_set_precision(self._h, int(bits)))
+
     def get_batch_eval(self) -> int:
         """0 fp64 products, 1 binary spin, 2 product tables."""
         v = C.c_int32(-1)

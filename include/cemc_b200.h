@@ -137,8 +137,17 @@ int cemc_set_spin_kernel(cemc_handle *h, int on);
  * the product tables (cemc_batch_kernel.cuh, EV_TAB); both give the same bits      */
 int cemc_set_table_eval(cemc_handle *h, int on);
 /* evaluation scheme the batch kernel uses for this system: 0 fp64 products, 1 binary
- * spin (XOR / popcount), 2 product tables                                          */
+ * spin (XOR / popcount), 2 product tables, 3 fp32 product tables                    */
 int cemc_get_batch_eval(cemc_handle *h, int *ev);
+/* Precision of the cluster-product sums: 64 (default; bit-identical to the reference's
+ * fp64 CEUpdater) or 32 = the fp32 variant: product tables and sums over sub-clusters
+ * (spin_product_one_atom, ce_updater.cpp:244-285) in single precision, quotients, CF
+ * vector, energies and observer sums in fp64.  Same accept/reject decisions as fp64
+ * unless a move lies within fp32 rounding of its Metropolis threshold; CFs and
+ * energies within 1e-5 relative.  Needs a system the table evaluation takes (<= 32
+ * ECIs, one symmetry group, tables fit shared memory); a binary +-1 basis is exact
+ * integer arithmetic in either setting.  Fails otherwise.                            */
+int cemc_set_precision(cemc_handle *h, int bits);
 /* testing hook: widen the band in which the batch kernel's Metropolis screen
  * defers to the exact expression (factor >= 1; 1e30 = always exact)           */
 int cemc_set_screen_slack(cemc_handle *h, double factor);

@@ -702,3 +702,64 @@ def test_short_launch_autotuning_is_invariant(cuda_device):
     accs = gpu.get_accumulators()
     for r, c in enumerate(chains):
         assert np.array_equal(accs[r], c.acc)
+
+
+@pytest.mark.parametrize("variant", [-1, 1, 2, 3])
+def test_fp32_variant(cuda_device, variant):
+    """The fp32 variant (cemc_set_precision(32)): product tables and sub-cluster sums in
+    single precision, quotients / CF vector / energies in fp64.  North-star bar: the same
+    accept/reject decisions as the fp64 reference, energies and CFs within 1e-5 relative
+    (tolerance of this test; the fp64 default is bit-exact)."""
+    from cemc_b200._lib import CemcError
+    st, eci, symbols, ft = build(**dict(TERNARY, L=5))
+    R = 4
+    kTs = np.linspace(0.02, 0.15, R)
+    gpu, chains = make_pair(ft, [symbols] * R, kTs, seed=211)
+    gpu.set_precision(32)
+    assert gpu.get_batch_eval() == 3
+    if variant >= 0:
+        gpu.set_variant(variant, variant)
+    n = 4000
+    gpu.set_trace(n)
+    gpu.run_sgc(n)
+    gpu.synchronize()
+    acc_sgc = gpu.get_trace(n)[3].copy()
+    gpu.run_canonical(n)
+    gpu.synchronize()
+    tr = gpu.get_trace(n)
+    for r, c in enumerate(chains):
+        o = c.run_sgc(n, trace=True)
+        assert np.array_equal(acc_sgc[r], o[3])                # decisions identical
+        o = c.run_canonical(n, trace=True)
+        assert np.array_equal(tr[3][r], o[3])
+        # energy after every move: 1e-5 relative to the energy scale of the trajectory
+        np.testing.assert_allclose(tr[4][r], o[4], rtol=1e-5, atol=1e-5 * np.abs(o[4]).max())
+    assert np.array_equal(gpu.get_occupancy(), np.stack([c.occ for c in chains]))
+    cf, cf_ref = gpu.get_cf(), np.stack([c.cf for c in chains])
+    np.testing.assert_allclose(cf, cf_ref, rtol=1e-5, atol=1e-5 * np.abs(cf_ref).max())
+    e_ref = np.array([c.e for c in chains])
+    np.testing.assert_allclose(gpu.get_energy(), e_ref, rtol=1e-5, atol=1e-5 * np.abs(e_ref).max())
+    assert not np.array_equal(cf, cf_ref)                      # it really was single precision
+    # back to fp64: bit-exact again from the oracle's state
+    gpu.set_precision(64)
+    gpu.set_cf(cf_ref)
+    gpu.run_sgc(500)
+    gpu.synchronize()
+    for c in chains:
+        c.run_sgc(500)
+    assert_state_equal(gpu, chains)
+    # a binary +-1 system is integer arithmetic in either setting
+    st, eci, symbols, ft = build(**BINARY)
+    gpu, chains = make_pair(ft, [symbols] * 2, [0.03, 0.1], seed=5)
+    gpu.set_precision(32)
+    gpu.run_sgc(1000)
+    gpu.synchronize()
+    for c in chains:
+        c.run_sgc(1000)
+    assert_state_equal(gpu, chains)
+    # no table evaluation for this system (quaternary quadruplets): refused, loudly
+    species = ["Al", "Cu", "Mg", "Si"]
+    st, eci, symbols, ft = build(4, species, ["nn", "tet"], {"Al": 0.4, "Cu": 0.2, "Mg": 0.2, "Si": 0.2})
+    gpu, chains = make_pair(ft, [symbols], [0.05], seed=5)
+    with pytest.raises(CemcError):
+        gpu.set_precision(32)
