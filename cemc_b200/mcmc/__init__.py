@@ -1,7 +1,10 @@
 """Samplers of the hot path (mirrors of cemc.mcmc.{Montecarlo, SGCMonteCarlo,
 ParallelTempering, MCParameterSweep}, /root/reference/cemc/mcmc/)."""
 from .averager import Averager  # noqa: F401
-from .mc_observers import MCObserver, SGCObserver  # noqa: F401
+from .mc_observers import (EnergyEvolution, EnergyHistogram,  # noqa: F401
+                           LowestEnergyStructure, MCObserver,
+                           PairCorrelationObserver, SGCObserver,
+                           SiteOrderParameter)
 from .montecarlo import (CanNotFindLegalMoveError,  # noqa: F401
                          DidNotReachEquillibriumError, Montecarlo,
                          TooFewElementsError)

@@ -86,3 +86,191 @@ class SGCObserver(MCObserver):
     @property
     def counter(self):
         return self.quantities["counter"]
+
+
+# ---- observers of the chain state ---------------------------------
+# Called at their ``interval`` like in the reference: the samplers stop the device loop on
+# the boundary, mirror the occupations into ``atoms`` and pass the NET changes since the
+# previous call (``Montecarlo._steps``).  All four only look at the state on the boundary
+# (energy, CFs, symbols), which is what the reference's versions see at that step too.
+
+class PairCorrelationObserver(MCObserver):
+    """Thermal average and spread of the pair correlation functions
+    (reference: cemc/mcmc/mc_observers.py:81-136; every ``c2_*`` name of the ECI set)."""
+
+    def __init__(self, ce_calc):
+        super(PairCorrelationObserver, self).__init__()
+        self.name = "PairCorrelationObserver"
+        self.ce_calc = ce_calc
+        if getattr(ce_calc, "updater", None) is None:
+            raise RuntimeError("This observer needs the CE calculator's updater")
+        self._names = [k for k in ce_calc.eci.keys() if k.startswith("c2_")]
+        self.reset()
+
+    def reset(self):
+        self.cf = {k: 0.0 for k in self._names}
+        self.cf_squared = {k: 0.0 for k in self._names}
+        self.n_entries = 0
+
+    def __call__(self, system_changes):
+        now = self.ce_calc.updater.get_cf()
+        self.n_entries += 1
+        for k in self._names:
+            v = now[k]
+            self.cf[k] += v
+            self.cf_squared[k] += v * v
+
+    def get_averages(self):
+        return {k: v / self.n_entries for k, v in self.cf.items()}
+
+    def get_std(self):
+        n = float(self.n_entries)
+        return {k: float(np.sqrt(max(self.cf_squared[k] / n - (self.cf[k] / n) ** 2, 0.0)))
+                for k in self._names}
+
+
+class LowestEnergyStructure(MCObserver):
+    """Keeps the lowest-energy state seen on the observer's boundaries
+    (reference: mc_observers.py:138-183: first call stores the state, later calls replace
+    it when ``mc_obj.current_energy`` is strictly lower)."""
+
+    def __init__(self, ce_calc, mc_obj, verbose=False):
+        super(LowestEnergyStructure, self).__init__()
+        self.name = "LowestEnergyStructure"
+        self.ce_calc = ce_calc
+        self.mc_obj = mc_obj
+        self.verbose = verbose
+        self.reset()
+
+    def reset(self):
+        self.lowest_energy = np.inf
+        self.lowest_energy_cf = None
+        self.atoms = None
+        self.lowest_energy_atoms = None        # alias kept by the reference
+
+    def _store(self):
+        self.lowest_energy = self.mc_obj.current_energy
+        self.lowest_energy_cf = self.ce_calc.get_cf()
+        self.atoms = self.mc_obj.atoms.copy()
+        self.lowest_energy_atoms = self.atoms
+
+    def __call__(self, system_changes):
+        if self.atoms is None or self.lowest_energy_cf is None:
+            self._store()
+        elif self.mc_obj.current_energy < self.lowest_energy:
+            dE = self.mc_obj.current_energy - self.lowest_energy
+            self._store()
+            if self.verbose:
+                print("Found new low energy structure. New energy: {} eV. Change: {} eV".format(
+                    self.lowest_energy, dE))
+
+
+class SiteOrderParameter(MCObserver):
+    """Number of sites whose species differs from the initial configuration, averaged over
+    the calls (reference: mc_observers.py:614-686; symbols stand in for atomic numbers)."""
+
+    def __init__(self, atoms):
+        super(SiteOrderParameter, self).__init__()
+        self.name = "SiteOrderParameter"
+        self.atoms = atoms
+        self.orig_symbols = np.array([a.symbol for a in atoms])
+        self.reset()
+
+    def _check_all_sites(self):
+        now = np.array([a.symbol for a in self.atoms])
+        self.site_changed = now != self.orig_symbols
+        self.current_num_changed = int(np.count_nonzero(self.site_changed))
+
+    def reset(self):
+        self.avg_num_changed = 0
+        self.avg_num_changed_sq = 0
+        self.num_calls = 0
+        self._check_all_sites()
+
+    def __call__(self, system_changes):
+        self.num_calls += 1
+        for change in system_changes:            # atoms already hold the new symbols
+            i = change[0]
+            differs = self.atoms[i].symbol != self.orig_symbols[i]
+            if differs != bool(self.site_changed[i]):
+                self.current_num_changed += 1 if differs else -1
+                self.site_changed[i] = differs
+        self.avg_num_changed += self.current_num_changed
+        self.avg_num_changed_sq += self.current_num_changed ** 2
+
+    def get_averages(self):
+        avg = float(self.avg_num_changed) / self.num_calls
+        var = max(float(self.avg_num_changed_sq) / self.num_calls - avg ** 2, 0.0)
+        return {"site_order_average": avg, "site_order_std": float(np.sqrt(var))}
+
+
+class EnergyEvolution(MCObserver):
+    """Energy on every boundary (reference: mc_observers.py:689-706)."""
+
+    def __init__(self, mc_obj):
+        super(EnergyEvolution, self).__init__()
+        self.name = "EnergyEvolution"
+        self.mc = mc_obj
+        self.energies = []
+
+    def __call__(self, system_changes):
+        self.energies.append(self.mc.current_energy_without_vib())
+
+    def reset(self):
+        self.energies = []
+
+
+class EnergyHistogram(MCObserver):
+    """Histogram of the sampled energies (reference: mc_observers.py:709-761): the first
+    ``buffer_size`` samples fix the range [Emin, Emax], later samples are binned directly.
+    The reference sizes its histogram with ``len(self.n_bins)`` (a TypeError for the int it
+    documents, :742); here the histogram has ``n_bins`` bins, and samples outside the range
+    fixed by the buffer are clamped to the edge bins."""
+
+    def __init__(self, mc_obj, buffer_size=100000, n_bins=100):
+        super(EnergyHistogram, self).__init__()
+        self.name = "EnergyHistogram"
+        self.mc = mc_obj
+        self.n_bins = int(n_bins)
+        self.buffer = np.zeros(int(buffer_size))
+        self.reset()
+
+    def reset(self):
+        self._next = 0
+        self._histogram = None
+        self.Emin = None
+        self.Emax = None
+        self.sample_in_buffer = True
+
+    def _get_indx(self, E):
+        if self.Emin is None or self.Emax is None:
+            raise RuntimeError("the histogram range is not fixed yet")
+        if self.Emax == self.Emin:
+            return 0
+        i = int((E - self.Emin) * (self.n_bins - 1) / (self.Emax - self.Emin))
+        return min(max(i, 0), self.n_bins - 1)
+
+    def _on_buffer_full(self):
+        filled = self.buffer[:self._next] if self._next < len(self.buffer) else self.buffer
+        self.Emin = float(np.min(filled))
+        self.Emax = float(np.max(filled))
+        self._histogram = np.zeros(self.n_bins)
+        for e in filled:
+            self._histogram[self._get_indx(e)] += 1
+        self.sample_in_buffer = False
+
+    def __call__(self, system_changes):
+        E = self.mc.current_energy_without_vib()
+        if self.sample_in_buffer:
+            self.buffer[self._next] = E
+            self._next += 1
+            if self._next >= len(self.buffer):
+                self._on_buffer_full()
+        else:
+            self._histogram[self._get_indx(E)] += 1
+
+    @property
+    def histogram(self):
+        if self._histogram is None:
+            self._on_buffer_full()
+        return self._histogram

@@ -249,3 +249,61 @@ def test_checkpoint_roundtrip(cuda_device, tmp_path):
     calc.save(str(tmp_path / "ce.json"))
     calc2 = CE.load(str(tmp_path / "ce.json"))
     assert abs(calc2.get_energy() - calc.get_energy()) < 1e-12
+
+
+def test_state_observers_match_oracle(cuda_device):
+    """PairCorrelationObserver / LowestEnergyStructure / SiteOrderParameter / EnergyEvolution /
+    EnergyHistogram see, on their interval boundaries, exactly the state
+    the oracle chain has after the same number of moves."""
+    from cemc_b200.mcmc import (EnergyEvolution, EnergyHistogram, LowestEnergyStructure,
+                                PairCorrelationObserver, SiteOrderParameter)
+    st, eci, symbols, ft, atoms, calc = make_ce(TERNARY, seed=9)
+    cf0 = calc.updater.batch.get_cf()[0]
+    e0 = calc.get_energy()
+    T, steps, iv = 700.0, 3000, 250
+    mc = Montecarlo(atoms, T, seed=77)
+    pair, low = PairCorrelationObserver(calc), LowestEnergyStructure(calc, mc)
+    order, evo, hist = SiteOrderParameter(atoms), EnergyEvolution(mc), EnergyHistogram(mc, buffer_size=8, n_bins=5)
+    for o in (pair, low, order, evo, hist):
+        mc.attach(o, interval=iv)
+    mc.runMC(steps=steps, equil=False)
+
+    # the same run on the oracle, stopped on the same boundaries
+    oc = OracleChain(ft, ft.occupancy(symbols), cf=cf0, kT=T * KB, seed=77, ref=e0)
+    oc.run_canonical(1)
+    oc.run_canonical(1000)
+    bias = oc.e
+    e = oc.eci.copy()
+    e[ft.eci_index["c0"]] -= bias / ft.N
+    oc.set_ecis(e)
+    oc.reset_acc()
+    occ_start = oc.occ.copy()        # runMC resets the observers here (after the bias probe)
+    pair_names = [n for n in ft.eci_names if n.startswith("c2_")]
+    s1 = {n: 0.0 for n in pair_names}
+    energies, changed, best_e, best_occ = [], [], np.inf, None
+    occ_initial = ft.occupancy(symbols)
+    for _ in range(steps // iv):
+        oc.run_canonical(iv)
+        for n in pair_names:
+            s1[n] += oc.cf[ft.eci_index[n]]
+        energies.append(oc.e)
+        changed.append(int(np.count_nonzero(oc.occ != occ_initial)))
+        if oc.e < best_e:
+            best_e, best_occ = oc.e, oc.occ.copy()
+    ncall = steps // iv
+    assert pair.n_entries == ncall
+    avg = pair.get_averages()
+    for n in pair_names:
+        assert avg[n] == s1[n] / ncall
+        assert pair.get_std()[n] >= 0.0
+    assert evo.energies == energies
+    assert low.lowest_energy == best_e
+    assert low.atoms.get_chemical_symbols() == ft.symbols_of(best_occ)
+    assert set(low.lowest_energy_cf.keys()) == set(ft.eci_names)
+    so = order.get_averages()
+    assert so["site_order_average"] == pytest.approx(np.mean(changed), rel=0, abs=1e-12)
+    assert so["site_order_std"] == pytest.approx(np.std(changed), abs=1e-9)
+    h = hist.histogram
+    assert h.sum() == ncall and len(h) == 5
+    assert hist.Emin == min(energies[:8]) and hist.Emax == max(energies[:8])
+    del occ_start
