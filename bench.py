@@ -265,10 +265,11 @@ def gpu_arm(args):
         # per launch: one rank's launch processes R * MOVES_PER_STEP moves
         launch_s = (ms_total * 1e-3) / args.steps
         achieved = B * R * MOVES_PER_STEP / launch_s / 1e9
-        traffic = None
+        traffic, ncu_extra = None, {}
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tj.get("batch_kernel_sgc_dram_bytes_per_launch", None)
+            ncu_extra = {k[4:]: tj[k] for k in tj if k.startswith("ncu_")}
         except (OSError, ValueError):
             pass
         h2d = w.occ.nbytes + w.eci_matrix.nbytes + w.kT.nbytes
@@ -293,7 +294,9 @@ def gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                         "note": "latency-bound gather by design: replicas x 1 CTA, state in smem"},
+                         "note": "latency / issue bound by design: one dependent chain per replica, state "
+                                 "in shared memory; DRAM traffic is the one-time staging",
+                         "ncu": ncu_extra},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
