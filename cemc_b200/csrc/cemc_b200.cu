@@ -86,7 +86,7 @@ struct cemc_handle {
   int tuned_sgc = -1, tuned_can = -1;  // variant chosen by the autotuner
   // tuning across short launches: next variant to time, ms per move of the timed ones
   int xt_next[2] = {0, 0};
-  float xt_ms[2][8];
+  float xt_ms[2][16];
   int cluster = 0;                    // CTAs per chain in the batch kernel (0 = auto, 1, 2)
   int n_sms = 148;
   int batch = 0;                      // moves evaluated speculatively per batch (0 = auto)
@@ -834,7 +834,7 @@ int cemc_set_autotune(cemc_handle *h, int on) {
   return 0;
 }
 
-static const int kNumVariants = 8;   // see launch_variant
+static const int kNumVariants = 9;   // see launch_variant
 
 int cemc_set_variant(cemc_handle *h, int sgc, int canonical) {
   if (!h) return fail("null handle");
@@ -1080,11 +1080,11 @@ static RunArgs run_args(cemc_handle *h, long long n_steps) {
 
 // speculative batch kernel with B moves per CTA and C CTAs per chain; -1 when not applicable
 template <int MODE>
-static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 1) {
+static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 1, int split = 0) {
   if (h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
       2 * h->t.KP > 64) return -1;
   BatchLaunch L{};
-  L.mode = MODE; L.B = B; L.C = C; L.M = M; L.R = h->R; L.max_smem_optin = h->max_smem_optin;
+  L.mode = MODE; L.B = B; L.C = C; L.M = M; L.split = split; L.R = h->R; L.max_smem_optin = h->max_smem_optin;
   L.tree = ((h->order_mode == CEMC_ORDER_TREE) || h->integer_bf) ? 1 : 0;
   L.stream = h->stream; L.t = h->t; L.st = h->st; L.a = a; L.acc_stride = h->acc_stride;
   L.sp = h->spin; L.tb = h->tab;
@@ -1105,7 +1105,8 @@ static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 
 // Kernel variants of one sampler.  All of them produce the same trajectory bit for
 // bit, so the choice is a pure performance knob: 0 spin, 1..4 batch (B,C) =
 // (16,2) (16,1) (8,1) (4,1), 5 one move at a time (mc_kernel, always applicable),
-// 6..7 batch (8,1) / (16,1) with two moves per evaluation warp.
+// 6..7 batch (8,1) / (16,1) with two moves per evaluation warp, 8 batch (16,2) with the two
+// changed sites of a swap split over the two CTAs (canonical only).
 
 template <int MODE>
 static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
@@ -1117,6 +1118,8 @@ static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
     case 4: return launch_batch<MODE>(h, a, 4, 1);
     case 6: return launch_batch<MODE>(h, a, 8, 1, 2);
     case 7: return launch_batch<MODE>(h, a, 16, 1, 2);
+    case 8: return (MODE == MODE_CANONICAL && (2 * h->R <= h->n_sms || h->cluster == 2))
+                       ? launch_batch<MODE>(h, a, 16, 2, 1, 1) : -1;
     default: return launch_mc<MODE>(h, a, 0, h->R);
   }
 }
@@ -1127,7 +1130,7 @@ static bool variant_allowed(const cemc_handle *h, int v) {
   if (h->fp32 && !h->spin_ok && (v == 0 || v == 5)) return false;
   if (v == 0 && h->batch > 0) return false;       // an explicit batch size asks for the batch kernel
   if ((v >= 1 && v <= 4) || v >= 6) {
-    static const int Bs[8] = {0, 16, 16, 8, 4, 0, 8, 16}, Cs[8] = {0, 2, 1, 1, 1, 0, 1, 1};
+    static const int Bs[9] = {0, 16, 16, 8, 4, 0, 8, 16, 16}, Cs[9] = {0, 2, 1, 1, 1, 0, 1, 1, 2};
     if (h->batch > 0 && h->batch != Bs[v]) return false;
     if (h->cluster > 0 && h->cluster != Cs[v]) return false;
   }

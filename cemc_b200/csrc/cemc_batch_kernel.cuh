@@ -65,7 +65,7 @@ struct TabTables {
 enum BatchEval : int { EV_PRODUCT = 0, EV_SPIN = 1, EV_TAB = 2, EV_TAB32 = 3 };
 
 struct BatchSmem {
-  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *Pm, *Ch, *obE, *tab, *pub;
+  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *dEb, *Pm, *Ch, *obE, *tab, *pub;
   uint4 *items;
   int2 *task_sum;
   int4 *ttask;
@@ -73,6 +73,7 @@ struct BatchSmem {
   uint4 *ring;              // [32][2]: proposal; uniform + Metropolis threshold
   int32_t *prop;            // [B][8] decoded proposal
   int32_t *cmask;           // [B] bit k: move b reads a site that move k changes
+  int32_t *cmask2;          // site split: the same for the second changed site (written by CTA 1)
   int32_t *ctl;             // control words
   int32_t *list;
   int8_t *occ;
@@ -112,6 +113,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(sq, double, 2 * BT * 2 * 32);      // double buffered: the bookkeeper reads batch k during batch k+1
   CEMC_TAKE(pub, double, 34);
   CEMC_TAKE(dEa, double, BT);
+  CEMC_TAKE(dEb, double, BT);
   CEMC_TAKE(Pm, double, BT * 33);
   CEMC_TAKE(Ch, double, BT * 32);
   CEMC_TAKE(obE, double, BT);
@@ -121,6 +123,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(ring, uint4, 128 * 2);
   CEMC_TAKE(prop, int32_t, 2 * BT * 8);
   CEMC_TAKE(cmask, int32_t, BT);
+  CEMC_TAKE(cmask2, int32_t, BT);
   o = align_up(o, 8);
   CEMC_TAKE(ctl, int32_t, 8);
   CEMC_TAKE(mbar, uint64_t, 1);
@@ -159,7 +162,11 @@ __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, 
 // M: moves per evaluation warp and batch (one after the other): M = 2 doubles the batch at the
 // same number of warps / registers, so the per-batch costs (two barriers, the decision pass)
 // are shared by twice as many moves; the price is more speculation lost on hot chains.
-template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV, int M = 1>
+// kSplit (canonical, C = 2): SITE SPLIT -- both CTAs of the cluster evaluate the SAME B moves of a
+// batch, CTA q the CF change of changed site q of every swap (update_cf is called once per changed
+// site, ce_updater.cpp:845-852, and the two calls only meet in the sum of their increments).  A
+// swap then costs an evaluation warp what a one-site flip costs, instead of twice that.
+template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV, int M = 1, bool kSplit = false>
 __global__ void __launch_bounds__((B + 1) * 32, (EV != EV_PRODUCT && B <= 8) ? 2 : 1)
 batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTables sp, TabTables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -169,15 +176,19 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   constexpr int TSH = kTab32 ? 2 : 3;                                       // log2(sizeof(TR))
   constexpr bool kCanon = (MODE == MODE_CANONICAL);
   constexpr int NJ = kCanon ? 2 : 1;
-  constexpr int BW = B * C;                      // evaluation warps of the chain
+  static_assert(!kSplit || (C == 2 && MODE == MODE_CANONICAL && M == 1), "site split: swaps on a 2-CTA cluster");
+  constexpr int BW = kSplit ? B : B * C;         // moves evaluated concurrently by the chain's warps
   constexpr int BT = BW * M;                     // moves per batch over the whole cluster
+  constexpr int NJE = kSplit ? 1 : NJ;           // changed sites one warp evaluates
   static_assert(BT <= 32, "one decision lane per move");
   const int crank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int r = blockIdx.x / C;
   const int tid = threadIdx.x, nthr = (B + 1) * 32;
   const int lane = tid & 31, lwarp = tid >> 5;
   const bool is_obs = (lwarp == B);              // the observer warp (works in CTA 0 only)
-  const int warp = is_obs ? 1000 : crank * B + lwarp;   // cluster-wide move index of an evaluation warp
+  const int warp = is_obs ? 1000 : (kSplit ? lwarp : crank * B + lwarp);   // move index of an evaluation warp
+  const int jb = kSplit ? crank : 0;             // first changed site this warp evaluates
+  const bool is_decider = (warp == 0) && (!kSplit || crank == 0);
   auto csync = [&]() { if (C > 1) cg::this_cluster().sync(); else __syncthreads(); };
   const int N = t.N, K = t.K, KP = t.KP, S = t.S, D = t.D, VS = t.VS, n_eci = t.n_eci;
   const int RB = D * KP;
@@ -201,6 +212,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     s0.sq = cl.map_shared_rank(s.sq, 0);
     s0.dEa = cl.map_shared_rank(s.dEa, 0);
     s0.cmask = cl.map_shared_rank(s.cmask, 0);
+    s0.dEb = cl.map_shared_rank(s.dEb, 0);
+    s0.cmask2 = cl.map_shared_rank(s.cmask2, 0);
 #pragma unroll
     for (int q = 0; q < C; q++) {
       occ_of[q] = kStateSmem ? cl.map_shared_rank(s.occ, q) : g_occ;
@@ -570,17 +583,18 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int k = 0; k < b; k++) {
           const int a0 = __shfl_sync(0xffffffffu, sk0, k);
           bool hit = (gsx[0] == a0);
-          if (NJ == 2) hit |= (gsx[1] == a0);
+          if (NJE == 2) hit |= (gsx[1] == a0);
           if (kCanon) {
             const int a1 = __shfl_sync(0xffffffffu, sk1, k);
-            hit |= (gsx[0] == a1) | (gsx[1] == a1);
+            hit |= (gsx[0] == a1);
+            if (NJE == 2) hit |= (gsx[1] == a1);
           }
           if (__any_sync(0xffffffffu, hit)) m |= 1u << k;
         }
       } else {
         bool hit = false;
 #pragma unroll
-        for (int j = 0; j < NJ; j++)
+        for (int j = 0; j < NJE; j++)
           for (int q = 0; q < KP; q++) {
             const int g = __shfl_sync(0xffffffffu, gsx[j], q);
             hit |= (g == sk0) | (kCanon & (g == sk1));
@@ -619,7 +633,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
             site[mi][0] = s.list[slot0]; site[mi][1] = s.list[slot1];
             oldv[mi][0] = newv[mi][1]; oldv[mi][1] = newv[mi][0];
           }
-          if (lane == 0) {                         // the deciding warp commits from this record
+          if (lane == 0 && (!kSplit || crank == 0)) {     // the deciding warp commits from this record
             int32_t *pp = s0.prop + par * (BT * 8) + b * 8;
             *reinterpret_cast<int4 *>(pp) = make_int4(site[mi][0], site[mi][1], newv[mi][0], newv[mi][1]);
             *reinterpret_cast<int4 *>(pp + 4) = make_int4(oldv[mi][0], oldv[mi][1], slot0, slot1);
@@ -628,16 +642,17 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
         for (int mi = 0; mi < M; mi++) {
 #pragma unroll
-          for (int j = 0; j < 2; j++) {
-            gs[mi][j] = -1; qv[mi][j] = 0.0;
-            if (j < NJ) {
+          for (int je = 0; je < 2; je++) {
+            gs[mi][je] = -1; qv[mi][je] = 0.0;
+            if (je < NJE) {
+              const int j = jb + je;
               uint32_t v = 0;
               if (lane < K) {
                 const int nbs = __ldg(&t.trans[(size_t)site[mi][j] * K + lane]);      // :264
-                gs[mi][j] = nbs;
+                gs[mi][je] = nbs;
                 v = (uint32_t)s.occ[nbs];
                 if (j == 1 && nbs == site[mi][0]) v = (uint32_t)newv[mi][0];   // change 1 sees change 0 applied (:845-852)
-              } else if (lane == K) gs[mi][j] = site[mi][j];
+              } else if (lane == K) gs[mi][je] = site[mi][j];
               const uint32_t ob = __ballot_sync(0xffffffffu, (v & 1u) != 0u);
               int cnt = 0;
 #pragma unroll
@@ -649,7 +664,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
               }
               const int dsig = 2 * sp.b0 * (oldv[mi][j] - newv[mi][j]);      // sigma_new - sigma_old
               const int num = s_coef * dsig * (s_msub - 2 * cnt);
-              qv[mi][j] = exact_div((double)num, f_den, f_rden);             // :402
+              qv[mi][je] = exact_div((double)num, f_den, f_rden);            // :402
             }
           }
         }
@@ -657,8 +672,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int mi = 0; mi < M; mi++) {
           const int b = warp + mi * BW;
           double *sqb = s0.sq + par * (BT * 64) + b * 64;   // this move's per-ECI quotients [2][32]
-          sqb[lane] = qv[mi][0];
-          sqb[32 + lane] = qv[mi][1];
+          if (!kSplit) { sqb[lane] = qv[mi][0]; sqb[32 + lane] = qv[mi][1]; }
+          else sqb[jb * 32 + lane] = qv[mi][0];
         }
         double de[M];
 #pragma unroll
@@ -669,7 +684,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           for (int mi = 0; mi < M; mi++) de[mi] += __shfl_xor_sync(0xffffffffu, de[mi], o);
 #pragma unroll
         for (int mi = 0; mi < M; mi++)
-          if (lane == 0) s0.dEa[warp + mi * BW] = de[mi] * dN;
+          if (lane == 0) (kSplit && crank ? s0.dEb : s0.dEa)[warp + mi * BW] = de[mi] * dN;
         CEMC_TICK(12);
         int sk0, sk1;
         changed_sites(warp + (M - 1) * BW, sk0, sk1);
@@ -677,7 +692,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int mi = 0; mi < M; mi++) {
           const int b = warp + mi * BW;
           const uint32_t m = conflict_mask(b, gs[mi], sk0, sk1);
-          if (lane == 0) s0.cmask[b] = (int32_t)m;
+          if (lane == 0) (kSplit && crank ? s0.cmask2 : s0.cmask)[b] = (int32_t)m;
         }
         CEMC_TICK(13);
       }
@@ -709,7 +724,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       }
       double *Vb = s.V + lwarp * NJ * VS;
       double *sqb = s0.sq + par * (BT * 64) + b * 64;   // this move's per-ECI quotients [2][32]
-      if (lane == 0) {                           // the deciding warp commits from this record
+      if (lane == 0 && (!kSplit || crank == 0)) {    // the deciding warp commits from this record
         int32_t *pp = s0.prop + par * (BT * 8) + b * 8;
         *reinterpret_cast<int4 *>(pp) = make_int4(site0, site1, new0, new1);
         *reinterpret_cast<int4 *>(pp + 4) = make_int4(old0, old1, slot0, slot1);
@@ -722,14 +737,15 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         const int olds[2] = {old0, old1}, news[2] = {new0, new1};
         uint32_t *cw = s.codes + lwarp * NJ * n_sub;
 #pragma unroll
-        for (int j = 0; j < NJ; j++) {
+        for (int je = 0; je < NJE; je++) {
+          const int j = jb + je;
           int v = 0;
           if (lane < K) {
             const int nbs = __ldg(&t.trans[(size_t)sites[j] * K + lane]);        // :264
-            gsx[j] = nbs;
+            gsx[je] = nbs;
             v = s.occ[nbs];
             if (j && nbs == site0) v = new0;      // change 1 sees change 0 applied (:845-852)
-          } else if (lane == K) gsx[j] = sites[j];
+          } else if (lane == K) gsx[je] = sites[j];
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             if (q < t_rounds) {
@@ -742,7 +758,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
               const uint32_t cO = (rest + (uint32_t)olds[j] * wr) * nd, cN = (rest + (uint32_t)news[j] * wr) * nd;
               uint32_t word = (cO << TSH) | (cN << (16 + TSH));
               if (tdy[q] == 0u) { const uint32_t z = (tdx[q] & 0xffffu) >> (3 - TSH); word = z | (z << 16); }   // padding: the table's zero row
-              if (q * 32 + lane < n_sub) cw[j * n_sub + q * 32 + lane] = word;
+              if (q * 32 + lane < n_sub) cw[je * n_sub + q * 32 + lane] = word;
             }
           }
         }
@@ -757,20 +773,20 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           const uint32_t *cp = cw + tt.y;
           auto TV = [&](uint32_t off) { return *reinterpret_cast<const TR *>(tbl + off); };
           if (!kTree) {
-            TR spO[NJ], spN[NJ];
+            TR spO[NJE], spN[NJE];
 #pragma unroll
-            for (int j = 0; j < NJ; j++) { spO[j] = (TR)0; spN[j] = (TR)0; }
+            for (int j = 0; j < NJE; j++) { spO[j] = (TR)0; spN[j] = (TR)0; }
 #pragma unroll 1
             for (int m = 0; m < tt.z; m += 8) {         // M is padded to a multiple of 8 with zero entries
-              uint4 w[NJ][2];
+              uint4 w[NJE][2];
 #pragma unroll
-              for (int j = 0; j < NJ; j++) {
+              for (int j = 0; j < NJE; j++) {
                 w[j][0] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m);
                 w[j][1] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m + 4);
               }
-              TR vo[NJ][8], vn[NJ][8];
+              TR vo[NJE][8], vn[NJE][8];
 #pragma unroll
-              for (int j = 0; j < NJ; j++)
+              for (int j = 0; j < NJE; j++)
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                   vo[j][4 * h + 0] = TV(w[j][h].x & 0xffffu); vn[j][4 * h + 0] = TV(w[j][h].x >> 16);
@@ -781,13 +797,13 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
               for (int x = 0; x < 8; x++)
 #pragma unroll
-                for (int j = 0; j < NJ; j++) { spO[j] = add_rn(spO[j], vo[j][x]); spN[j] = add_rn(spN[j], vn[j][x]); }
+                for (int j = 0; j < NJE; j++) { spO[j] = add_rn(spO[j], vo[j][x]); spN[j] = add_rn(spN[j], vn[j][x]); }
             }
 #pragma unroll
-            for (int j = 0; j < NJ; j++) db[j * max_tasks + tk] = (double)sub_rn(spN[j], spO[j]);     // :397
+            for (int j = 0; j < NJE; j++) db[j * max_tasks + tk] = (double)sub_rn(spN[j], spO[j]);     // :397
           } else {
 #pragma unroll
-            for (int j = 0; j < NJ; j++) {
+            for (int j = 0; j < NJE; j++) {
               TR o[4] = {(TR)0, (TR)0, (TR)0, (TR)0}, n[4] = {(TR)0, (TR)0, (TR)0, (TR)0};
 #pragma unroll 1
               for (int m = 0; m < tt.z; m += 4) {
@@ -804,28 +820,35 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         }
         __syncwarp();
         CEMC_TICK(7);
-        // per-ECI quotients (:393-402): lane i = ECI i, both changed sites
+        // per-ECI quotients (:393-402): lane i = ECI i, this warp's changed site(s)
         {
-          double num0 = 0.0, num1 = 0.0;
+          double num[NJE];
+#pragma unroll
+          for (int je = 0; je < NJE; je++) num[je] = 0.0;
           if (f_kind == 1) {                                  // :366-371
-            num0 = __dsub_rn(s.bf[f_d * S + new0], s.bf[f_d * S + old0]);
-            if (kCanon) num1 = __dsub_rn(s.bf[f_d * S + new1], s.bf[f_d * S + old1]);
+#pragma unroll
+            for (int je = 0; je < NJE; je++)
+              num[je] = __dsub_rn(s.bf[f_d * S + news[jb + je]], s.bf[f_d * S + olds[jb + je]]);
           } else if (f_kind == 2) {
             for (int q = 0; q < f_nd; q++) {                  // :397
-              num0 = __dadd_rn(num0, db[f_t0 + q]);
-              if (kCanon) num1 = __dadd_rn(num1, db[max_tasks + f_t0 + q]);
+#pragma unroll
+              for (int je = 0; je < NJE; je++) num[je] = __dadd_rn(num[je], db[je * max_tasks + f_t0 + q]);
             }
-            num0 = __dmul_rn(num0, f_scale);                  // :400
-            num1 = __dmul_rn(num1, f_scale);
+#pragma unroll
+            for (int je = 0; je < NJE; je++) num[je] = __dmul_rn(num[je], f_scale);      // :400
           }
-          const double qa = exact_div(num0, f_den, f_rden);                     // :402
-          const double qb = kCanon ? exact_div(num1, f_den, f_rden) : 0.0;
-          sqb[lane] = qa;
-          sqb[32 + lane] = qb;
-          double de = f_kind > 0 ? eci_reg * (qa + qb) : 0.0;   // screen only
+          double qsum = 0.0;
+#pragma unroll
+          for (int je = 0; je < NJE; je++) {
+            const double qj = exact_div(num[je], f_den, f_rden);                 // :402
+            sqb[(jb + je) * 32 + lane] = qj;
+            qsum += qj;
+          }
+          if (!kCanon) sqb[32 + lane] = 0.0;
+          double de = f_kind > 0 ? eci_reg * qsum : 0.0;      // screen only
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
-          if (lane == 0) s0.dEa[b] = de * dN;
+          if (lane == 0) (kSplit && crank ? s0.dEb : s0.dEa)[b] = de * dN;
         }
       } else {
       // P1: gather
@@ -963,7 +986,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         int sk0, sk1;
         changed_sites(b, sk0, sk1);
         const uint32_t m = conflict_mask(b, gsx, sk0, sk1);
-        if (lane == 0) s0.cmask[b] = (int32_t)m;
+        if (lane == 0) (kSplit && crank ? s0.cmask2 : s0.cmask)[b] = (int32_t)m;
       }
       CEMC_TICK(13);
       if (M > 1) __syncwarp();                  // the warp's scratch is reused by its next move
@@ -985,17 +1008,17 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     // dot, observer sums) of the decided moves follows, lane-parallel over moves
     // where the reference's operation order allows.  A move whose screen is
     // inconclusive (|dE - L| inside the band) is decided with the exact expression.
-    if (warp == 0) {
+    if (is_decider) {
       const uint4 rec1 = s.ring[(int)((sdone + (lane < nb ? lane : 0)) & 127) * 2 + 1];
       const double u_l = __hiloint2double((int)rec1.y, (int)rec1.x);
       const double L_l = __hiloint2double((int)rec1.w, (int)rec1.z);
-      const double dE_l = s.dEa[lane < nb ? lane : 0];
+      const double dE_l = kSplit ? s.dEa[lane < nb ? lane : 0] + s.dEb[lane < nb ? lane : 0] : s.dEa[lane < nb ? lane : 0];
       const double band = a.screen_slack * (4e-7 * (kT + fabs(L_l)) + 1e-9 * fabs(dE_l)) + etol;
       const bool t_acc = lane < nb && (dE_l < L_l - band);
       const bool t_bdr = lane < nb && !t_acc && !(dE_l > L_l + band);
       const uint32_t tmask = __ballot_sync(0xffffffffu, t_acc);
       const uint32_t bmask = __ballot_sync(0xffffffffu, t_bdr);
-      const uint32_t cm_l = lane < nb ? (uint32_t)s.cmask[lane] : 0u;
+      const uint32_t cm_l = lane < nb ? (uint32_t)(kSplit ? (s.cmask[lane] | s.cmask2[lane]) : s.cmask[lane]) : 0u;
       uint32_t tm = tmask;
       if (bmask & 1u) {
         // move 0 is inconclusive: exact path (rare) -- ordered dot (named_array.cpp:27-31)
@@ -1082,7 +1105,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     if (lane < n_eci) st.cf[(size_t)r * n_eci + lane] = cf_reg;
     if (lane == 0) st.e_cur[r] = e_cur;
   }
-  if (warp == 0) {
+  if (is_decider) {
     if (lane == 0) {
       st.step[r] = step0 + (unsigned long long)a.n_steps;
       st.accepted[r] += n_acc;

@@ -12,6 +12,7 @@ struct BatchLaunch {
   int mode;               // MODE_SGC | MODE_CANONICAL
   int tree;               // TREE summation order
   int B, C, M;            // warps per CTA, CTAs per chain, moves per evaluation warp
+  int split;              // site split: the two CTAs of a cluster evaluate the two sites of the same swaps
   int R;                  // replicas
   int max_smem_optin;
   cudaStream_t stream;
@@ -29,9 +30,9 @@ int batch_launch_spin(const BatchLaunch &L);
 int batch_launch_tab(const BatchLaunch &L);
 int batch_launch_tab32(const BatchLaunch &L);
 
-template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M>
+template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M, bool kSplit = false>
 static int batch_launch_kc(const BatchLaunch &L, size_t sm) {
-  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV, M>;
+  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV, M, kSplit>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return 1000 + (int)e;
   cudaLaunchConfig_t cfg{};
@@ -65,8 +66,22 @@ static int batch_launch_b(const BatchLaunch &L) {
   }
 }
 
+// site split (canonical, cluster of 2, shared-memory state, spin / table evaluation)
+template <int MODE, bool kTree, int B, int EV>
+static int batch_launch_split(const BatchLaunch &L) {
+  if constexpr (MODE == MODE_CANONICAL && EV != EV_PRODUCT) {
+    const TabTables *tb = (EV == EV_TAB || EV == EV_TAB32) ? &L.tb : nullptr;
+    const size_t sm = batch_smem_layout<B, B>(nullptr, nullptr, L.t, true, true, tb, EV == EV_TAB32);
+    if (sm > (size_t)L.max_smem_optin) return -1;
+    return batch_launch_kc<MODE, kTree, B, true, 2, EV, 1, true>(L, sm);
+  } else {
+    return -1;
+  }
+}
+
 template <int MODE, bool kTree, int EV>
 static int batch_launch_bc(const BatchLaunch &L) {
+  if (L.split) return (L.B == 16 && L.C == 2) ? batch_launch_split<MODE, kTree, 15, EV>(L) : -1;
   // L.B counts the warps of a CTA: B - 1 evaluation warps (moves per batch) + the observer
   // warp; power-of-two CTAs get the full register budget (512 threads x 128 registers)
   if (L.M == 2) {

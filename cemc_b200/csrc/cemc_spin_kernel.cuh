@@ -251,6 +251,7 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
       }
       e_new = __dmul_rn(e_new, dN);                                // ce_updater.cpp:241
       const bool accept = metropolis(e_new, e_cur, u, kT, rkT);
+      __syncwarp();               // every lane's reads of this move precede lane 0's commit
       if (accept) {
         cf_reg = c;
         e_cur = e_new;

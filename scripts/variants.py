@@ -14,7 +14,7 @@ for which in names:
         gpu.set_table_eval(int(opts["tab"]) != 0)
     run = gpu.run_sgc if w.mode == "sgc" else gpu.run_canonical
     res = []
-    for v in range(8):
+    for v in range(9):
         gpu.set_variant(v, v)
         run(2000); gpu.synchronize()
         best = 1e30

@@ -650,13 +650,15 @@ def test_table_evaluation_quaternary(cuda_device, batch, cluster, order):
             np.testing.assert_allclose(gpu.get_cf(), np.stack([c.cf for c in chains]), rtol=1e-10, atol=1e-13)
 
 
-@pytest.mark.parametrize("variant", [6, 7])
+@pytest.mark.parametrize("variant", [6, 7, 8])
 @pytest.mark.parametrize("system", ["binary", "ternary_tab", "ternary_product"])
 @pytest.mark.parametrize("mode", ["sgc", "canonical"])
 def test_two_moves_per_warp_variants(cuda_device, variant, system, mode):
     """Kernel variants 6 / 7: every evaluation warp of the batch kernel takes two moves of
-    a batch (14 / 30 moves per batch).  Same trajectory, trace, observer sums as the oracle
-    for the three evaluation schemes, also on the 27-site cell (constant collisions)."""
+    a batch (14 / 30 moves per batch); variant 8: site split -- the two CTAs of a cluster
+    evaluate the two changed sites of the same swaps (canonical only; SGC falls back).
+    Same trajectory, trace, observer sums as the oracle for the three evaluation schemes,
+    also on the 27-site cell (constant collisions)."""
     base = BINARY if system == "binary" else TERNARY
     for case, R in ((base, 3), (dict(base, L=3), 2)):
         st, eci, symbols, ft = build(**case)
