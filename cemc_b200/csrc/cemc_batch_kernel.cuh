@@ -77,7 +77,7 @@ struct BatchSmem {
   int32_t *ctl;             // control words
   int32_t *list;
   int8_t *occ;
-  uint64_t *mbar;           // mbarrier of the TMA staging copies
+  uint64_t *mbar;           // [0] TMA staging copies; async cluster protocol: [1] evaluations complete (CTA 0), [2] decision arrived (CTA 1)
 };
 
 // B = moves evaluated by this CTA, BT = moves per batch over the whole cluster
@@ -126,7 +126,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(cmask2, int32_t, BT);
   o = align_up(o, 8);
   CEMC_TAKE(ctl, int32_t, 8);
-  CEMC_TAKE(mbar, uint64_t, 1);
+  CEMC_TAKE(mbar, uint64_t, 4);
   if (state_in_smem) {
     if (canonical) CEMC_TAKE16(list, int32_t, t.N);
     CEMC_TAKE16(occ, int8_t, t.N);
@@ -224,6 +224,44 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   } else {
     occ_of[0] = s.occ; list_of[0] = s.list; prop_of[0] = s.prop; ctl_of[0] = s.ctl;
   }
+  // ---- async cluster protocol (C = 2, state in shared memory): CTA 1 sends its evaluation
+  // results to CTA 0 with st.async (the bytes complete CTA 0's mbarrier E), CTA 0's warp 0 waits
+  // for (local arrivals, remote bytes), decides, commits its own copy of the state and sends the
+  // 8-byte decision (moves decided, accept mask) to CTA 1 (completes CTA 1's mbarrier D); CTA 1
+  // applies the commits to its own copy from its own proposal ring.  No barrier.cluster (with
+  // its MEMBAR.ALL.GPU / L1 invalidation) inside the batch loop.
+  constexpr bool kAsync = (C == 2) && kStateSmem;
+  const bool remote = kAsync && crank == 1;
+  constexpr uint32_t kTxPerMove = kSplit ? (256u + 8u + 4u) : (32u + 512u + 8u + 4u);
+  uint32_t rE = 0, r_sq = 0, r_dE = 0, r_cm = 0, r_prop = 0, rD = 0, r_ctl = 0, phE = 0, phD = 0;
+  if (kAsync) {
+    rE = mapa_u32(smem_u32(s.mbar + 1), 0);
+    r_sq = mapa_u32(smem_u32(s.sq), 0);
+    r_dE = mapa_u32(smem_u32(kSplit ? s.dEb : s.dEa), 0);
+    r_cm = mapa_u32(smem_u32(kSplit ? s.cmask2 : s.cmask), 0);
+    r_prop = mapa_u32(smem_u32(s.prop), 0);
+    rD = mapa_u32(smem_u32(s.mbar + 2), 1);
+    r_ctl = mapa_u32(smem_u32(s.ctl), 1);
+  }
+  // results of one evaluated move -> CTA 0 (b = move of the batch, pp = batch parity)
+  auto put_sq = [&](int pp, int b, int half, double q) {          // per-ECI quotient, lane = ECI
+    const int idx = pp * (BT * 64) + b * 64 + half * 32 + lane;
+    if (remote) st_async_f64(r_sq + (uint32_t)idx * 8u, q, rE); else s0.sq[idx] = q;
+  };
+  auto put_de = [&](int b, double de) {                            // lane 0
+    if (remote) st_async_f64(r_dE + (uint32_t)b * 8u, de, rE);
+    else (kSplit && crank ? s0.dEb : s0.dEa)[b] = de;
+  };
+  auto put_cm = [&](int b, uint32_t m) {                           // lane 0
+    if (remote) st_async_b32(r_cm + (uint32_t)b * 4u, m, rE);
+    else (kSplit && crank ? s0.cmask2 : s0.cmask)[b] = (int32_t)m;
+  };
+  auto put_prop = [&](int pp, int b, int4 p0, int4 p1) {           // lane 0; site split: CTA 0 writes its own
+    if (kSplit && crank) return;
+    const int idx = pp * (BT * 8) + b * 8;
+    if (remote) { st_async_v4b32(r_prop + (uint32_t)idx * 4u, p0, rE); st_async_v4b32(r_prop + (uint32_t)idx * 4u + 16u, p1, rE); }
+    else { *reinterpret_cast<int4 *>(s0.prop + idx) = p0; *reinterpret_cast<int4 *>(s0.prop + idx + 4) = p1; }
+  };
 
   // ---- stage: the TMA engine copies the read-only tables -- and the replica's occupations /
   // site lists when their global addresses are 16-byte aligned -- into shared memory
@@ -231,7 +269,10 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // global image (V) or is misaligned
   const bool occ_tma = kStateSmem && tma_aligned(g_occ, (size_t)N);
   const bool list_tma = kStateSmem && kCanon && tma_aligned(g_list, (size_t)N * 4);
-  if (tid == 0) mbar_init(s.mbar, 1);
+  if (tid == 0) {
+    mbar_init(s.mbar, 1);
+    if (kAsync) { mbar_init(s.mbar + 1, B + 1); mbar_init(s.mbar + 2, 1); }   // E: CTA 0's warps; D: CTA 1's poster
+  }
   __syncthreads();
   if (tid == 0) {
     const uint32_t b_tab = kTab ? (uint32_t)align_up((size_t)tb.n_tab * sizeof(TR), 16) : 0u;
@@ -542,6 +583,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 
   while (sdone < a.n_steps) {
     const int nb = (int)((a.n_steps - sdone) < BT ? (a.n_steps - sdone) : BT);
+    if (remote && tid == 0) mbar_expect_tx(s.mbar + 2, 8u);          // this batch's decision record
     CEMC_TICK(0);
 
 #ifdef CEMC_PHASE_TIMING
@@ -633,11 +675,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
             site[mi][0] = s.list[slot0]; site[mi][1] = s.list[slot1];
             oldv[mi][0] = newv[mi][1]; oldv[mi][1] = newv[mi][0];
           }
-          if (lane == 0 && (!kSplit || crank == 0)) {     // the deciding warp commits from this record
-            int32_t *pp = s0.prop + par * (BT * 8) + b * 8;
-            *reinterpret_cast<int4 *>(pp) = make_int4(site[mi][0], site[mi][1], newv[mi][0], newv[mi][1]);
-            *reinterpret_cast<int4 *>(pp + 4) = make_int4(oldv[mi][0], oldv[mi][1], slot0, slot1);
-          }
+          if (lane == 0)                           // the deciding warp commits from this record
+            put_prop(par, b, make_int4(site[mi][0], site[mi][1], newv[mi][0], newv[mi][1]),
+                     make_int4(oldv[mi][0], oldv[mi][1], slot0, slot1));
         }
 #pragma unroll
         for (int mi = 0; mi < M; mi++) {
@@ -671,9 +711,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
         for (int mi = 0; mi < M; mi++) {
           const int b = warp + mi * BW;
-          double *sqb = s0.sq + par * (BT * 64) + b * 64;   // this move's per-ECI quotients [2][32]
-          if (!kSplit) { sqb[lane] = qv[mi][0]; sqb[32 + lane] = qv[mi][1]; }
-          else sqb[jb * 32 + lane] = qv[mi][0];
+          // this move's per-ECI quotients [2][32]
+          if (!kSplit) { put_sq(par, b, 0, qv[mi][0]); put_sq(par, b, 1, qv[mi][1]); }
+          else put_sq(par, b, jb, qv[mi][0]);
         }
         double de[M];
 #pragma unroll
@@ -684,7 +724,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           for (int mi = 0; mi < M; mi++) de[mi] += __shfl_xor_sync(0xffffffffu, de[mi], o);
 #pragma unroll
         for (int mi = 0; mi < M; mi++)
-          if (lane == 0) (kSplit && crank ? s0.dEb : s0.dEa)[warp + mi * BW] = de[mi] * dN;
+          if (lane == 0) put_de(warp + mi * BW, de[mi] * dN);
         CEMC_TICK(12);
         int sk0, sk1;
         changed_sites(warp + (M - 1) * BW, sk0, sk1);
@@ -692,7 +732,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int mi = 0; mi < M; mi++) {
           const int b = warp + mi * BW;
           const uint32_t m = conflict_mask(b, gs[mi], sk0, sk1);
-          if (lane == 0) (kSplit && crank ? s0.cmask2 : s0.cmask)[b] = (int32_t)m;
+          if (lane == 0) put_cm(b, m);
         }
         CEMC_TICK(13);
       }
@@ -700,7 +740,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll 1
     for (int mi = 0; mi < M; mi++) {
       const int b = warp + mi * BW;             // warp w evaluates moves w, w + BW, ...
-      if (b >= nb) break;
+      if (is_obs || (b >= nb && !kAsync)) break;   // async protocol: fixed byte count per batch, evaluate anyway
       int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check); host: NJ*KP <= 64
       const uint4 rec0 = s.ring[(int)((sdone + b) & 127) * 2];
       int site0, site1 = -1, new0, new1 = 0, old0, old1 = 0, slot0 = -1, slot1 = -1;
@@ -723,12 +763,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         old0 = new1; old1 = new0;
       }
       double *Vb = s.V + lwarp * NJ * VS;
-      double *sqb = s0.sq + par * (BT * 64) + b * 64;   // this move's per-ECI quotients [2][32]
-      if (lane == 0 && (!kSplit || crank == 0)) {    // the deciding warp commits from this record
-        int32_t *pp = s0.prop + par * (BT * 8) + b * 8;
-        *reinterpret_cast<int4 *>(pp) = make_int4(site0, site1, new0, new1);
-        *reinterpret_cast<int4 *>(pp + 4) = make_int4(old0, old1, slot0, slot1);
-      }
+      if (lane == 0)                             // the deciding warp commits from this record
+        put_prop(par, b, make_int4(site0, site1, new0, new1), make_int4(old0, old1, slot0, slot1));
       if (kTab) {
         CEMC_TICK(5);
         // ---- table evaluation: neighbour occupations stay in registers (lane c = column c),
@@ -841,14 +877,14 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
           for (int je = 0; je < NJE; je++) {
             const double qj = exact_div(num[je], f_den, f_rden);                 // :402
-            sqb[(jb + je) * 32 + lane] = qj;
+            put_sq(par, b, jb + je, qj);
             qsum += qj;
           }
-          if (!kCanon) sqb[32 + lane] = 0.0;
+          if (!kCanon) put_sq(par, b, 1, 0.0);
           double de = f_kind > 0 ? eci_reg * qsum : 0.0;      // screen only
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
-          if (lane == 0) (kSplit && crank ? s0.dEb : s0.dEa)[b] = de * dN;
+          if (lane == 0) put_de(b, de * dN);
         }
       } else {
       // P1: gather
@@ -971,14 +1007,14 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         }
         const double qa = exact_div(num0, f_den, f_rden);                     // :402
         const double qb = kCanon ? exact_div(num1, f_den, f_rden) : 0.0;
-        sqb[lane] = qa;
-        sqb[32 + lane] = qb;
+        put_sq(par, b, 0, qa);
+        put_sq(par, b, 1, qb);
         // state-independent energy change of this move, N * sum_i eci_i (q0_i + q1_i):
         // only used to SCREEN the Metropolis test (any summation order will do)
         double de = f_kind > 0 ? eci_reg * (qa + qb) : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
-        if (lane == 0) s0.dEa[b] = de * dN;
+        if (lane == 0) put_de(b, de * dN);
       }
       }
       CEMC_TICK(12);
@@ -986,13 +1022,22 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         int sk0, sk1;
         changed_sites(b, sk0, sk1);
         const uint32_t m = conflict_mask(b, gsx, sk0, sk1);
-        if (lane == 0) (kSplit && crank ? s0.cmask2 : s0.cmask)[b] = (int32_t)m;
+        if (lane == 0) put_cm(b, m);
       }
       CEMC_TICK(13);
       if (M > 1) __syncwarp();                  // the warp's scratch is reused by its next move
     }
     }
-    csync();
+    if (kAsync) {
+      // CTA 0: every warp arrives on E (the deciding warp also posts CTA 1's byte count) and
+      // only the deciding warp waits; CTA 1 has sent its results and goes on to wait for D
+      __syncwarp();
+      if (crank == 0) {
+        if (lane == 0) { if (is_decider) mbar_expect_tx(s.mbar + 1, (uint32_t)B * kTxPerMove); else mbar_arrive(s.mbar + 1); }
+        if (is_decider) mbar_wait(s.mbar + 1, phE);
+        phE ^= 1u;
+      }
+    } else csync();
 #ifdef CEMC_PHASE_TIMING
     if (*reinterpret_cast<volatile int32_t *>(s.ctl + 7) == 0x7fffffff) tlast = 0;   // wait for the barrier release
     if (is_obs && crank == 0 && lane == 0) { tph[14] += (unsigned long long)(tob1 - tob0); tph[15] += (unsigned long long)(clock64() - tob1); }
@@ -1055,7 +1100,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           const int4 pa = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8);
           const int4 pb = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8 + 4);
 #pragma unroll
-          for (int q = 0; q < (kStateSmem ? C : 1); q++) {       // every CTA's copy of the state
+          for (int q = 0; q < ((kStateSmem && !kAsync) ? C : 1); q++) {       // every CTA's copy of the state (async: CTA 1 commits its own)
             occ_of[q][pa.x] = (int8_t)pa.z;
             if (kCanon) {                      // swap_move_index_tracker.py:39-59
               occ_of[q][pa.y] = (int8_t)pa.w;
@@ -1066,7 +1111,12 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         }
       }
       if (!kStateSmem) { if (C > 1) __threadfence(); else __threadfence_block(); }
-      if (lane < C) {
+      if (kAsync) {
+        if (lane == 0) {
+          *reinterpret_cast<int2 *>(s.ctl) = make_int2(ndone, (int)accmask);
+          st_async_v2b32(r_ctl, (uint32_t)ndone, accmask, rD);      // completes CTA 1's mbarrier D
+        }
+      } else if (lane < C) {
         int32_t *cp = ctl_of[0];
 #pragma unroll
         for (int q = 1; q < C; q++) if (lane == q) cp = ctl_of[q];
@@ -1077,7 +1127,40 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       if (tid == 0) { tph[8] += 1; tph[9] += ndone; tph[10] += __popc(accmask); tph[11] += (stops ? 1 : 0); }
 #endif
     }
-    csync();
+    if (kAsync) {
+      if (crank == 1) {
+        mbar_wait(s.mbar + 2, phD);                 // the decision record has landed in s.ctl
+        phD ^= 1u;
+        if (lwarp == 0) {
+          // CTA 1 applies the accepted moves to its own copy of the state, re-deriving each
+          // move from its own proposal ring (accepted moves of a batch touch disjoint sites)
+          const int2 ct = *reinterpret_cast<const int2 *>(s.ctl);
+          if (lane < ct.x && ((ct.y >> lane) & 1)) {
+            const uint4 rk = s.ring[(int)((sdone + lane) & 127) * 2];
+            if (!kCanon) {
+              const int site = t.active ? t.active[rk.x] : (int)rk.x;
+              const int old = s.occ[site];
+              int nw;
+              if (t.allowed_identity) { nw = (int)__umulhi(rk.y, (uint32_t)(S - 1)); nw += (nw >= old); }
+              else {
+                const int p = t.allowed_pos[old];
+                int rr;
+                if (p >= 0) { rr = (int)__umulhi(rk.y, (uint32_t)(n_allowed - 1)); rr += (rr >= p); }
+                else rr = (int)__umulhi(rk.y, (uint32_t)n_allowed);
+                nw = t.allowed[rr];
+              }
+              s.occ[site] = (int8_t)nw;
+            } else {                                  // swap_move_index_tracker.py:39-59
+              const int sl0 = (int)rk.x, sl1 = (int)rk.y;
+              const int st0 = s.list[sl0], st1 = s.list[sl1];
+              s.occ[st0] = (int8_t)rk.z; s.occ[st1] = (int8_t)rk.w;
+              s.list[sl0] = st1; s.list[sl1] = st0;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    } else csync();
 #ifdef CEMC_PHASE_TIMING
     if (*reinterpret_cast<volatile int32_t *>(s.ctl + 7) == 0x7fffffff) tlast = 0;
 #endif

@@ -195,6 +195,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!ok);
 }
+// ---- distributed shared memory without fences: st.async + mbarrier transaction bytes --------
+// A remote store that signals the destination CTA's mbarrier with the bytes it wrote: the
+// consumer waits for (arrivals, bytes) of the phase and then reads plain shared memory.  No
+// barrier.cluster, no MEMBAR, no L1 invalidation on the critical path.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t dst, double v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(dst), "l"(__double_as_longlong(v)), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t dst, uint32_t v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(dst), "r"(v), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_async_v2b32(uint32_t dst, uint32_t a, uint32_t b, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+               ::"r"(dst), "r"(a), "r"(b), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4b32(uint32_t dst, int4 v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ bool tma_aligned(const void *p, size_t bytes) {
   return ((reinterpret_cast<uintptr_t>(p) | bytes) & 15u) == 0 && bytes > 0;
 }
