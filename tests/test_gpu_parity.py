@@ -765,3 +765,39 @@ def test_fp32_variant(cuda_device, variant):
     gpu, chains = make_pair(ft, [symbols], [0.05], seed=5)
     with pytest.raises(CemcError):
         gpu.set_precision(32)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 8])
+def test_full_size_cluster_stress(cuda_device, variant):
+    """BASELINE config 3 size (fcc 20^3 ternary, 8000 sites), 12 replicas over the whole
+    temperature range, 30 000 SGC + 30 000 canonical moves: the CTA-cluster kernels with the
+    async DSMEM protocol (variant 1), the site-split variant (8) and the single-CTA batch
+    kernel (2) must give the oracle's occupations / CFs / energies / observer sums bit for bit
+    (thousands of batches per chain, every barrier phase and ring wrap exercised)."""
+    from cemc_b200 import workloads as wl
+    R, n = 12, 30000
+    w = wl.c3s_almgsi_sgc(R=R)
+    ft = w.tables
+    kT = np.linspace(w.kT.min(), w.kT.max() * 1.5, R)
+    chains = [OracleChain(ft, w.occ[r], kT=kT[r], seed=4242, replica=r, eci=w.eci_matrix[r])
+              for r in range(R)]
+    gpu = BatchedCEUpdater(ft, R)
+    gpu.set_occupancy(w.occ)
+    gpu.set_cf(np.stack([c.cf for c in chains]))
+    gpu.set_ecis(w.eci_matrix)
+    gpu.set_kT(kT)
+    gpu.seed(4242)
+    gpu.set_variant(variant, variant)
+    gpu.reset_accumulators()
+    gpu.run_sgc(n)
+    gpu.run_canonical(n)
+    gpu.synchronize()
+    for c in chains:
+        c.run_sgc(n)
+        c.run_canonical(n)
+    assert_state_equal(gpu, chains)
+    accs = gpu.get_accumulators()
+    steps, n_acc = gpu.get_counters()
+    for r, c in enumerate(chains):
+        assert np.array_equal(accs[r], c.acc)
+        assert steps[r] == 2 * n and n_acc[r] == c.n_accepted.value
