@@ -73,6 +73,10 @@ struct cemc_handle {
   int32_t *pt_scratch = nullptr; int pt_scratch_n = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // cemc_timer_start / _stop
   cudaEvent_t tv0 = nullptr, tv1 = nullptr;     // the autotuner's own pair
+  // pinned staging buffers of the setters: the caller's buffer is consumed when the call
+  // returns, the copy itself is stream-ordered (no host synchronisation per setter)
+  struct Staging { void *host = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; };
+  Staging stg_occ, stg_eci, stg_kT, stg_cf, stg_ref;
   // host copies needed by the API
   std::vector<int32_t> symm_of_site;
   std::vector<int8_t> allowed;
@@ -98,6 +102,21 @@ struct cemc_handle {
   TabTables tab{};
   unsigned long long *d_phase = nullptr;   // CEMC_PHASE_TIMING builds
 };
+
+static int h2d_staged(cemc_handle *h, cemc_handle::Staging &st, void *dst, const void *src, size_t bytes) {
+  if (st.cap < bytes) {
+    if (st.host) { CU(cudaEventSynchronize(st.ev)); CU(cudaFreeHost(st.host)); st.host = nullptr; st.cap = 0; }
+    CU(cudaMallocHost(&st.host, bytes));
+    st.cap = bytes;
+    if (!st.ev) CU(cudaEventCreateWithFlags(&st.ev, cudaEventDisableTiming));
+  } else {
+    CU(cudaEventSynchronize(st.ev));          // the previous copy out of this buffer has finished
+  }
+  memcpy(st.host, src, bytes);
+  CU(cudaMemcpyAsync(dst, st.host, bytes, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaEventRecord(st.ev, h->stream));
+  return 0;
+}
 
 static void reset_tuning(cemc_handle *h) {
   h->tuned_sgc = h->tuned_can = -1;
@@ -167,22 +186,53 @@ __global__ void cf_partial_kernel(DeviceTables t, const int8_t *occ, double *par
     const int2 ts = t.task_sum[job];
     int q0 = t.item_base[g];
     while (t.item_slot[q0] != ts.x) q0++;
+    // the task's factors decoded once per CTA (no integer division in the site loop):
+    // x = row of bf (basis function), y = translation column, or -1 = the site itself
+    __shared__ short2 s_dc[1024];
+    const bool staged = ts.y * 4 <= 1024;
+    if (staged) {
+      for (int e = threadIdx.x; e < ts.y * 4; e += blockDim.x) {
+        const unsigned long long w = t.items[q0 + (e >> 2)];
+        const int idx = (int)((w >> (CEMC_ITEM_BITS * (e & 3))) & CEMC_ITEM_MASK);
+        short2 v;
+        if (idx == t.K) v = make_short2(-1, 0);                           // unused position
+        else if (idx >= RB) v = make_short2((short)(idx - RB), -1);
+        else v = make_short2((short)(idx / t.KP), (short)(idx % t.KP));
+        s_dc[e] = v;
+      }
+      __syncthreads();
+    }
     for (int a = threadIdx.x; a < t.N; a += blockDim.x) {
       if (t.symm_of_site[a] != g) continue;
       const int me = o[a];
+      const int32_t *row = t.trans + (size_t)a * t.K;
       double sp = 0.0;
-      for (int m = 0; m < ts.y; m++) {
-        const unsigned long long w = t.items[q0 + m];
-        double tt = 1.0;
-        for (int k = 0; k < 4; k++) {
-          const int idx = (int)((w >> (CEMC_ITEM_BITS * k)) & CEMC_ITEM_MASK);
-          if (idx == t.K) continue;                       // unused position
-          double f;
-          if (idx >= RB) f = t.bf[(idx - RB) * t.S + me];
-          else { const int d = idx / t.KP, c = idx % t.KP; f = t.bf[d * t.S + o[t.trans[(size_t)a * t.K + c]]]; }
-          tt *= f;
+      if (staged) {
+        for (int m = 0; m < ts.y; m++) {
+          double tt = 1.0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const short2 dc = s_dc[m * 4 + k];
+            if (dc.x < 0) continue;
+            const int sp_id = dc.y < 0 ? me : (int)o[__ldg(row + dc.y)];
+            tt *= t.bf[dc.x * t.S + sp_id];
+          }
+          sp += tt;
         }
-        sp += tt;
+      } else {
+        for (int m = 0; m < ts.y; m++) {
+          const unsigned long long w = t.items[q0 + m];
+          double tt = 1.0;
+          for (int k = 0; k < 4; k++) {
+            const int idx = (int)((w >> (CEMC_ITEM_BITS * k)) & CEMC_ITEM_MASK);
+            if (idx == t.K) continue;                       // unused position
+            double f;
+            if (idx >= RB) f = t.bf[(idx - RB) * t.S + me];
+            else { const int d = idx / t.KP, c = idx % t.KP; f = t.bf[d * t.S + o[t.trans[(size_t)a * t.K + c]]]; }
+            tt *= f;
+          }
+          sp += tt;
+        }
       }
       acc += sp;
     }
@@ -672,6 +722,10 @@ int cemc_destroy(cemc_handle *h) {
   for (void *p : extra) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (cemc_handle::Staging *st : {&h->stg_occ, &h->stg_eci, &h->stg_kT, &h->stg_cf, &h->stg_ref}) {
+    if (st->ev) { cudaEventSynchronize(st->ev); cudaEventDestroy(st->ev); }
+    if (st->host) cudaFreeHost(st->host);
+  }
   if (h->tv0) cudaEventDestroy(h->tv0);
   if (h->tv1) cudaEventDestroy(h->tv1);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -722,8 +776,7 @@ int cemc_set_occupancy(cemc_handle *h, const int8_t *occ) {
     for (size_t q = 0; q < n; q++) bad |= (unsigned)((unsigned char)occ[q] >= S);
     if (bad) return fail("occupancy value out of range");
   }
-  CU(cudaMemcpyAsync(h->st.occ, occ, n, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  { const int rc = h2d_staged(h, h->stg_occ, h->st.occ, occ, n); if (rc) return rc; }
   h->tracker_dirty = true;
   drop_trials(h);
   return 0;
@@ -740,8 +793,7 @@ int cemc_get_occupancy(cemc_handle *h, int8_t *occ) {
 int cemc_set_cf(cemc_handle *h, const double *cf) {
   if (!h || !cf) return fail("null argument");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(h->st.cf, cf, sizeof(double) * h->R * h->t.n_eci, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  { const int rc = h2d_staged(h, h->stg_cf, h->st.cf, cf, sizeof(double) * h->R * h->t.n_eci); if (rc) return rc; }
   drop_trials(h);
   return refresh_energy(h);
 }
@@ -777,8 +829,7 @@ int cemc_set_ecis(cemc_handle *h, const double *eci, int per_replica) {
     for (int r = 0; r < h->R; r++) memcpy(&tmp[(size_t)r * n], eci, sizeof(double) * n);
     src = tmp.data();
   }
-  CU(cudaMemcpyAsync(h->st.eci, src, sizeof(double) * h->R * n, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  { const int rc = h2d_staged(h, h->stg_eci, h->st.eci, src, sizeof(double) * h->R * n); if (rc) return rc; }
   return refresh_energy(h);
 }
 
@@ -802,9 +853,7 @@ int cemc_set_kT(cemc_handle *h, const double *kT) {
   if (!h || !kT) return fail("null argument");
   CU(cudaSetDevice(h->device));
   for (int r = 0; r < h->R; r++) if (!(kT[r] > 0.0)) return fail("kT must be positive");
-  CU(cudaMemcpyAsync(h->st.kT, kT, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return 0;
+  return h2d_staged(h, h->stg_kT, h->st.kT, kT, sizeof(double) * h->R);
 }
 
 int cemc_get_kT(cemc_handle *h, double *kT) {
@@ -1458,9 +1507,9 @@ int cemc_reset_accumulators(cemc_handle *h, const double *ref) {
   CU(cudaMemsetAsync(h->st.acc, 0, sizeof(double) * h->R * h->acc_stride, h->stream));
   if (ref) {
     for (int r = 0; r < h->R; r++) if (ref[r] == 0.0) return fail("Averager reference value must be non-zero");
-    CU(cudaMemcpyAsync(h->st.ref, ref, sizeof(double) * h->R, cudaMemcpyHostToDevice, h->stream));
+    const int rc = h2d_staged(h, h->stg_ref, h->st.ref, ref, sizeof(double) * h->R);
+    if (rc) return rc;
   }
-  CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
