@@ -82,6 +82,7 @@ SIGNATURES = {
     "cemc_set_spin_kernel": [_H, C.c_int],
     "cemc_set_table_eval": [_H, C.c_int],
     "cemc_set_precision": [_H, C.c_int],
+    "cemc_set_replica_order": [_H, _i32p],
     "cemc_get_batch_eval": [_H, _i32p],
     "cemc_set_screen_slack": [_H, C.c_double],
     "cemc_debug_phase_cycles": [_H, _u64p],

@@ -99,6 +99,10 @@ struct cemc_handle {
   bool tab_ok = false;                // product tables fit: table evaluation in the batch kernel
   bool no_tab = false;                // testing: keep the fp64 product evaluation
   bool fp32 = false;                  // cemc_set_precision(32): single-precision tables / sums
+  int32_t *d_order = nullptr;         // CTA -> replica map of the batch kernel (load balance), or null
+  int32_t *d_order_buf = nullptr;
+  int32_t *d_order_auto = nullptr;    // hottest-first order computed on the device (order_kernel)
+  bool order_dirty = true;            // temperatures changed since d_order_auto was computed
   TabTables tab{};
   unsigned long long *d_phase = nullptr;   // CEMC_PHASE_TIMING builds
 };
@@ -756,6 +760,24 @@ int cemc_set_order_mode(cemc_handle *h, int mode) {
   return 0;
 }
 
+// Load balance of the batch kernel when there are more chains than SMs (one CTA per chain,
+// two CTAs per SM): CTA i works on the chain with the i-th highest temperature.  The block
+// scheduler fills the SMs breadth first, so the hottest chains (most accepted moves, most
+// bookkeeping: the slowest CTAs) end up sharing an SM with the coldest ones and the launch,
+// which ends with its slowest CTA, gets shorter (config 2: 209.6 -> 202.4 ns/move).  Results
+// never depend on the order (chains are keyed by replica id).
+__global__ void order_kernel(int R, const double *kT, int32_t *order) {
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const double k = kT[r];
+    int rank = 0;
+    for (int j = 0; j < R; j++) {
+      const double kj = kT[j];
+      rank += (kj > k) || (kj == k && j < r);
+    }
+    order[rank] = r;
+  }
+}
+
 static int refresh_energy(cemc_handle *h) {
   energy_kernel<<<(h->R + 127) / 128, 128, 0, h->stream>>>(h->R, h->t.n_eci, h->t.N, h->st.eci,
                                                            h->st.cf, h->st.e_cur);
@@ -853,6 +875,7 @@ int cemc_set_kT(cemc_handle *h, const double *kT) {
   if (!h || !kT) return fail("null argument");
   CU(cudaSetDevice(h->device));
   for (int r = 0; r < h->R; r++) if (!(kT[r] > 0.0)) return fail("kT must be positive");
+  h->order_dirty = true;
   return h2d_staged(h, h->stg_kT, h->st.kT, kT, sizeof(double) * h->R);
 }
 
@@ -919,6 +942,22 @@ int cemc_set_table_eval(cemc_handle *h, int on) {
   if (!h) return fail("null handle");
   h->no_tab = (on == 0);
   reset_tuning(h);
+  return 0;
+}
+
+int cemc_set_replica_order(cemc_handle *h, const int32_t *order) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  if (!order) { h->d_order = nullptr; return 0; }
+  std::vector<char> seen(h->R, 0);
+  for (int i = 0; i < h->R; i++) {
+    if (order[i] < 0 || order[i] >= h->R || seen[order[i]]) return fail("replica order must be a permutation of 0..R-1");
+    seen[order[i]] = 1;
+  }
+  if (!h->d_order_buf) { int rc = dalloc(h, &h->d_order_buf, h->R); if (rc) return rc; }
+  CU(cudaMemcpyAsync(h->d_order_buf, order, sizeof(int32_t) * h->R, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->d_order = h->d_order_buf;
   return 0;
 }
 
@@ -1120,6 +1159,7 @@ static RunArgs run_args(cemc_handle *h, long long n_steps) {
   a.observe = 1;
   a.screen_slack = h->screen_slack;
   a.phase = h->d_phase;
+  a.order = h->d_order;
   if (h->trace_capacity > 0) {
     a.tr_sites = h->tr_sites; a.tr_news = h->tr_news; a.tr_u = h->tr_u; a.tr_acc = h->tr_acc;
     a.tr_e = h->tr_e; a.tr_capacity = h->trace_capacity;
@@ -1137,6 +1177,16 @@ static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 
   L.tree = ((h->order_mode == CEMC_ORDER_TREE) || h->integer_bf) ? 1 : 0;
   L.stream = h->stream; L.t = h->t; L.st = h->st; L.a = a; L.acc_stride = h->acc_stride;
   L.sp = h->spin; L.tb = h->tab;
+  if (!h->d_order && C == 1 && h->R > h->n_sms && h->R <= 4096) {      // more chains than SMs: hottest first
+    if (!h->d_order_auto) { const int rc0 = dalloc(h, &h->d_order_auto, h->R); if (rc0) return rc0; h->order_dirty = true; }
+    if (h->order_dirty) {
+      order_kernel<<<1, 256, 0, h->stream>>>(h->R, h->st.kT, h->d_order_auto);
+      h->launches++;
+      CU(cudaGetLastError());
+      h->order_dirty = false;
+    }
+    L.a.order = h->d_order_auto;
+  }
   int rc;
   if (h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4)
     rc = batch_launch_spin(L);          // binary +-1 basis: spin evaluation
@@ -1533,6 +1583,7 @@ int cemc_pt_exchange(cemc_handle *h, int n_total, const double *energies_dev,
     CU(cudaMalloc((void **)&h->pt_scratch, sizeof(int32_t) * n_total));
     h->pt_scratch_n = n_total;
   }
+  h->order_dirty = true;
   pt_exchange_kernel<<<1, 256, 0, h->stream>>>(n_total, energies_dev, slot_of_replica_dev, kT_of_slot_dev,
                                                direction, h->seed, round, h->pt_scratch, h->st.kT,
                                                h->replica_offset, h->R, n_accepted_dev);

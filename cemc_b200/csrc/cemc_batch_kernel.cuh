@@ -182,7 +182,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   constexpr int NJE = kSplit ? 1 : NJ;           // changed sites one warp evaluates
   static_assert(BT <= 32, "one decision lane per move");
   const int crank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
-  const int r = blockIdx.x / C;
+  const int r = a.order ? a.order[blockIdx.x / C] : (int)(blockIdx.x / C);
   const int tid = threadIdx.x, nthr = (B + 1) * 32;
   const int lane = tid & 31, lwarp = tid >> 5;
   const bool is_obs = (lwarp == B);              // the observer warp (works in CTA 0 only)

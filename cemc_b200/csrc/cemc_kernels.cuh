@@ -119,6 +119,7 @@ struct RunArgs {
   double *tr_e;
   long long tr_capacity;
   unsigned long long *phase;   // [R][24] per-phase cycle counts (CEMC_PHASE_TIMING builds), may be null
+  const int32_t *order;        // [R] replica handled by CTA (cluster) i, or null = identity (load balance)
 };
 
 // ---------------------------------------------------------------------------

@@ -159,6 +159,14 @@ class BatchedCEUpdater(object):
         (single-precision product tables and sub-cluster sums, fp64 everything else)."""
         _lib.check(self.lib.cemc_set_precision(self._h, int(bits)))
 
+    def set_replica_order(self, order=None):
+        """CTA i of the batch kernel works on replica ``order[i]`` (load balance only)."""
+        if order is None:
+            _lib.check(self.lib.cemc_set_replica_order(self._h, None))
+        else:
+            o = np.ascontiguousarray(order, dtype=np.int32)
+            _lib.check(self.lib.cemc_set_replica_order(self._h, _p(o, C.c_int32)))
+
     def get_batch_eval(self) -> int:
         """0 fp64 products, 1 binary spin, 2 product tables."""
         v = C.c_int32(-1)

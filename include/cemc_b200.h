@@ -148,6 +148,9 @@ int cemc_get_batch_eval(cemc_handle *h, int *ev);
  * ECIs, one symmetry group, tables fit shared memory); a binary +-1 basis is exact
  * integer arithmetic in either setting.  Fails otherwise.                            */
 int cemc_set_precision(cemc_handle *h, int bits);
+/* Load balance of the batch kernel: CTA (cluster) i works on replica order[i] (a permutation of
+ * 0..R-1; NULL = identity).  Results never depend on it (chains are keyed by replica id).     */
+int cemc_set_replica_order(cemc_handle *h, const int32_t *order);
 /* testing hook: widen the band in which the batch kernel's Metropolis screen
  * defers to the exact expression (factor >= 1; 1e30 = always exact)           */
 int cemc_set_screen_slack(cemc_handle *h, double factor);

@@ -801,3 +801,34 @@ def test_full_size_cluster_stress(cuda_device, variant):
     for r, c in enumerate(chains):
         assert np.array_equal(accs[r], c.acc)
         assert steps[r] == 2 * n and n_acc[r] == c.n_accepted.value
+
+
+def test_replica_order_is_invisible(cuda_device):
+    """CTA -> replica order of the batch kernel (load balance): a user permutation and the
+    automatic hottest-first order used when there are more chains than SMs (R = 160 > 148) both
+    leave every chain's trajectory bit-identical to the oracle."""
+    st, eci, symbols, ft = build(**BINARY)
+    rng = np.random.default_rng(5)
+    for R, user in ((160, False), (7, True)):
+        kTs = rng.uniform(0.02, 0.2, R)
+        gpu, chains = make_pair(ft, [symbols] * R, kTs, seed=19)
+        gpu.set_variant(3, 3)
+        if user:
+            gpu.set_replica_order(rng.permutation(R))
+        gpu.reset_accumulators()
+        gpu.run_canonical(400)
+        gpu.run_sgc(700)
+        gpu.set_kT(kTs[::-1].copy())              # the automatic order follows the temperatures
+        gpu.run_sgc(500)
+        gpu.synchronize()
+        for r, c in enumerate(chains):
+            c.run_canonical(400)
+            c.run_sgc(700)
+            c.kT = float(kTs[::-1][r])
+            c.run_sgc(500)
+        assert_state_equal(gpu, chains)
+        accs = gpu.get_accumulators()
+        for r, c in enumerate(chains):
+            assert np.array_equal(accs[r], c.acc)
+    with pytest.raises(Exception):
+        gpu.set_replica_order([0] * 7)            # not a permutation
