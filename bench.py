@@ -153,9 +153,20 @@ def gpu_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL's banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # keep stdout to the one JSON line: NCCL prints its version banner (and any NCCL_DEBUG
+        # output) on stdout when the first communicator is created, so stdout points at stderr
+        # until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
 
     # CPU baseline first (rank 0, N=1 only), before this process touches CUDA
