@@ -6,6 +6,7 @@ from cemc_b200 import workloads as wl
 w = wl.WORKLOADS["C2"]()
 gpu = wl.make_updater(w)
 gpu.set_variant(3, 3)
+gpu.set_replica_order(np.arange(w.R))      # "identity" = the automatic hottest-first order switched off
 R = w.R
 hot = np.argsort(-w.kT, kind="stable")           # hottest first
 def timeit(tag):
@@ -21,10 +22,8 @@ alone = hot[:40]; rest = hot[40:]                 # 216 chains, hottest first
 order[108:148] = alone
 order[:108] = rest[:108]                          # hotter half on first-wave CTAs 0..107
 order[148:] = rest[108:][::-1]                    # partner of CTA i is CTA 148+i: coldest with hottest
-timeit("hot alone + hot/cold pairs")
 order2 = np.empty(R, dtype=np.int32)
 order2[:148] = hot[:148]; order2[148:] = hot[148:][::-1]
-timeit_order = order2
 gpu.set_replica_order(order); timeit("hot alone + hot/cold pairs")
 gpu.set_replica_order(order2); timeit("hot first wave, cold partners")
 gpu.set_replica_order(hot.astype(np.int32)); timeit("sorted hot -> cold")
