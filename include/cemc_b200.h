@@ -31,7 +31,9 @@
  * cemc_last_error() gives the message.  Host pointers unless the name says
  * `_dev`.  All arrays are dense, row-major, replica-major ([R][...]).
  * One handle = one CUDA device + one stream; calls are stream-ordered and
- * the handle is not thread-safe.  No torch types appear in this ABI.
+ * the handle is not thread-safe.  Setters copy the caller's buffer before they
+ * return (pinned staging), the upload itself is stream-ordered; getters and
+ * cemc_synchronize wait for the stream.  No torch types appear in this ABI.
  */
 #ifndef CEMC_B200_H
 #define CEMC_B200_H
