@@ -558,6 +558,7 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
     h->spin.n_items = (int)sp_items.size();
     h->spin.n_rounds = ((int)sp_items.size() + 31) / 32;
     h->spin.b0 = b0;
+    h->spin.wq = *std::max_element(sp_msub.begin(), sp_msub.end()) + 1;
   }
 
   // ---- product tables of the batch kernel's table evaluation (TabTables) --------

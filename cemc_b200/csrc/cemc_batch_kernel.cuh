@@ -65,7 +65,7 @@ struct TabTables {
 enum BatchEval : int { EV_PRODUCT = 0, EV_SPIN = 1, EV_TAB = 2, EV_TAB32 = 3 };
 
 struct BatchSmem {
-  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *dEb, *Pm, *Ch, *obE, *tab, *pub;
+  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *dEb, *Pm, *Ch, *obE, *tab, *pub, *qtab;
   uint4 *items;
   int2 *task_sum;
   int4 *ttask;
@@ -86,7 +86,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
                                                     const DeviceTables &t, bool canonical,
                                                     bool state_in_smem = true,
                                                     const TabTables *tb = nullptr,
-                                                    bool tab_fp32 = false) {
+                                                    bool tab_fp32 = false, int spin_wq = 0) {
   size_t o = 0;
 #define CEMC_TAKE(field, type, count)                                   \
   do {                                                                  \
@@ -112,6 +112,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(codes, uint32_t, tb ? B * nj * tb->n_sub : 0);
   CEMC_TAKE(sq, double, 2 * BT * 2 * 32);      // double buffered: the bookkeeper reads batch k during batch k+1
   CEMC_TAKE(pub, double, 34);
+  CEMC_TAKE(qtab, double, spin_wq * 64);      // spin evaluation: quotient table [new species][count][ECI lane]
   CEMC_TAKE(dEa, double, BT);
   CEMC_TAKE(dEb, double, BT);
   CEMC_TAKE(Pm, double, BT * 33);
@@ -200,7 +201,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   int32_t *g_list = st.list + (size_t)r * N;
   int32_t *g_loc = st.loc + (size_t)r * N;
   BatchSmem s;
-  batch_smem_layout<B, BT>(&s, smem_raw, t, kCanon, kStateSmem, kTab ? &tb : nullptr, kTab32);
+  batch_smem_layout<B, BT>(&s, smem_raw, t, kCanon, kStateSmem, kTab ? &tb : nullptr, kTab32, kSpin ? sp.wq : 0);
   if (!kStateSmem) { s.occ = g_occ; s.list = g_list; }
   // CTA 0's copies of the arrays the deciding warp reads (DSMEM when C > 1)
   BatchSmem s0 = s;
@@ -386,6 +387,17 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       smc[q] = xc != 0xffu ? 1u : 0u;
       smv[q] = valid ? 1u : 0u;
       smask[q] = sp.masks[lane * 4 + q];
+    }
+    // Every quotient the evaluation can produce, once per launch: the numerator
+    // n (sigma_new - sigma_old)(M - 2 count) takes 2 (M + 1) integer values per ECI, so the
+    // exact division (ce_updater.cpp:402) becomes one shared-memory load per evaluated site.
+    if (lwarp == 0) {
+      for (int nw = 0; nw < 2; nw++)
+        for (int cnt = 0; cnt < sp.wq; cnt++) {
+          const int dsig = 2 * sp.b0 * (1 - 2 * nw);                 // old = 1 - new
+          const int num = s_coef * dsig * (s_msub - 2 * cnt);
+          s.qtab[(nw * sp.wq + cnt) * 32 + lane] = cnt <= s_msub ? exact_div((double)num, f_den, f_rden) : 0.0;
+        }
     }
   }
 
@@ -702,9 +714,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                   cnt += __popc(__ballot_sync(0xffffffffu, bit != 0u) & smask[q]);
                 }
               }
-              const int dsig = 2 * sp.b0 * (oldv[mi][j] - newv[mi][j]);      // sigma_new - sigma_old
-              const int num = s_coef * dsig * (s_msub - 2 * cnt);
-              qv[mi][je] = exact_div((double)num, f_den, f_rden);            // :402
+              qv[mi][je] = s.qtab[(newv[mi][j] * sp.wq + cnt) * 32 + lane];   // n dsigma (M - 2 cnt) / den, :393-402
             }
           }
         }

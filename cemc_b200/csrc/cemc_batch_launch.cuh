@@ -54,9 +54,10 @@ template <int MODE, bool kTree, int B, int C, int EV, int M = 1>
 static int batch_launch_b(const BatchLaunch &L) {
   const TabTables *tb = (EV == EV_TAB || EV == EV_TAB32) ? &L.tb : nullptr;
   constexpr bool f32 = (EV == EV_TAB32);
-  size_t sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, tb, f32);
+  const int wq = EV == EV_SPIN ? L.sp.wq : 0;
+  size_t sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, tb, f32, wq);
   const bool in_smem = sm <= (size_t)L.max_smem_optin;
-  if (!in_smem) sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, false, tb, f32);
+  if (!in_smem) sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, false, tb, f32, wq);
   if (sm > (size_t)L.max_smem_optin) return -1;
   if constexpr (M > 1) {            // two moves per warp: shared-memory state only
     return in_smem ? batch_launch_kc<MODE, kTree, B, true, C, EV, M>(L, sm) : -1;
@@ -71,7 +72,7 @@ template <int MODE, bool kTree, int B, int EV>
 static int batch_launch_split(const BatchLaunch &L) {
   if constexpr (MODE == MODE_CANONICAL && EV != EV_PRODUCT) {
     const TabTables *tb = (EV == EV_TAB || EV == EV_TAB32) ? &L.tb : nullptr;
-    const size_t sm = batch_smem_layout<B, B>(nullptr, nullptr, L.t, true, true, tb, EV == EV_TAB32);
+    const size_t sm = batch_smem_layout<B, B>(nullptr, nullptr, L.t, true, true, tb, EV == EV_TAB32, EV == EV_SPIN ? L.sp.wq : 0);
     if (sm > (size_t)L.max_smem_optin) return -1;
     return batch_launch_kc<MODE, kTree, B, true, 2, EV, 1, true>(L, sm);
   } else {

@@ -30,6 +30,7 @@ struct SpinTables {
   const int32_t *coef;         // [32] n * b0^(n-1) (clusters), 1 (singlets), 0 (copied)
   const int32_t *msub;         // [32] M (clusters), 1 (singlets)
   int b0;                      // bf[0][species 0] = +1 or -1
+  int wq;                      // max msub + 1: width of the batch kernel's quotient table
 };
 
 template <int MODE, int NR>
