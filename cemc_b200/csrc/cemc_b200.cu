@@ -1144,7 +1144,7 @@ template <int MODE>
 static int launch_spin(cemc_handle *h, const RunArgs &a) {
   if (!h->spin_ok || h->force_generic || h->no_spin || !h->t.allowed_identity) return -1;
   const size_t N = (size_t)h->t.N;
-  const size_t sm = 1024 + 4 * (size_t)((h->spin.n_items + 3) & ~3) +
+  const size_t sm = 1024 + 512 * (size_t)h->spin.wq + 4 * (size_t)((h->spin.n_items + 3) & ~3) +
                     (MODE == MODE_CANONICAL ? 4 * ((N + 3) & ~(size_t)3) : 0) + ((N + 15) & ~(size_t)15);
   if (sm > (size_t)h->max_smem_optin) return -1;
   const int nr = h->spin.n_rounds * 1;

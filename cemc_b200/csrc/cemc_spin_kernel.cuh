@@ -43,9 +43,10 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
   const int lane = threadIdx.x;
   const int N = t.N, K = t.K, n_eci = t.n_eci;
 
-  // ---- shared memory: ring | items | [list] | occ ---------------------------
+  // ---- shared memory: ring | quotient table | items | [list] | occ ----------
   uint4 *ring = reinterpret_cast<uint4 *>(smem_raw);                   // [32][2]
-  uint32_t *s_items = reinterpret_cast<uint32_t *>(ring + 64);         // [n_items]
+  double *s_qtab = reinterpret_cast<double *>(ring + 64);              // [2][wq][32]
+  uint32_t *s_items = reinterpret_cast<uint32_t *>(s_qtab + sp.wq * 64);   // [n_items]
   int32_t *s_list = reinterpret_cast<int32_t *>(s_items + ((sp.n_items + 3) & ~3));
   int8_t *s_occ = reinterpret_cast<int8_t *>(s_list + (kCanon ? ((N + 3) & ~3) : 0));
 
@@ -74,6 +75,14 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
   const double f_den = (f_kind == 1) ? dN : (mine ? t.fin_d[lane].y : 1.0);
   const double f_rden = __ddiv_rn(1.0, f_den);
   const int coef = sp.coef[lane], msub = sp.msub[lane];
+  // every quotient n (sigma_new - sigma_old)(M - 2 count) / den this lane's ECI can take, once per
+  // launch: the exact division (ce_updater.cpp:402) becomes one shared-memory load per site
+  for (int nw = 0; nw < 2; nw++)
+    for (int cnt = 0; cnt < sp.wq; cnt++) {
+      const int num = coef * (2 * sp.b0 * (1 - 2 * nw)) * (msub - 2 * cnt);
+      s_qtab[(nw * sp.wq + cnt) * 32 + lane] = cnt <= msub ? exact_div((double)num, f_den, f_rden) : 0.0;
+    }
+  __syncwarp();
   uint32_t mask[NR];
 #pragma unroll
   for (int q = 0; q < NR; q++) mask[q] = sp.masks[lane * 4 + q];
@@ -238,9 +247,7 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
         int cnt = 0;
 #pragma unroll
         for (int q = 0; q < NR; q++) cnt += __popc(ball[j][q] & mask[q]);
-        const int dsig = 2 * b0 * (oldsp[j] - newsp[j]);          // sigma_new - sigma_old
-        const int num = coef * dsig * (msub - 2 * cnt);
-        const double dl = exact_div((double)num, f_den, f_rden);  // :402
+        const double dl = s_qtab[(newsp[j] * sp.wq + cnt) * 32 + lane];   // n dsigma (M - 2 cnt) / den, :393-402
         if (f_kind > 0) c = __dadd_rn(c, dl);                      // :404
       }
       const double p = __dmul_rn(eci_reg, c);
