@@ -231,7 +231,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // 8-byte decision (moves decided, accept mask) to CTA 1 (completes CTA 1's mbarrier D); CTA 1
   // applies the commits to its own copy from its own proposal ring.  No barrier.cluster (with
   // its MEMBAR.ALL.GPU / L1 invalidation) inside the batch loop.
+#ifdef CEMC_SYNC_CLUSTER   // debugging aid: barrier.cluster everywhere (compute-sanitizer's racecheck does not
+  constexpr bool kAsync = false;   // model mbarrier transaction counts / st.async as synchronisation)
+#else
   constexpr bool kAsync = (C == 2) && kStateSmem;
+#endif
   const bool remote = kAsync && crank == 1;
   constexpr uint32_t kTxPerMove = kSplit ? (256u + 8u + 4u) : (32u + 512u + 8u + 4u);
   uint32_t rE = 0, r_sq = 0, r_dE = 0, r_cm = 0, r_prop = 0, rD = 0, r_ctl = 0, phE = 0, phD = 0;
