@@ -1141,10 +1141,15 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       if (tid == 0) { tph[8] += 1; tph[9] += ndone; tph[10] += __popc(accmask); tph[11] += (stops ? 1 : 0); }
 #endif
     }
+    int2 ct_early = make_int2(0, 0);
     if (kAsync) {
       if (crank == 1) {
         mbar_wait(s.mbar + 2, phD);                 // the decision record has landed in s.ctl
         phD ^= 1u;
+        // every warp of CTA 1 (also the observer warp, which sends nothing to CTA 0) takes its copy
+        // BEFORE the block barrier: the next decision can only be sent after all evaluation warps
+        // passed that barrier, so it can never overwrite a record somebody still has to read
+        ct_early = *reinterpret_cast<const int2 *>(s.ctl);
         if (lwarp == 0) {
           // CTA 1 applies the accepted moves to its own copy of the state, re-deriving each
           // move from its own proposal ring (accepted moves of a batch touch disjoint sites)
@@ -1179,7 +1184,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     if (*reinterpret_cast<volatile int32_t *>(s.ctl + 7) == 0x7fffffff) tlast = 0;
 #endif
     {   // rewritten only after the next barrier: no second barrier needed
-      const int2 ct = *reinterpret_cast<const int2 *>(s.ctl);
+      const int2 ct = (kAsync && crank == 1) ? ct_early : *reinterpret_cast<const int2 *>(s.ctl);
       bk_nd = ct.x; bk_am = (uint32_t)ct.y; bk_base = sdone;
       sdone += ct.x;
       par ^= 1;
