@@ -299,8 +299,8 @@ def gpu_arm(args):
                          "is shared-memory resident by design",
                 "parallelism": "replicas sharded over %d GPU(s), no data-path collective" % world,
                 "kernel_variant": "%d (0 spin, 1-4 batch (16,2)/(16,1)/(8,1)/(4,1), 5 one move at a "
-                                  "time, 6-7 batch (8,1)/(16,1) with two moves per warp; autotuned "
-                                  "unless --variant)" % gpu.get_variant()[0],
+                                  "time, 6-7 batch (8,1)/(16,1) with two moves per warp, 8 batch (16,2) "
+                                  "site split; autotuned unless --variant)" % gpu.get_variant()[0],
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
