@@ -1171,8 +1171,10 @@ static RunArgs run_args(cemc_handle *h, long long n_steps) {
 // speculative batch kernel with B moves per CTA and C CTAs per chain; -1 when not applicable
 template <int MODE>
 static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 1, int split = 0) {
+  const bool spin_eval = h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4;
+  // K <= 31 translation columns (one per lane); the spin evaluation also takes 32..63 (two per lane)
   if (h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
-      2 * h->t.KP > 64) return -1;
+      h->t.KP > (spin_eval ? 64 : 32)) return -1;
   BatchLaunch L{};
   L.mode = MODE; L.B = B; L.C = C; L.M = M; L.split = split; L.R = h->R; L.max_smem_optin = h->max_smem_optin;
   L.tree = ((h->order_mode == CEMC_ORDER_TREE) || h->integer_bf) ? 1 : 0;

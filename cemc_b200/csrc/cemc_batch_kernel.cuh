@@ -167,7 +167,9 @@ __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, 
 // batch, CTA q the CF change of changed site q of every swap (update_cf is called once per changed
 // site, ce_updater.cpp:845-852, and the two calls only meet in the sum of their increments).  A
 // swap then costs an evaluation warp what a one-site flip costs, instead of twice that.
-template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV, int M = 1, bool kSplit = false>
+// kWide (spin evaluation only): 32 <= K <= 63 translation columns -- every lane gathers two columns
+// (lane, lane + 32), the occupation mask has 64 bits.
+template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV, int M = 1, bool kSplit = false, bool kWide = false>
 __global__ void __launch_bounds__((B + 1) * 32, (EV != EV_PRODUCT && B <= 8) ? 2 : 1)
 batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTables sp, TabTables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -182,6 +184,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   constexpr int BT = BW * M;                     // moves per batch over the whole cluster
   constexpr int NJE = kSplit ? 1 : NJ;           // changed sites one warp evaluates
   static_assert(BT <= 32, "one decision lane per move");
+  static_assert(!kWide || EV == EV_SPIN, "two columns per lane: spin evaluation only");
   const int crank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int r = a.order ? a.order[blockIdx.x / C] : (int)(blockIdx.x / C);
   const int tid = threadIdx.x, nthr = (B + 1) * 32;
@@ -635,17 +638,19 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     // gathered sites (one vote per move); with many, every gathered site is broadcast and
     // compared by the lanes holding the moves.  Both are short independent shuffle / compare
     // / vote sequences (MATCH.ANY over 32 distinct values costs ~400 cycles on sm_100).
-    auto conflict_mask = [&](int b, const int (&gsx)[2], int sk0, int sk1) -> uint32_t {
+    auto conflict_mask = [&](int b, const int (&gsx)[2], int sk0, int sk1, const int (&gsy)[2]) -> uint32_t {
       uint32_t m = 0;
       if (b <= KP) {
         for (int k = 0; k < b; k++) {
           const int a0 = __shfl_sync(0xffffffffu, sk0, k);
           bool hit = (gsx[0] == a0);
           if (NJE == 2) hit |= (gsx[1] == a0);
+          if (kWide) { hit |= (gsy[0] == a0); if (NJE == 2) hit |= (gsy[1] == a0); }
           if (kCanon) {
             const int a1 = __shfl_sync(0xffffffffu, sk1, k);
             hit |= (gsx[0] == a1);
             if (NJE == 2) hit |= (gsx[1] == a1);
+            if (kWide) { hit |= (gsy[0] == a1); if (NJE == 2) hit |= (gsy[1] == a1); }
           }
           if (__any_sync(0xffffffffu, hit)) m |= 1u << k;
         }
@@ -654,7 +659,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
         for (int j = 0; j < NJE; j++)
           for (int q = 0; q < KP; q++) {
-            const int g = __shfl_sync(0xffffffffu, gsx[j], q);
+            const int g = __shfl_sync(0xffffffffu, (kWide && q >= 32) ? gsy[j] : gsx[j], q & 31);
             hit |= (g == sk0) | (kCanon & (g == sk1));
           }
         m = __ballot_sync(0xffffffffu, hit) & (b >= 32 ? 0xffffffffu : ((1u << b) - 1u));
@@ -673,7 +678,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       // division.  Moves past the end of the run are evaluated too (their records exist in
       // the ring; nobody reads the results): no divergence between the M streams.
       if (!is_obs) {
-        int site[M][2], oldv[M][2], newv[M][2], gs[M][2];
+        int site[M][2], oldv[M][2], newv[M][2], gs[M][2], gs2[M][2];
         double qv[M][2];
 #pragma unroll
         for (int mi = 0; mi < M; mi++) {
@@ -699,7 +704,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int mi = 0; mi < M; mi++) {
 #pragma unroll
           for (int je = 0; je < 2; je++) {
-            gs[mi][je] = -1; qv[mi][je] = 0.0;
+            gs[mi][je] = -1; gs2[mi][je] = -1; qv[mi][je] = 0.0;
             if (je < NJE) {
               const int j = jb + je;
               uint32_t v = 0;
@@ -709,12 +714,23 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                 v = (uint32_t)s.occ[nbs];
                 if (j == 1 && nbs == site[mi][0]) v = (uint32_t)newv[mi][0];   // change 1 sees change 0 applied (:845-852)
               } else if (lane == K) gs[mi][je] = site[mi][j];
-              const uint32_t ob = __ballot_sync(0xffffffffu, (v & 1u) != 0u);
+              typename std::conditional<kWide, unsigned long long, uint32_t>::type ob =
+                  __ballot_sync(0xffffffffu, (v & 1u) != 0u);
+              if (kWide) {                         // columns 32 .. K-1 and the site itself in the upper half
+                uint32_t v1 = 0;
+                if (lane + 32 < K) {
+                  const int nbs = __ldg(&t.trans[(size_t)site[mi][j] * K + lane + 32]);
+                  gs2[mi][je] = nbs;
+                  v1 = (uint32_t)s.occ[nbs];
+                  if (j == 1 && nbs == site[mi][0]) v1 = (uint32_t)newv[mi][0];
+                } else if (lane + 32 == K) gs2[mi][je] = site[mi][j];
+                ob |= (unsigned long long)__ballot_sync(0xffffffffu, (v1 & 1u) != 0u) << 32;
+              }
               int cnt = 0;
 #pragma unroll
               for (int q = 0; q < 4; q++) {
                 if (q < s_rounds) {
-                  const uint32_t bit = ((ob >> sca[q]) ^ ((ob >> scb[q]) & smb[q]) ^ ((ob >> scc[q]) & smc[q])) & smv[q];
+                  const uint32_t bit = (uint32_t)((ob >> sca[q]) ^ ((ob >> scb[q]) & smb[q]) ^ ((ob >> scc[q]) & smc[q])) & smv[q];
                   cnt += __popc(__ballot_sync(0xffffffffu, bit != 0u) & smask[q]);
                 }
               }
@@ -745,7 +761,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
         for (int mi = 0; mi < M; mi++) {
           const int b = warp + mi * BW;
-          const uint32_t m = conflict_mask(b, gs[mi], sk0, sk1);
+          const uint32_t m = conflict_mask(b, gs[mi], sk0, sk1, gs2[mi]);
           if (lane == 0) put_cm(b, m);
         }
         CEMC_TICK(13);
@@ -1035,7 +1051,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       {
         int sk0, sk1;
         changed_sites(b, sk0, sk1);
-        const uint32_t m = conflict_mask(b, gsx, sk0, sk1);
+        const int gsy[2] = {-1, -1};
+        const uint32_t m = conflict_mask(b, gsx, sk0, sk1, gsy);
         if (lane == 0) put_cm(b, m);
       }
       CEMC_TICK(13);

@@ -30,9 +30,9 @@ int batch_launch_spin(const BatchLaunch &L);
 int batch_launch_tab(const BatchLaunch &L);
 int batch_launch_tab32(const BatchLaunch &L);
 
-template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M, bool kSplit = false>
+template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M, bool kSplit = false, bool kWide = false>
 static int batch_launch_kc(const BatchLaunch &L, size_t sm) {
-  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV, M, kSplit>;
+  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV, M, kSplit, kWide>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return 1000 + (int)e;
   cudaLaunchConfig_t cfg{};
@@ -80,8 +80,26 @@ static int batch_launch_split(const BatchLaunch &L) {
   }
 }
 
+// 32 <= K <= 63 translation columns (spin evaluation, one CTA per chain, shared-memory state)
+template <int MODE, bool kTree, int B, int EV>
+static int batch_launch_wide(const BatchLaunch &L) {
+  if constexpr (EV == EV_SPIN) {
+    const size_t sm = batch_smem_layout<B, B>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, nullptr, false, L.sp.wq);
+    if (sm > (size_t)L.max_smem_optin) return -1;
+    return batch_launch_kc<MODE, kTree, B, true, 1, EV, 1, false, true>(L, sm);
+  } else {
+    return -1;
+  }
+}
+
 template <int MODE, bool kTree, int EV>
 static int batch_launch_bc(const BatchLaunch &L) {
+  if (L.t.K > 31) {
+    if (L.split || L.M != 1 || L.C != 1) return -1;
+    if (L.B == 16) return batch_launch_wide<MODE, kTree, 15, EV>(L);
+    if (L.B == 8) return batch_launch_wide<MODE, kTree, 7, EV>(L);
+    return -1;
+  }
   if (L.split) return (L.B == 16 && L.C == 2) ? batch_launch_split<MODE, kTree, 15, EV>(L) : -1;
   // L.B counts the warps of a CTA: B - 1 evaluation warps (moves per batch) + the observer
   // warp; power-of-two CTAs get the full register budget (512 threads x 128 registers)
