@@ -23,14 +23,25 @@
 //
 // Results are bit-identical to the one-move-at-a-time kernels (tested): the
 // arithmetic of each phase is the same code path, operation for operation.
-// CTA clusters (template parameter C > 1): C CTAs of one thread-block cluster work on
-// ONE chain.  Each CTA evaluates B moves of the batch (C*B <= 32 moves per batch);
-// proposals, per-ECI quotients, screens and conflict masks are written straight into
-// CTA 0's shared memory through distributed shared memory (DSMEM), CTA 0's warp 0
-// decides, and the commits go to every CTA's copy of the occupations (or to global
-// memory for supercells that do not fit).  barrier.cluster replaces __syncthreads.
-// This is the "large supercell / few replicas" mode: twice the evaluation
-// throughput for one chain, the exact sequential Markov chain is kept.
+// CTA clusters (template parameter C = 2): the two CTAs of a thread-block cluster work on ONE
+// chain: twice the evaluation throughput for one chain, the exact sequential Markov chain is
+// kept.  Each CTA evaluates B moves of the batch (2 B <= 32 moves per batch), CTA 0's warp 0
+// decides.  With the state in shared memory the CTAs talk through an async DSMEM protocol
+// (st.async + mbarrier transaction bytes, see kAsync below) and each commits its own copy of
+// the occupations; with the state in global memory (supercells that do not fit) the results
+// are written straight into CTA 0's shared memory and barrier.cluster replaces __syncthreads.
+//
+// Template parameters of batch_kernel:
+//   MODE        MODE_SGC (one-site flips) | MODE_CANONICAL (swaps: two changed sites per move)
+//   kTree       4-way interleaved sums over sub-clusters (CEMC_ORDER_TREE) instead of the
+//               reference's sequential order
+//   B           evaluation warps per CTA (15 / 7 / 3; plus one observer / bookkeeper warp)
+//   kStateSmem  occupations and site lists in shared memory (else global memory)
+//   C           CTAs per chain (1 | 2)
+//   EV          EV_PRODUCT | EV_SPIN | EV_TAB | EV_TAB32: how one move is evaluated
+//   M           moves per evaluation warp and batch (1 | 2)
+//   kSplit      site split (swaps, C = 2): both CTAs evaluate the same moves, one changed site each
+//   kWide       spin evaluation with 32..63 translation columns (two per lane)
 //
 // Used when the CF vector fits one warp (<= 32 ECIs), one symmetry group, state
 // in shared memory; everything else runs mc_kernel.
