@@ -43,8 +43,8 @@
 //   kSplit      site split (swaps, C = 2): both CTAs evaluate the same moves, one changed site each
 //   kWide       spin evaluation with 32..63 translation columns (two per lane)
 //
-// Used when the CF vector fits one warp (<= 32 ECIs), one symmetry group, state
-// in shared memory; everything else runs mc_kernel.
+// Used when the CF vector fits one warp (<= 32 ECIs), one symmetry group and K <= 31
+// translation columns (<= 63 for the spin evaluation); everything else runs mc_kernel.
 #pragma once
 #include <cooperative_groups.h>
 #include <type_traits>
