@@ -28,6 +28,18 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
 _lib = None
 
 
+def source_hash() -> str:
+    """sha256 (first 16 hex digits) over the kernel sources and the C header: identifies the
+    build that profiler-derived figures (profiles/traffic.json) were taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(SOURCES):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 class CemcError(RuntimeError):
     pass
 
@@ -69,6 +81,7 @@ SIGNATURES = {
     "cemc_create": [C.POINTER(CemcTablesStruct), C.c_int, C.c_int, C.c_int,
                     C.c_void_p, C.POINTER(_H)],
     "cemc_destroy": [_H],
+    "cemc_set_replica_stride": [_H, C.c_int],
     "cemc_set_stream": [_H, C.c_void_p],
     "cemc_synchronize": [_H],
     "cemc_set_order_mode": [_H, C.c_int],
@@ -78,6 +91,7 @@ SIGNATURES = {
     "cemc_set_cluster": [_H, C.c_int],
     "cemc_set_autotune": [_H, C.c_int],
     "cemc_get_variant": [_H, _i32p, _i32p],
+    "cemc_last_variant": [_H, _i32p],
     "cemc_set_variant": [_H, C.c_int, C.c_int],
     "cemc_set_spin_kernel": [_H, C.c_int],
     "cemc_set_table_eval": [_H, C.c_int],

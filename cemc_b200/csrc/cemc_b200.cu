@@ -49,7 +49,7 @@ struct cemc_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  int R = 0, replica_offset = 0;
+  int R = 0, replica_offset = 0, replica_stride = 1;
   int acc_stride = 0;
   int order_mode = CEMC_ORDER_REFERENCE;
   uint64_t seed = 0;
@@ -88,6 +88,7 @@ struct cemc_handle {
   double screen_slack = 1.0;          // testing: widen the Metropolis screening band
   bool autotune = true;               // pick the fastest kernel variant on long runs
   int tuned_sgc = -1, tuned_can = -1;  // variant chosen by the autotuner
+  int last_variant = -1;              // variant of the most recent Metropolis launch (cemc_last_variant)
   // tuning across short launches: next variant to time, ms per move of the timed ones
   int xt_next[2] = {0, 0};
   float xt_ms[2][16];
@@ -283,9 +284,20 @@ __global__ void cf_final_kernel(DeviceTables t, const double *partial, int n_job
 __global__ void pt_exchange_kernel(int n_total, const double *energies, int32_t *slot_of_replica,
                                    const double *kT_of_slot, int direction, unsigned long long seed,
                                    unsigned long long round, int32_t *rep_of_slot, double *kT_local,
-                                   int offset, int R, int32_t *n_accepted) {
+                                   int offset, int stride, int R, int32_t *n_accepted) {
+  // `energies` is in all-gather order (rank-major).  Contiguous sharding (stride 1): that is the
+  // global replica order; round-robin sharding (replica g on rank g % stride as local g / stride):
+  // replica g sits at (g % stride) * (n_total / stride) + g / stride
+  auto e_of = [&](int g) { return stride > 1 ? energies[(g % stride) * (n_total / stride) + g / stride] : energies[g]; };
   __shared__ int s_acc;
   if (threadIdx.x == 0) s_acc = 0;
+  if (direction < 0) {
+    // "up" or "down" per cycle (random.choice, parallel_tempering.py:191) from the counter
+    // stream: Philox(seed; round, replica 0, stream 3) -- identical on every rank, restartable
+    uint32_t c0 = (uint32_t)round, c1 = (uint32_t)(round >> 32), c2 = 0, c3 = 3;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    direction = (int)(c0 >> 31);
+  }
   for (int g = threadIdx.x; g < n_total; g += blockDim.x) rep_of_slot[slot_of_replica[g]] = g;
   __syncthreads();
   const int n_pairs = n_total / 2;
@@ -294,7 +306,7 @@ __global__ void pt_exchange_kernel(int n_total, const double *energies, int32_t 
     const int j = direction == 0 ? i + 1 : i - 1;
     if (j < 0 || j >= n_total) continue;
     const int r1 = rep_of_slot[i], r2 = rep_of_slot[j];
-    const double dE = __dsub_rn(energies[r1], energies[r2]);          // :139
+    const double dE = __dsub_rn(e_of(r1), e_of(r2));                  // :139
     const double b1 = __ddiv_rn(1.0, kT_of_slot[i]);                  // :140
     const double b2 = __ddiv_rn(1.0, kT_of_slot[j]);                  // :141
     const double pr = exp(__dmul_rn(__dsub_rn(b1, b2), dE));          // :143
@@ -308,8 +320,8 @@ __global__ void pt_exchange_kernel(int n_total, const double *energies, int32_t 
   __syncthreads();
   for (int s = threadIdx.x; s < n_total; s += blockDim.x) slot_of_replica[rep_of_slot[s]] = s;
   __syncthreads();
-  for (int r = threadIdx.x; r < R; r += blockDim.x) kT_local[r] = kT_of_slot[slot_of_replica[offset + r]];
-  if (threadIdx.x == 0 && n_accepted) *n_accepted = s_acc;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) kT_local[r] = kT_of_slot[slot_of_replica[offset + r * stride]];
+  if (threadIdx.x == 0 && n_accepted) { n_accepted[0] = s_acc; n_accepted[1] += s_acc; }
 }
 
 // ---------------------------------------------------------------------------
@@ -738,6 +750,13 @@ int cemc_destroy(cemc_handle *h) {
   return 0;
 }
 
+int cemc_set_replica_stride(cemc_handle *h, int stride) {
+  if (!h) return fail("null handle");
+  if (stride < 1) return fail("replica stride must be >= 1");
+  h->replica_stride = stride;
+  return 0;
+}
+
 int cemc_set_stream(cemc_handle *h, void *stream) {
   if (!h) return fail("null handle");
   CU(cudaStreamSynchronize(h->stream));
@@ -853,6 +872,15 @@ int cemc_set_ecis(cemc_handle *h, const double *eci, int per_replica) {
     src = tmp.data();
   }
   { const int rc = h2d_staged(h, h->stg_eci, h->st.eci, src, sizeof(double) * h->R * n); if (rc) return rc; }
+  // the reference always reports dot(ecis, cf) (ce_updater.cpp:236-242): with trial changes
+  // pending, the energy an undo restores must be the committed CFs under the NEW ECIs
+  for (int r = 0; r < h->R; r++)
+    if (!h->trial_log[r].empty()) {
+      energy_kernel<<<1, 32, 0, h->stream>>>(1, n, h->t.N, h->st.eci + (size_t)r * n,
+                                             h->cf_committed + (size_t)r * n, h->e_committed + r);
+      h->launches++;
+    }
+  CU(cudaGetLastError());
   return refresh_energy(h);
 }
 
@@ -914,6 +942,12 @@ int cemc_set_variant(cemc_handle *h, int sgc, int canonical) {
   if (sgc < -1 || sgc >= kNumVariants || canonical < -1 || canonical >= kNumVariants) return fail("no such kernel variant");
   h->tuned_sgc = sgc;
   h->tuned_can = canonical;
+  return 0;
+}
+
+int cemc_last_variant(cemc_handle *h, int *variant) {
+  if (!h || !variant) return fail("null argument");
+  *variant = h->last_variant;
   return 0;
 }
 
@@ -1156,7 +1190,7 @@ static int launch_spin(cemc_handle *h, const RunArgs &a) {
 
 static RunArgs run_args(cemc_handle *h, long long n_steps) {
   RunArgs a{};
-  a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset;
+  a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset; a.replica_stride = (uint32_t)h->replica_stride;
   a.observe = 1;
   a.screen_slack = h->screen_slack;
   a.phase = h->d_phase;
@@ -1211,7 +1245,17 @@ static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 
 // changed sites of a swap split over the two CTAs (canonical only).
 
 template <int MODE>
+static int launch_variant_raw(cemc_handle *h, const RunArgs &a, int v);
+
+template <int MODE>
 static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
+  const int rc = launch_variant_raw<MODE>(h, a, v);
+  if (rc == 0) h->last_variant = v;
+  return rc;
+}
+
+template <int MODE>
+static int launch_variant_raw(cemc_handle *h, const RunArgs &a, int v) {
   switch (v) {
     case 0: return launch_spin<MODE>(h, a);
     case 1: return (2 * h->R <= h->n_sms || h->cluster == 2) ? launch_batch<MODE>(h, a, 16, 2) : -1;
@@ -1315,6 +1359,9 @@ static int ensure_scratch(cemc_handle *h, long long n_steps) {
   void *old[] = {h->d_sites, h->d_news, h->d_u, h->d_acc, h->d_e};
   CU(cudaStreamSynchronize(h->stream));
   for (void *p : old) if (p) cudaFree(p);
+  // a failed allocation below must not leave dangling pointers for cemc_destroy
+  h->d_sites = nullptr; h->d_news = nullptr; h->d_u = nullptr; h->d_acc = nullptr; h->d_e = nullptr;
+  h->scratch_steps = 0;
   const size_t n = (size_t)h->R * n_steps;
   CU(cudaMalloc((void **)&h->d_sites, n * 2 * sizeof(int32_t)));
   CU(cudaMalloc((void **)&h->d_news, n * 2));
@@ -1339,13 +1386,43 @@ int cemc_replay(cemc_handle *h, int n_steps, const int32_t *sites, const int8_t 
   CU(cudaMemcpyAsync(h->d_news, news, n * 2, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_u, uniforms, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   RunArgs a{};
-  a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset;
+  a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset; a.replica_stride = (uint32_t)h->replica_stride;
   a.observe = 1;
+  a.screen_slack = h->screen_slack;
+  a.phase = h->d_phase;
   a.rp_sites = h->d_sites; a.rp_news = h->d_news; a.rp_u = h->d_u;
   a.tr_acc = h->d_acc; a.tr_e = h->d_e; a.tr_capacity = n_steps;
   drop_trials(h);
+  // The recorded trajectory runs through the SAME kernels the samplers use (spin / batch
+  // variants; the pinned one, else the default preference order) when every step has the
+  // same shape -- all one-site (SGC kernels) or all two-site (canonical kernels) -- and is
+  // in range; everything else (mixed records, bad input, background sites, pinned variant 5)
+  // takes the generic one-move-at-a-time kernel, which also reports the errors.
+  bool all1 = true, all2 = true, valid = true;
+  for (size_t q = 0; q < n && valid; q++) {
+    const int s0 = sites[2 * q], s1 = sites[2 * q + 1];
+    if (s0 < 0 || s0 >= h->t.N || s1 >= h->t.N || news[2 * q] < 0 || news[2 * q] >= h->t.S) valid = false;
+    if (s1 >= 0) { all1 = false; if (news[2 * q + 1] < 0 || news[2 * q + 1] >= h->t.S) valid = false; }
+    else all2 = false;
+  }
+  int launched = -1;
+  if (valid && (all1 || all2) && h->t.uniform_group) {
+    if (all2) { if ((rc = ensure_tracker(h))) return rc; }      // offsets read at kernel start
+    const int pinned = all1 ? h->tuned_sgc : h->tuned_can;
+    for (int k = -1; k < kNumVariants && launched < 0; k++) {
+      const int v = k < 0 ? pinned : k;
+      if (v < 0 || v == 5 || (k >= 0 && pinned >= 0)) continue;
+      if (!variant_allowed(h, v)) continue;
+      rc = all1 ? launch_variant<MODE_SGC>(h, a, v) : launch_variant<MODE_CANONICAL>(h, a, v);
+      if (rc == 0) launched = v;
+      else if (rc != -1) return rc;
+    }
+  }
   h->tracker_dirty = true;
-  if ((rc = launch_mc<MODE_REPLAY>(h, a, 0, h->R))) return rc;
+  if (launched < 0) {
+    if ((rc = launch_mc<MODE_REPLAY>(h, a, 0, h->R))) return rc;
+    h->last_variant = 5;
+  }
   if (accepted_out) CU(cudaMemcpyAsync(accepted_out, h->d_acc, n, cudaMemcpyDeviceToHost, h->stream));
   if (e_after_out) CU(cudaMemcpyAsync(e_after_out, h->d_e, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -1500,7 +1577,7 @@ int cemc_trial_changes(cemc_handle *h, int replica, int n_changes, const int32_t
     CU(cudaMemcpyAsync(dn, n2.data(), n2.size(), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(du, uu.data(), uu.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     RunArgs a{};
-    a.n_steps = n_changes; a.seed = h->seed; a.force_accept = 1; a.observe = 0;
+    a.n_steps = n_changes; a.seed = h->seed; a.force_accept = 1; a.observe = 0; a.replica_stride = 1;
     a.rp_sites = ds; a.rp_news = dn; a.rp_u = du;
     int rc = launch_mc<MODE_REPLAY>(h, a, replica, 1);   // rp arrays hold this replica only
     CU(cudaStreamSynchronize(h->stream));
@@ -1579,17 +1656,20 @@ int cemc_pt_exchange(cemc_handle *h, int n_total, const double *energies_dev,
                      int32_t *slot_of_replica_dev, const double *kT_of_slot_dev, int direction,
                      uint64_t round, int32_t *n_accepted_dev) {
   if (!h || !energies_dev || !slot_of_replica_dev || !kT_of_slot_dev) return fail("null argument");
-  if (h->replica_offset + h->R > n_total) return fail("local replicas exceed n_total");
+  if (h->replica_offset + (h->R - 1) * h->replica_stride + 1 > n_total) return fail("local replicas exceed n_total");
+  if (h->replica_stride > 1 && h->R * h->replica_stride != n_total)
+    return fail("round-robin sharding: n_total must be n_replicas * replica_stride");
   CU(cudaSetDevice(h->device));
   if (h->pt_scratch_n < n_total) {
-    if (h->pt_scratch) cudaFree(h->pt_scratch);
+    if (h->pt_scratch) { CU(cudaStreamSynchronize(h->stream)); cudaFree(h->pt_scratch); }
+    h->pt_scratch = nullptr; h->pt_scratch_n = 0;
     CU(cudaMalloc((void **)&h->pt_scratch, sizeof(int32_t) * n_total));
     h->pt_scratch_n = n_total;
   }
   h->order_dirty = true;
   pt_exchange_kernel<<<1, 256, 0, h->stream>>>(n_total, energies_dev, slot_of_replica_dev, kT_of_slot_dev,
                                                direction, h->seed, round, h->pt_scratch, h->st.kT,
-                                               h->replica_offset, h->R, n_accepted_dev);
+                                               h->replica_offset, h->replica_stride, h->R, n_accepted_dev);
   h->launches++;
   CU(cudaGetLastError());
   return 0;

@@ -332,7 +332,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       }
   }
   mbar_wait(s.mbar, 0);                        // every staged byte has landed
-  if (kCanon && n_present < 2) {               // TooFewElementsError, montecarlo.py:310
+  if (kCanon && n_present < 2 && a.rp_sites == nullptr) {   // TooFewElementsError, montecarlo.py:310
     if (tid == 0) st.status[r] = 2;
     return;
   }
@@ -370,11 +370,14 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   const bool ref_is_one = (ref == 1.0);
   const unsigned long long step0 = st.step[r];
   unsigned long long n_acc = 0;
-  const uint32_t rep_global = a.replica_offset + (uint32_t)r;
+  const uint32_t rep_global = a.replica_offset + (uint32_t)r * a.replica_stride;
   const int n_eci4 = pin_reg((n_eci + 3) & ~3);
   const int observe = pin_reg(a.observe);
   const bool tracing = (a.tr_acc != nullptr) || (a.tr_e != nullptr);
   const int n_allowed = t.n_allowed;
+  // replay of recorded proposals / uniforms: the ring is filled from
+  // rp_sites / rp_news / rp_u instead of the Philox stream; records hold sites, not list slots
+  const bool replay = (a.rp_sites != nullptr);
   // absolute slack of the Metropolis screen: rounding noise of the two ordered dot
   // products the reference subtracts, N * sum_i |eci_i| * max|cf| * O(n_eci * eps)
   double etol;
@@ -439,7 +442,19 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     philox4x32_10(c0, c1, c2, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     uint4 rec0;
     double u;
-    if (!kCanon) {
+    if (replay) {
+      // recorded step (or, past the end of the run, a harmless dummy nobody decides)
+      const long long q = first + lane;
+      int s0 = 0, s1 = kCanon ? 1 : -1, n0 = 0, n1 = 0;
+      u = 0.5;
+      if (q < a.n_steps) {
+        const size_t g = (size_t)r * (size_t)a.n_steps + (size_t)q;
+        s0 = a.rp_sites[2 * g]; n0 = a.rp_news[2 * g];
+        if (kCanon) { s1 = a.rp_sites[2 * g + 1]; n1 = a.rp_news[2 * g + 1]; }
+        u = a.rp_u[g];
+      }
+      rec0 = make_uint4((uint32_t)s0, (uint32_t)s1, (uint32_t)n0, (uint32_t)n1);
+    } else if (!kCanon) {
       const uint32_t ia = __umulhi(c0, (uint32_t)t.n_active);       // sgc_montecarlo.py:69
       rec0 = make_uint4(ia, c1, 0u, 0u);
       u = u53(c2, c3);
@@ -640,7 +655,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       sk0 = -2; sk1 = -2;
       if (lane < bmax) {
         const uint4 rk = s.ring[(int)((sdone + lane) & 127) * 2];
-        if (!kCanon) sk0 = t.active ? t.active[rk.x] : (int)rk.x;
+        if (replay) { sk0 = (int)rk.x; if (kCanon) sk1 = (int)rk.y; }
+        else if (!kCanon) sk0 = t.active ? t.active[rk.x] : (int)rk.x;
         else { sk0 = s.list[rk.x]; sk1 = s.list[rk.y]; }
       }
     };
@@ -697,7 +713,14 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           const uint4 rec0 = s.ring[(int)((sdone + b) & 127) * 2];
           int slot0 = -1, slot1 = -1;
           site[mi][1] = -1; oldv[mi][1] = 0; newv[mi][1] = 0;
-          if (!kCanon) {                          // sgc_montecarlo.py:69-75 (all species allowed)
+          if (replay) {                           // recorded sites / new species
+            site[mi][0] = (int)rec0.x; newv[mi][0] = (int)rec0.z;
+            oldv[mi][0] = s.occ[site[mi][0]];
+            if (kCanon) {
+              site[mi][1] = (int)rec0.y; newv[mi][1] = (int)rec0.w;
+              oldv[mi][1] = site[mi][1] == site[mi][0] ? newv[mi][0] : (int)s.occ[site[mi][1]];
+            }
+          } else if (!kCanon) {                   // sgc_montecarlo.py:69-75 (all species allowed)
             site[mi][0] = t.active ? t.active[rec0.x] : (int)rec0.x;
             oldv[mi][0] = s.occ[site[mi][0]];
             int rr = (int)__umulhi(rec0.y, (uint32_t)(S - 1)); rr += (rr >= oldv[mi][0]);
@@ -746,6 +769,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                 }
               }
               qv[mi][je] = s.qtab[(newv[mi][j] * sp.wq + cnt) * 32 + lane];   // n dsigma (M - 2 cnt) / den, :393-402
+              if (newv[mi][j] == oldv[mi][j]) qv[mi][je] = 0.0;   // recorded no-op change (:315): the table assumes old != new
             }
           }
         }
@@ -785,7 +809,14 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check); host: NJ*KP <= 64
       const uint4 rec0 = s.ring[(int)((sdone + b) & 127) * 2];
       int site0, site1 = -1, new0, new1 = 0, old0, old1 = 0, slot0 = -1, slot1 = -1;
-      if (!kCanon) {
+      if (replay) {                                     // recorded sites / new species
+        site0 = (int)rec0.x; new0 = (int)rec0.z;
+        old0 = s.occ[site0];
+        if (kCanon) {
+          site1 = (int)rec0.y; new1 = (int)rec0.w;
+          old1 = site1 == site0 ? new0 : (int)s.occ[site1];
+        }
+      } else if (!kCanon) {
         site0 = t.active ? t.active[rec0.x] : (int)rec0.x;
         old0 = s.occ[site0];
         if (t.allowed_identity) {                       // sgc_montecarlo.py:70-75
@@ -1146,10 +1177,10 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
             occ_of[q][pa.x] = (int8_t)pa.z;
             if (kCanon) {                      // swap_move_index_tracker.py:39-59
               occ_of[q][pa.y] = (int8_t)pa.w;
-              list_of[q][pb.z] = pa.y; list_of[q][pb.w] = pa.x;
+              if (pb.z >= 0) { list_of[q][pb.z] = pa.y; list_of[q][pb.w] = pa.x; }   // replay: no list slots
             }
           }
-          if (kCanon) { g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z); }
+          if (kCanon && pb.z >= 0) { g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z); }
         }
       }
       if (!kStateSmem) { if (C > 1) __threadfence(); else __threadfence_block(); }
@@ -1184,7 +1215,10 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           const int2 ct = *reinterpret_cast<const int2 *>(s.ctl);
           if (lane < ct.x && ((ct.y >> lane) & 1)) {
             const uint4 rk = s.ring[(int)((sdone + lane) & 127) * 2];
-            if (!kCanon) {
+            if (replay) {
+              s.occ[rk.x] = (int8_t)rk.z;
+              if (kCanon) s.occ[rk.y] = (int8_t)rk.w;
+            } else if (!kCanon) {
               const int site = t.active ? t.active[rk.x] : (int)rk.x;
               const int old = s.occ[site];
               int nw;

@@ -103,7 +103,8 @@ struct ReplicaState {    // device pointers, replica-major
 struct RunArgs {
   long long n_steps;
   unsigned long long seed;
-  uint32_t replica_offset;
+  uint32_t replica_offset;   // global id of local replica r = replica_offset + r * replica_stride
+  uint32_t replica_stride;   // (keys the Philox streams: sharding over GPUs never changes a chain)
   int force_accept;      // trial semantics: commit every step (CEUpdater::calculate)
   int observe;           // accumulate observers
   double screen_slack;   // multiplies the Metropolis screening band (testing; default 1)
@@ -392,7 +393,7 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
   const double rN = __ddiv_rn(1.0, dN);
   const unsigned long long step0 = st.step[r];
   unsigned long long n_acc = 0;
-  const uint32_t rep_global = a.replica_offset + (uint32_t)r;
+  const uint32_t rep_global = a.replica_offset + (uint32_t)r * a.replica_stride;
   const int n_allowed = t.n_allowed;
   int err = 0;
 

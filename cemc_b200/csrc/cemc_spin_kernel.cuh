@@ -59,7 +59,7 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
   if (kCanon) {
     for (int i = lane; i < N; i += 32) s_list[i] = g_list[i];
     off1 = st.off[(size_t)r * 3 + 1];
-    if (off1 == 0 || off1 == st.off[(size_t)r * 3 + 2]) {       // TooFewElementsError
+    if ((off1 == 0 || off1 == st.off[(size_t)r * 3 + 2]) && a.rp_sites == nullptr) {   // TooFewElementsError
       if (lane == 0) st.status[r] = 2;
       return;
     }
@@ -103,13 +103,15 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
   const bool ref_is_one = (ref == 1.0);
   const unsigned long long step0 = st.step[r];
   unsigned long long n_acc = 0;
-  const uint32_t rep_global = a.replica_offset + (uint32_t)r;
+  const uint32_t rep_global = a.replica_offset + (uint32_t)r * a.replica_stride;
   const int32_t *__restrict__ trans = t.trans;
   const int b0 = pin_reg(sp.b0);
   const int Kr = pin_reg(K);
   const int n_eci4 = pin_reg((n_eci + 3) & ~3);
   const int observe = pin_reg(a.observe);
   const bool tracing = (a.tr_acc != nullptr) || (a.tr_e != nullptr);
+  // replay of recorded proposals / uniforms: records hold sites, not list slots
+  const bool replay = (a.rp_sites != nullptr);
 
   // ---- this lane's items (sub-clusters), decoded once: branch-free evaluation --
   // unused neighbour slots alias slot a and are masked out of the XOR
@@ -148,7 +150,19 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
       uint32_t c0 = (uint32_t)stp, c1 = (uint32_t)(stp >> 32), c2 = rep_global, c3 = 0;
       philox4x32_10(c0, c1, c2, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       uint4 rec0, rec1;
-      if (!kCanon) {
+      if (replay) {
+        const long long q = it0 + lane;
+        int s0 = 0, s1 = kCanon ? 1 : -1, n0 = 0, n1 = 0;
+        double u = 0.5;
+        if (q < a.n_steps) {
+          const size_t g = (size_t)r * (size_t)a.n_steps + (size_t)q;
+          s0 = a.rp_sites[2 * g]; n0 = a.rp_news[2 * g];
+          if (kCanon) { s1 = a.rp_sites[2 * g + 1]; n1 = a.rp_news[2 * g + 1]; }
+          u = a.rp_u[g];
+        }
+        rec0 = make_uint4((uint32_t)s0, (uint32_t)s1, (uint32_t)n0, (uint32_t)n1);
+        rec1 = make_uint4((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u), 0u, 0u);
+      } else if (!kCanon) {
         // sgc_montecarlo.py:69: site uniform; binary: the new species is the other one
         const uint32_t ia = __umulhi(c0, (uint32_t)N);
         const double u = u53(c2, c3);
@@ -176,8 +190,15 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
       // ---- proposal -----------------------------------------------------------
       const uint4 rec0 = ring[ib_ * 2], rec1 = ring[ib_ * 2 + 1];
       const double u = __hiloint2double((int)rec1.y, (int)rec1.x);
-      int site[NJ], newsp[NJ], oldsp[NJ], slot0 = 0, slot1 = 0;
-      if (!kCanon) {
+      int site[NJ], newsp[NJ], oldsp[NJ], slot0 = -1, slot1 = -1;
+      if (replay) {
+        site[0] = (int)rec0.x; newsp[0] = (int)rec0.z;
+        oldsp[0] = s_occ[site[0]];
+        if (kCanon) {
+          site[NJ - 1] = (int)rec0.y; newsp[NJ - 1] = (int)rec0.w;
+          oldsp[NJ - 1] = site[NJ - 1] == site[0] ? newsp[0] : (int)s_occ[site[NJ - 1]];
+        }
+      } else if (!kCanon) {
         site[0] = (int)rec0.x;
         oldsp[0] = s_occ[site[0]];
         newsp[0] = 1 - oldsp[0];
@@ -208,7 +229,7 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
         const uint4 nx = ring[(ib_ + 1) * 2];
 #pragma unroll
         for (int j = 0; j < NJ; j++) {
-          const int sj = kCanon ? s_list[j ? (int)nx.y : (int)nx.x] : (int)nx.x;
+          const int sj = replay ? (j ? (int)nx.y : (int)nx.x) : kCanon ? s_list[j ? (int)nx.y : (int)nx.x] : (int)nx.x;
           psite[j] = sj;
           const int32_t *row = trans + (size_t)sj * Kr;
 #pragma unroll
@@ -248,7 +269,7 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
 #pragma unroll
         for (int q = 0; q < NR; q++) cnt += __popc(ball[j][q] & mask[q]);
         const double dl = s_qtab[(newsp[j] * sp.wq + cnt) * 32 + lane];   // n dsigma (M - 2 cnt) / den, :393-402
-        if (f_kind > 0) c = __dadd_rn(c, dl);                      // :404
+        if (f_kind > 0 && newsp[j] != oldsp[j]) c = __dadd_rn(c, dl);   // :404 (:315: a recorded no-op changes nothing)
       }
       const double p = __dmul_rn(eci_reg, c);
       double e_new = 0.0;                       // named_array.cpp:27-31; lanes >= n_eci add +0.0
@@ -268,9 +289,11 @@ spin_kernel(SpinTables sp, DeviceTables t, ReplicaState st, RunArgs a, int acc_s
           s_occ[site[0]] = (int8_t)newsp[0];
           if (kCanon) {                        // swap_move_index_tracker.py:39-59
             s_occ[site[NJ - 1]] = (int8_t)newsp[NJ - 1];
-            s_list[slot0] = site[NJ - 1]; s_list[slot1] = site[0];
-            g_loc[site[NJ - 1]] = slot0 - (newsp[NJ - 1] ? off1 : 0);
-            g_loc[site[0]] = slot1 - (newsp[0] ? off1 : 0);
+            if (slot0 >= 0) {                  // replay: no list slots
+              s_list[slot0] = site[NJ - 1]; s_list[slot1] = site[0];
+              g_loc[site[NJ - 1]] = slot0 - (newsp[NJ - 1] ? off1 : 0);
+              g_loc[site[0]] = slot1 - (newsp[0] ? off1 : 0);
+            }
           }
         }
       }

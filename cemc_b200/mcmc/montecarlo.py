@@ -195,15 +195,33 @@ class Montecarlo(object):
         self._gpu.run_canonical(n)
 
     def _sync_atoms(self):
-        """Mirror device occupations into ``atoms``; returns the net changes."""
+        """Mirror device occupations into ``atoms``; returns the net changes since the
+        previous mirror.  Only the sites that differ are touched (vectorised compare)."""
         occ = self._gpu.get_occupancy()[0]
         species = self._tables.species
+        mirror = getattr(self, "_occ_mirror", None)
+        if mirror is None or len(mirror) != len(occ):
+            mirror = self._tables.occupancy([a.symbol for a in self.atoms])
         changes = []
-        for i, atom in enumerate(self.atoms):
-            s = species[int(occ[i])]
-            if atom.symbol != s:
-                changes.append((i, atom.symbol, s))
-                atom.symbol = s
+        for i in np.nonzero(occ != mirror)[0]:
+            i = int(i)
+            changes.append((i, species[int(mirror[i])], species[int(occ[i])]))
+            self.atoms[i].symbol = species[int(occ[i])]
+        self._occ_mirror = occ.copy()
+        return changes
+
+    def _changes_for(self, obs):
+        """Net changes since THIS observer's previous call (its own snapshot: with several
+        observers on non-commensurate intervals each one still sees every change once)."""
+        occ = self._occ_mirror
+        snaps = self.__dict__.setdefault("_obs_snapshots", {})
+        old = snaps.get(id(obs))
+        if old is None:
+            old = self.__dict__.get("_occ_at_start", occ)
+        species = self._tables.species
+        changes = [(int(i), species[int(old[i])], species[int(occ[i])])
+                   for i in np.nonzero(occ != old)[0]]
+        snaps[id(obs)] = occ.copy()
         return changes
 
     def _pull_counters(self):
@@ -220,6 +238,9 @@ class Montecarlo(object):
         """n trial moves on the device, observers at their intervals."""
         done = 0
         intervals = [iv for iv, _ in self.observers if self._is_host_observer(_)]
+        if observe and intervals:
+            self._sync_atoms()
+            self._occ_at_start = self._occ_mirror       # snapshot for observers not called yet
         chunk = min([self.chunk_size] + intervals) if observe else self.chunk_size
         while done < n:
             m = min(chunk, n - done)
@@ -234,11 +255,10 @@ class Montecarlo(object):
                 due = [o for iv, o in self.observers
                        if self._is_host_observer(o) and self.current_step % iv == 0]
                 if due:
-                    self._gpu.synchronize()
-                    changes = self._sync_atoms()
+                    self._sync_atoms()                  # waits for the stream
                     self.current_energy = float(self._gpu.get_energy()[0])
                     for o in due:
-                        o(changes)
+                        o(self._changes_for(o))
         self._gpu.synchronize()
         self.current_energy = float(self._gpu.get_energy()[0])
 

@@ -2,9 +2,19 @@
 (/root/reference/cemc/mcmc/parallel_tempering.py:6-191), with every replica
 advanced by ONE kernel launch per cycle and the exchange sweep on the device.
 
+The round loop is sync-free: a cycle enqueues, on ONE CUDA stream,
+
+    leg kernel (cemc_run_canonical)  ->  all-gather of the local energies (NCCL over
+    NVLink, only when sharded)  ->  exchange kernel (cemc_pt_exchange)
+
+and the host never waits: the slot map, the per-cycle direction (drawn on the device
+from the counter stream) and the accepted-exchange count stay on the device and are
+read back once when ``run`` returns.  ``timing=True`` brackets the two halves of every
+cycle with CUDA events (no synchronisation either) for ``last_timing``.
+
 Differences from the reference (DESIGN.md "Parallel tempering"):
 
-* replicas run concurrently (one CTA / warp each) instead of sequentially;
+* replicas run concurrently (one CTA / cluster each) instead of sequentially;
 * an accepted exchange permutes the temperature<->replica map; the reference
   copies whole configurations site by site (:146-151, up to 2N update_cf);
 * the exchange uses the true energies.  The reference compares
@@ -13,8 +23,13 @@ Differences from the reference (DESIGN.md "Parallel tempering"):
   skews its criterion by the difference of the two biases;
 * the temperature ladder can be given explicitly (``temperatures=``); the
   reference's bisection search (:47-136) is kept as ``_init_temperature_scheme``;
-* replicas can be sharded over ranks (torch.distributed); the only collective
-  is the all-gather of the energies.
+* replicas can be sharded over ranks (torch.distributed), round-robin
+  (replica g on GPU ``g mod world``) so that every GPU holds
+  every world-th temperature; the only collective is the all-gather of the
+  energies.  Chains are keyed by their global replica id: the sharded run is
+  the single-process run, bit for bit.
+* only the canonical sampler is supported (the reference's class effectively
+  is canonical-only as well: it never forwards chemical potentials).
 """
 from __future__ import annotations
 
@@ -31,6 +46,11 @@ class ParallelTempering(object):
                  target_accept=0.2, seed=None, device=None):
         if not isinstance(mc_obj, Montecarlo):
             raise TypeError("mc_obj has to be of type Montecarlo!")
+        if getattr(mc_obj, "name", "MonteCarlo") != "MonteCarlo":
+            # chemical potentials / restricted symbol lists of an SGC sampler would be
+            # silently dropped (the replicas are built from the calculator's ECIs)
+            raise TypeError("ParallelTempering supports the canonical Montecarlo "
+                            "sampler only (got {})".format(mc_obj.name))
         self.mc = mc_obj
         mc_obj.T = Tmax
         self.natoms = len(mc_obj.atoms)
@@ -43,11 +63,18 @@ class ParallelTempering(object):
             temperatures = self._init_temperature_scheme(target_accept)
         self._temps = [float(T) for T in temperatures]
         self.n_total = len(self._temps)
-        self.offset, self.R = parallel.shard_range(self.n_total, self.rank, self.world)
+        self.offset, self.stride, self.R = parallel.shard_round_robin(
+            self.n_total, self.rank, self.world)
         calc = mc_obj.atoms.get_calculator()
         self.tables = calc.updater.tables
+        import torch
+        self._torch = torch
+        self._dev = torch.device("cuda", self.device)
+        # one stream for the leg kernels, the NCCL all-gather and the exchange kernel
+        self._stream = torch.cuda.Stream(self._dev)
         self.gpu = BatchedCEUpdater(self.tables, self.R, device=self.device,
-                                    replica_offset=self.offset)
+                                    replica_offset=self.offset, replica_stride=self.stride,
+                                    stream=self._stream.cuda_stream)
         occ = calc.updater.batch.get_occupancy()
         cf = calc.updater.batch.get_cf()
         self.gpu.set_occupancy(np.repeat(occ, self.R, axis=0))
@@ -56,10 +83,15 @@ class ParallelTempering(object):
         self.gpu.seed(self.seed)
         self.kT_of_slot = np.array(self._temps) * KB        # slot 0 = Tmax
         self.slot_of_replica = np.arange(self.n_total, dtype=np.int32)
-        self.gpu.set_kT(self.kT_of_slot[self.offset:self.offset + self.R])
-        self.round = 0
-        self.num_accepted_exchanges = 0
-        self._dev = None
+        self.gpu.set_kT(self.kT_of_slot[self.global_ids()])
+        self.round = 0                    # exchange cycles done: counter of the direction /
+        self.num_accepted_exchanges = 0   # uniform streams, advances across run() calls
+        self.last_timing = None
+        self._bufs = None
+
+    def global_ids(self):
+        """Global replica ids of the local replicas."""
+        return self.offset + self.stride * np.arange(self.R)
 
     def _log(self, msg):
         if self.rank == 0:
@@ -124,56 +156,86 @@ class ParallelTempering(object):
 
     # ---- exchange ------------------------------------------------------------------
     def _device_buffers(self):
-        if self._dev is None:
-            import torch
-            dev = torch.device("cuda", self.device)
-            self._dev = dict(
-                torch=torch, dev=dev,
+        if self._bufs is None:
+            torch, dev = self._torch, self._dev
+            self._bufs = dict(
                 slots=torch.from_numpy(self.slot_of_replica.copy()).to(dev),
                 kts=torch.from_numpy(self.kT_of_slot.copy()).to(dev),
                 e_all=torch.empty(self.n_total, dtype=torch.float64, device=dev),
-                n_acc=torch.zeros(1, dtype=torch.int32, device=dev))
-        return self._dev
+                # the local energies never leave the device: alias the updater's buffer
+                e_loc=torch.as_tensor(parallel.DeviceArrayF64(self.gpu.energy_dev_ptr(), self.R),
+                                      device=dev),
+                n_acc=torch.zeros(2, dtype=torch.int32, device=dev))
+        return self._bufs
 
-    def _perform_exchange_move(self, direction="up"):
-        """One exchange sweep (parallel_tempering.py:153-175), on the device."""
-        d = self._device_buffers()
-        torch = d["torch"]
-        self.gpu.synchronize()
+    def _enqueue_exchange(self, direction):
+        """All-gather + exchange sweep of one cycle, enqueued on the stream (no host sync).
+        direction: 0 "up", 1 "down", -1 drawn on the device from (seed, round)."""
+        b = self._device_buffers()
         if self.world > 1:
             import torch.distributed as dist
-            # the local energies never leave the device: wrap the updater's buffer
-            e_loc = torch.as_tensor(parallel.DeviceArrayF64(self.gpu.energy_dev_ptr(), self.gpu.R),
-                                    device=d["dev"])
-            dist.all_gather_into_tensor(d["e_all"], e_loc)      # NCCL over NVLink
-            e_ptr = d["e_all"].data_ptr()
+            dist.all_gather_into_tensor(b["e_all"], b["e_loc"])      # NCCL over NVLink, stream-ordered
+            e_ptr = b["e_all"].data_ptr()
         else:
-            e_ptr = self.gpu.energy_dev_ptr()
-        torch.cuda.synchronize(d["dev"])
-        self.gpu.pt_exchange(self.n_total, e_ptr, d["slots"].data_ptr(), d["kts"].data_ptr(),
-                             0 if direction == "up" else 1, self.round, d["n_acc"].data_ptr())
-        self.gpu.synchronize()
-        self.slot_of_replica = d["slots"].cpu().numpy()
-        n_acc = int(d["n_acc"].item())
-        self.num_accepted_exchanges += n_acc
+            e_ptr = b["e_loc"].data_ptr()
+        self.gpu.pt_exchange(self.n_total, e_ptr, b["slots"].data_ptr(), b["kts"].data_ptr(),
+                             direction, self.round, b["n_acc"].data_ptr())
         self.round += 1
-        return n_acc
 
-    def run(self, mc_args={}, num_exchange_cycles=10):
-        """``num_exchange_cycles`` x (``steps`` moves on every replica, then
-        one exchange sweep) (parallel_tempering.py:177-191)."""
+    def _read_back(self):
+        b = self._device_buffers()
+        self._stream.synchronize()
+        self.slot_of_replica = b["slots"].cpu().numpy()
+        self.num_accepted_exchanges = int(b["n_acc"][1].item())
+
+    def _perform_exchange_move(self, direction="up"):
+        """One exchange sweep (parallel_tempering.py:153-175), on the device; returns the
+        number of accepted exchanges (this entry point reads the result back)."""
+        torch = self._torch
+        with torch.cuda.stream(self._stream):
+            self._enqueue_exchange(0 if direction == "up" else 1)
+        self._read_back()
+        return int(self._bufs["n_acc"][0].item())
+
+    def run(self, mc_args={}, num_exchange_cycles=10, timing=False):
+        """``num_exchange_cycles`` x (``steps`` moves on every replica, then one exchange
+        sweep) (parallel_tempering.py:177-191).  Only ``mc_args["steps"]`` is used: the
+        replicas share the sampler's seed / ECIs, and equilibration or observer
+        arguments of ``runMC`` do not apply to a leg."""
+        unknown = set(mc_args) - {"steps", "equil", "mode"}
+        if unknown:
+            raise ValueError("mc_args not supported by the GPU parallel tempering: "
+                             + ", ".join(sorted(unknown)))
         steps = int(mc_args.get("steps", 10 * self.natoms))
-        rng = np.random.RandomState(self.seed & 0x7fffffff)   # same direction on every rank
-        for _ in range(num_exchange_cycles):
-            self.gpu.run_canonical(steps) if self.mc.name == "MonteCarlo" \
-                else self.gpu.run_sgc(steps)
-            direction = "up" if rng.randint(0, 2) == 0 else "down"
-            self._perform_exchange_move(direction=direction)
+        torch = self._torch
+        ev = []
+        with torch.cuda.stream(self._stream):
+            for _ in range(num_exchange_cycles):
+                if timing:
+                    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    e0.record(self._stream)
+                self.gpu.run_canonical(steps)
+                if timing:
+                    e1.record(self._stream)
+                # the direction of cycle k is a pure function of (seed, k): identical on every
+                # rank, and a sequence of run(num_exchange_cycles=1) calls walks the same ladder
+                self._enqueue_exchange(-1)
+                if timing:
+                    e2.record(self._stream)
+                    ev.append((e0, e1, e2))
+        self._read_back()
+        if timing:
+            leg = sum(a.elapsed_time(b) for a, b, _ in ev)
+            exch = sum(b.elapsed_time(c) for _, b, c in ev)
+            self.last_timing = dict(cycles=num_exchange_cycles, steps_per_leg=steps,
+                                    leg_ms=leg, exchange_ms=exch)
 
     # ---- results -------------------------------------------------------------------
     def temperature_of_replica(self):
         return np.array(self._temps)[self.slot_of_replica]
 
     def gather_energies(self):
-        return parallel.all_gather_array(self.gpu.get_energy(), self.world,
-                                         None if self.world == 1 else "cuda:%d" % self.device)
+        """Energies of all replicas in global replica order."""
+        e = parallel.all_gather_array(self.gpu.get_energy(), self.world,
+                                      None if self.world == 1 else "cuda:%d" % self.device)
+        return e[parallel.gather_index(self.n_total, self.world, self.stride)]

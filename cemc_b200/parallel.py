@@ -34,6 +34,25 @@ def shard_range(n_total: int, rank: int, world: int):
     return rank * per, per
 
 
+def shard_round_robin(n_total: int, rank: int, world: int):
+    """Round-robin sharding (replica g on GPU ``g mod world``): returns
+    ``(offset, stride, n_local)``; local replica r is global replica ``offset + r * stride``.
+    Used by parallel tempering so that every GPU holds every ``world``-th temperature
+    of the ladder (hot chains accept more and run slower: a contiguous block would leave
+    one GPU with all of them)."""
+    if n_total % world:
+        raise ValueError("the number of replicas must be divisible by the number of ranks")
+    return rank, world, n_total // world
+
+
+def gather_index(n_total: int, world: int, stride: int) -> np.ndarray:
+    """Position of global replica g in an all-gather (rank-major) of per-rank arrays."""
+    g = np.arange(n_total)
+    if stride <= 1:
+        return g
+    return (g % stride) * (n_total // stride) + g // stride
+
+
 def all_gather_array(local: np.ndarray, world: int, device=None):
     """All-gather equally sized arrays; returns [world * n, ...]."""
     if world == 1:

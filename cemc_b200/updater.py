@@ -28,7 +28,7 @@ class BatchedCEUpdater(object):
     """R independent chains on one CUDA device."""
 
     def __init__(self, tables: FlatTables, n_replicas: int, device: int = 0,
-                 replica_offset: int = 0, stream=None):
+                 replica_offset: int = 0, stream=None, replica_stride: int = 1):
         self.lib = _lib.load()
         self.tables = tables
         self.R = int(n_replicas)
@@ -43,6 +43,9 @@ class BatchedCEUpdater(object):
         _lib.check(self.lib.cemc_create(C.byref(self._struct), self.R,
                                         self.replica_offset, self.device,
                                         stream, C.byref(self._h)))
+        self.replica_stride = int(replica_stride)
+        if self.replica_stride != 1:
+            _lib.check(self.lib.cemc_set_replica_stride(self._h, self.replica_stride))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -180,6 +183,12 @@ class BatchedCEUpdater(object):
         a, b = C.c_int32(-1), C.c_int32(-1)
         _lib.check(self.lib.cemc_get_variant(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def last_variant(self) -> int:
+        """Kernel variant of the most recent Metropolis launch (-1: none)."""
+        v = C.c_int32(-1)
+        _lib.check(self.lib.cemc_last_variant(self._h, C.byref(v)))
+        return v.value
 
     def set_cluster(self, c: int):
         _lib.check(self.lib.cemc_set_cluster(self._h, int(c)))

@@ -111,6 +111,11 @@ int  cemc_version(void);
 int cemc_create(const cemc_tables *tables, int n_replicas, int replica_offset,
                 int device, void *stream, cemc_handle **out);
 int cemc_destroy(cemc_handle *h);
+/* Round-robin sharding (replica g on GPU g mod n_gpus): the global id of
+ * local replica r is replica_offset + r * stride (default stride 1 = a contiguous block).
+ * With stride > 1 cemc_pt_exchange expects the gathered energies in all-gather (rank-major)
+ * order and n_total == n_replicas * stride.                                              */
+int cemc_set_replica_stride(cemc_handle *h, int stride);
 int cemc_set_stream(cemc_handle *h, void *stream);
 int cemc_synchronize(cemc_handle *h);
 int cemc_set_order_mode(cemc_handle *h, int mode);
@@ -127,6 +132,8 @@ int cemc_set_batch(cemc_handle *h, int b);
  * (4,1), 5 mc_kernel, -1 not tuned yet.                                        */
 int cemc_set_autotune(cemc_handle *h, int on);
 int cemc_get_variant(cemc_handle *h, int *sgc, int *canonical);
+/* variant of the most recent Metropolis launch (run_sgc / run_canonical / replay), -1 = none */
+int cemc_last_variant(cemc_handle *h, int *variant);
 /* pin the variant per sampler (-1 = let the autotuner decide); inapplicable variants
  * fall back to the default preference order                                     */
 int cemc_set_variant(cemc_handle *h, int sgc, int canonical);
@@ -201,7 +208,10 @@ int cemc_clear_history(cemc_handle *h, int replica);
 
 /* ---- batched Metropolis ---- */
 /* Replay recorded proposals + uniforms.  sites[.][1] < 0
- * marks a one-site (SGC) step.  accepted_out / e_after_out may be NULL.       */
+ * marks a one-site (SGC) step.  accepted_out / e_after_out may be NULL.  When all
+ * steps are one-site or all are two-site the trajectory runs through the samplers'
+ * own kernels (the variant pinned with cemc_set_variant, else the default order;
+ * cemc_last_variant tells which); mixed records use the generic kernel.        */
 int cemc_replay(cemc_handle *h, int n_steps,
                 const int32_t *sites /*[R][n_steps][2]*/,
                 const int8_t *new_species /*[R][n_steps][2]*/,
@@ -224,9 +234,14 @@ int cemc_get_accumulators(cemc_handle *h, double *acc /*[R][CEMC_ACC_STRIDE(D)]*
 /* ---- parallel tempering ---- */
 /* One exchange sweep over temperature slots.  slot_of_replica[g] for all
  * n_total global replicas and the matching energies (device pointer, e.g. the
- * output of an NCCL all-gather).  direction 0 = "up", 1 = "down".  Updates
+ * output of an NCCL all-gather).  direction 0 = "up", 1 = "down", -1 = drawn on
+ * the device from Philox(seed; round, stream 3) (random.choice per cycle,
+ * parallel_tempering.py:191; the same on every rank).  Updates
  * slot_of_replica_dev in place (identically on every rank) and the kT of the
- * local replicas from kT_of_slot_dev.                                        */
+ * local replicas from kT_of_slot_dev.  n_accepted_dev (may be NULL) points at
+ * int32[2]: [0] = exchanges accepted by this sweep, [1] += the same (running
+ * total, so a sync-free round loop reads it back once at the end).  The call
+ * only enqueues work on the handle's stream.                                 */
 int cemc_pt_exchange(cemc_handle *h, int n_total, const double *energies_dev,
                      int32_t *slot_of_replica_dev, const double *kT_of_slot_dev,
                      int direction, uint64_t round, int32_t *n_accepted_dev);

@@ -6,7 +6,7 @@
  * __graft_entry__.smoke() and in bench.py's cpu_baseline leg.  Nothing under
  * cemc_b200/ may link or call this file.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py drives this file
+ * Parity status: PINNED.  tests/test_oracle_cpu.py::test_oracle_vs_compiled_reference drives this file
  * and the reference's own compiled CEUpdater (oracle/_ref, built from
  * /root/reference by oracle/build_ref.sh) on the same inputs and requires
  * bit-identical CFs / energies / accept sequences; the committed fixtures in
@@ -389,6 +389,15 @@ int oracle_run_canonical(const cemc_tables *t, const double *eci, int8_t *occ,
  * with _accept_probability :138-144.  Slots are temperature indices; instead
  * of copying configurations (:146-151) the slot<->replica map is permuted.
  * Uniforms come from Philox(seed, round, slot pair index, stream 2). */
+/* direction of one exchange cycle, 0 = "up", 1 = "down" (random.choice per cycle,
+ * parallel_tempering.py:191), from this project's counter stream (stream 3) */
+int oracle_pt_direction(uint64_t seed, uint64_t round)
+{
+  uint32_t w[4];
+  oracle_philox(seed, round, 0, 3, w);
+  return (int)(w[0] >> 31);
+}
+
 int oracle_pt_exchange(int n_total, const double *energies /*by replica*/,
                        int32_t *slot_of_replica, const double *kT_of_slot,
                        int direction, uint64_t seed, uint64_t round)

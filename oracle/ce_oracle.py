@@ -199,6 +199,11 @@ def philox(seed, step, replica, stream):
     return [int(x) for x in out]
 
 
+def pt_direction(seed, rnd):
+    """0 = "up", 1 = "down": the per-cycle direction of the device-side round loop."""
+    return int(_lib().oracle_pt_direction(C.c_uint64(seed), C.c_uint64(rnd)))
+
+
 def pt_exchange(energies, slot_of_replica, kT_of_slot, direction, seed, rnd):
     e = np.ascontiguousarray(energies, dtype=np.float64)
     slots = np.array(slot_of_replica, dtype=np.int32).copy()

@@ -32,10 +32,9 @@ if rank == 0:
     cf0 = calc.updater.batch.get_cf()[0]
     chains = [OracleChain(ft, ft.occupancy(symbols), cf=cf0, kT=temps[r] * KB, seed=7, replica=r) for r in range(n_total)]
     slots = np.arange(n_total, dtype=np.int32); kts = np.array(temps) * KB
-    rng = np.random.RandomState(7)
     for rnd in range(8):
         for c in chains: c.run_canonical(500)
-        slots, _ = ce_oracle.pt_exchange([c.e for c in chains], slots, kts, 0 if rng.randint(0, 2) == 0 else 1, 7, rnd)
+        slots, _ = ce_oracle.pt_exchange([c.e for c in chains], slots, kts, ce_oracle.pt_direction(7, rnd), 7, rnd)
         for r, c in enumerate(chains): c.kT = float(kts[slots[r]])
     ok = np.array_equal(slots, pt.slot_of_replica) and np.array_equal(e_all, [c.e for c in chains])
     print("PT sharded over %d GPU(s): slots+energies identical to oracle: %s; accepted exchanges %d" % (world, ok, pt.num_accepted_exchanges))

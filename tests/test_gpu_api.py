@@ -200,6 +200,9 @@ def test_parameter_sweep_matches_oracle(cuda_device, tmp_path):
 
 
 def test_parallel_tempering_single_gpu(cuda_device, tmp_path):
+    """Sync-free round loop: legs, device-drawn directions and exchange sweeps match the oracle;
+    a sequence of run(num_exchange_cycles=1) calls continues the same direction / uniform
+    streams (the reference's random.choice advances across calls, parallel_tempering.py:191)."""
     st, eci, symbols, ft, atoms, calc = make_ce(TERNARY, seed=6)
     cf0 = calc.updater.batch.get_cf()[0]
     temps = list(np.geomspace(1500.0, 100.0, 8))
@@ -207,26 +210,40 @@ def test_parallel_tempering_single_gpu(cuda_device, tmp_path):
     pt = ParallelTempering(mc, Tmax=1500.0, Tmin=100.0, temperatures=temps,
                            temp_scheme_file=str(tmp_path / "scheme.csv"))
     assert pt.temperature_scheme == temps
-    pt.run(mc_args={"steps": 300}, num_exchange_cycles=6)
+    pt.run(mc_args={"steps": 300}, num_exchange_cycles=4, timing=True)
+    assert pt.last_timing["cycles"] == 4 and pt.last_timing["leg_ms"] > 0.0
+    for _ in range(4):
+        pt.run(mc_args={"steps": 300}, num_exchange_cycles=1)
     chains = [OracleChain(ft, ft.occupancy(symbols), cf=cf0, kT=temps[r] * KB, seed=99, replica=r)
               for r in range(8)]
     slots = np.arange(8, dtype=np.int32)
     kts = np.array(temps) * KB
-    rng = np.random.RandomState(99)
     total = 0
-    for rnd in range(6):
+    dirs = []
+    for rnd in range(8):
         for c in chains:
             c.run_canonical(300)
-        direction = 0 if rng.randint(0, 2) == 0 else 1
+        direction = ce_oracle.pt_direction(99, rnd)
+        dirs.append(direction)
         slots, n_acc = ce_oracle.pt_exchange([c.e for c in chains], slots, kts, direction, 99, rnd)
         total += n_acc
         for r, c in enumerate(chains):
             c.kT = float(kts[slots[r]])
+    assert len(set(dirs)) == 2          # both "up" and "down" sweeps occurred
     assert np.array_equal(pt.slot_of_replica, slots)
     assert pt.num_accepted_exchanges == total
     assert np.array_equal(pt.gpu.get_energy(), [c.e for c in chains])
     assert np.array_equal(pt.gpu.get_occupancy(), np.stack([c.occ for c in chains]))
     assert sorted(pt.temperature_of_replica()) == sorted(temps)
+    with pytest.raises(ValueError):
+        pt.run(mc_args={"steps": 10, "bogus": 1}, num_exchange_cycles=1)
+
+
+def test_parallel_tempering_rejects_sgc(cuda_device, tmp_path):
+    st, eci, symbols, ft, atoms, calc = make_ce(BINARY, seed=6)
+    sgc = SGCMonteCarlo(atoms, 500.0, symbols=["Al", "Mg"], seed=1)
+    with pytest.raises(TypeError):
+        ParallelTempering(sgc, temperatures=[800.0, 400.0], temp_scheme_file=str(tmp_path / "s.csv"))
 
 
 def test_checkpoint_roundtrip(cuda_device, tmp_path):

@@ -5,7 +5,7 @@ occupations, energies and CFs (reference operation order, fp64)."""
 import numpy as np
 import pytest
 
-from cases import BINARY, GOLDEN, TERNARY, build, load_golden
+from cases import BINARY, GOLDEN, GOLDEN_WORKLOADS, TERNARY, build, load_golden, load_golden_workload
 from cemc_b200.updater import BatchedCEUpdater, PyCEUpdater
 from cemc_b200 import synthetic as syn
 from oracle import ce_oracle
@@ -40,16 +40,37 @@ def assert_state_equal(gpu, chains):
         assert e[r] == c.e, "energy differs, replica %d" % r
 
 
+# kernel variants the recorded trajectories are put through: 0 spin kernel (warp per replica),
+# 1 / 2 / 3 / 4 batch kernel (16 warps, cluster of 2) / (16,1) / (8,1) / (4,1), 5 generic
+# one-move-at-a-time kernel, 8 batch kernel with site split (swaps)
+REPLAY_VARIANTS = [0, 1, 2, 3, 4, 5, 8]
+
+
+def _pin_replay_variant(gpu, variant, mode):
+    """Pin the kernel variant of cemc_replay; skip when it does not apply to this system."""
+    ev = gpu.get_batch_eval()
+    if variant == 0 and ev != 1:
+        pytest.skip("spin kernel: binary +-1 basis only")
+    if variant == 8 and mode != "canonical":
+        pytest.skip("site split: swaps only")
+    gpu.set_variant(variant, variant)
+
+
+@pytest.mark.parametrize("variant", REPLAY_VARIANTS)
 @pytest.mark.parametrize("name", GOLDEN)
-def test_replay_golden(cuda_device, name):
-    """Replay of trajectories recorded from the reference's own C++ CEUpdater."""
+def test_replay_golden(cuda_device, name, variant):
+    """Replay of trajectories recorded from the reference's own C++ CEUpdater, through every
+    kernel family the samplers time."""
     meta, st, ft, z = load_golden(name)
     gpu = BatchedCEUpdater(ft, 1)
     gpu.set_occupancy(ft.occupancy(meta["symbols0"])[None])
     gpu.set_cf(z["cf0"][None])
     gpu.set_kT([meta["kT"]])
     assert gpu.get_energy()[0] == float(z["e0"])
+    _pin_replay_variant(gpu, variant, meta["mode"])
     acc, e_after = gpu.replay(z["sites"][None], z["news"][None], z["u"][None])
+    if ft.K <= 31 or variant in (0, 2, 3, 5):      # K = 42 (config 1): spin / wide batch / generic kernels
+        assert gpu.last_variant() == variant
     assert np.array_equal(acc[0], z["accepted"])
     assert np.array_equal(e_after[0], z["e_after"])
     assert np.array_equal(gpu.get_cf()[0], z["cf_final"])
@@ -137,6 +158,67 @@ def test_per_replica_ecis_chemical_potential(cuda_device):
         assert np.array_equal(accs[r], c.acc)
     # different mu -> different compositions
     assert len({float(a[3]) for a in accs}) == R
+
+
+@pytest.mark.parametrize("variant", REPLAY_VARIANTS)
+@pytest.mark.parametrize("name", GOLDEN_WORKLOADS)
+def test_replay_golden_baseline_sizes(cuda_device, name, variant):
+    """BASELINE-size trajectories (replicas of bench configs[1], configs[2] and the north-star
+    Al-Mg-Si SGC sweep, recorded from the compiled reference) through the timed kernels:
+    accept sequence, energy after every step, final CFs and occupations bit-identical."""
+    meta, ft, z = load_golden_workload(name)
+    R = len(meta["replicas"])
+    gpu = BatchedCEUpdater(ft, R)
+    gpu.set_occupancy(z["occ0"])
+    gpu.set_cf(z["cf0"])
+    gpu.set_ecis(z["eci"])
+    gpu.set_kT(z["kT"])
+    assert np.array_equal(gpu.get_energy(), z["e0"])
+    _pin_replay_variant(gpu, variant, meta["mode"])
+    acc, e_after = gpu.replay(z["sites"], z["news"], z["u"])
+    assert gpu.last_variant() == variant
+    assert np.array_equal(acc, z["accepted"])
+    assert np.array_equal(e_after, z["e_after"])
+    assert np.array_equal(gpu.get_cf(), z["cf_final"])
+    assert np.array_equal(gpu.get_occupancy(), z["occ_final"])
+    steps, n_acc = gpu.get_counters()
+    assert np.all(steps == z["u"].shape[1]) and np.array_equal(n_acc, z["accepted"].sum(axis=1))
+    # the device's own CFs of the recorded start configuration equal the reference's
+    gpu.set_occupancy(z["occ0"])
+    gpu.recompute_cf()
+    np.testing.assert_allclose(gpu.get_cf(), z["cf0"], rtol=0, atol=2e-14)
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 2, 3])
+def test_replay_edge_cases_batch_kernels(cuda_device, variant):
+    """No-op changes (ce_updater.cpp:315), neighbouring swap partners (A.2) and the same site
+    twice, as uniform one-site / two-site records so that they run on the spin / batch kernels."""
+    for case in (BINARY, TERNARY):
+        st, eci, symbols, ft = build(**case)
+        occ = ft.occupancy(symbols)
+        S = ft.S
+        nb = int(ft.trans[5, 0])
+        other = [s for s in range(ft.N) if occ[s] != occ[5] and s != nb][0]
+        two = np.array([[5, nb], [5, other], [7, 7], [nb, 5], [11, 12], [5, nb], [3, 3]], dtype=np.int32)
+        two_new = np.array([[occ[nb], occ[5]], [occ[other], occ[5]], [(occ[7] + 1) % S, (occ[7] + 1) % S],
+                            [occ[nb], occ[nb]], [occ[12], occ[11]], [occ[5], occ[nb]],
+                            [(occ[3] + 1) % S, occ[3]]], dtype=np.int8)
+        one = np.array([[5, -1], [9, -1], [5, -1], [nb, -1], [9, -1], [5, -1]], dtype=np.int32)
+        one_new = np.array([[occ[5], 0], [(occ[9] + 1) % S, 0], [(occ[5] + 1) % S, 0], [occ[nb], 0],
+                            [(occ[9] + 1) % S, 0], [occ[5], 0]], dtype=np.int8)
+        for sites, news in ((one, one_new), (two, two_new)):
+            u = np.linspace(0.05, 0.95, len(sites))
+            gpu, chains = make_pair(ft, [symbols], [0.05], seed=0)
+            if variant >= 0:
+                if variant == 0 and gpu.get_batch_eval() != 1:
+                    continue
+                gpu.set_variant(variant, variant)
+            acc, e = gpu.replay(sites[None], news[None], u[None])
+            assert gpu.last_variant() != 5           # a sampler kernel took it
+            acc_o, e_o = chains[0].replay(sites, news, u)
+            assert np.array_equal(acc[0], acc_o)
+            assert np.array_equal(e[0], e_o)
+            assert_state_equal(gpu, chains)
 
 
 def test_replay_edge_cases(cuda_device):
@@ -266,8 +348,9 @@ def test_pt_exchange_matches_oracle(cuda_device):
     dev = torch.device("cuda:0")
     slots = torch.arange(R, dtype=torch.int32, device=dev)
     kt_slot = torch.tensor(kts, dtype=torch.float64, device=dev)
-    n_acc = torch.zeros(1, dtype=torch.int32, device=dev)
+    n_acc = torch.zeros(2, dtype=torch.int32, device=dev)    # [this sweep, running total]
     slots_o = np.arange(R, dtype=np.int32)
+    total = 0
     for rnd in range(6):
         gpu.run_canonical(200)
         gpu.synchronize()
@@ -280,7 +363,8 @@ def test_pt_exchange_matches_oracle(cuda_device):
         slots_o, n_o = ce_oracle.pt_exchange([c.e for c in chains], slots_o, kts,
                                              rnd % 2, 4242, rnd)
         assert np.array_equal(slots.cpu().numpy(), slots_o)
-        assert int(n_acc.item()) == n_o
+        total += n_o
+        assert n_acc.cpu().tolist() == [n_o, total]
         for r, c in enumerate(chains):
             c.kT = float(kts[slots_o[r]])
         assert np.array_equal(gpu.get_kT(), np.array([c.kT for c in chains]))

@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from cases import BINARY, GOLDEN, TERNARY, build, load_golden
+from cases import BINARY, GOLDEN, GOLDEN_WORKLOADS, TERNARY, build, load_golden, load_golden_workload
 from cemc_b200 import synthetic as syn
 from cemc_b200.tables import FlatTables, SelfInteractionError
 from oracle import ce_oracle, ref_driver
@@ -29,6 +29,28 @@ def test_oracle_matches_golden(name):
     assert np.array_equal(e_after, z["e_after"])
     assert np.array_equal(oc.cf, z["cf_final"])
     assert np.array_equal(oc.occ, z["occ_final"])
+
+
+@pytest.mark.parametrize("name", GOLDEN_WORKLOADS)
+def test_oracle_matches_golden_baseline_sizes(name):
+    """BASELINE-size fixtures (replicas of the bench workloads, recorded from the compiled
+    reference): the oracle agrees bit for bit, and its Philox chain regenerates the proposals."""
+    meta, ft, z = load_golden_workload(name)
+    for r, g in enumerate(meta["replicas"]):
+        oc = OracleChain(ft, z["occ0"][r], cf=z["cf0"][r], kT=float(z["kT"][r]), eci=z["eci"][r],
+                         seed=2024, replica=g)
+        assert oc.e == float(z["e0"][r])
+        acc, e_after = oc.replay(z["sites"][r], z["news"][r], z["u"][r])
+        assert np.array_equal(acc, z["accepted"][r])
+        assert np.array_equal(e_after, z["e_after"][r])
+        assert np.array_equal(oc.cf, z["cf_final"][r])
+        assert np.array_equal(oc.occ, z["occ_final"][r])
+        oc2 = OracleChain(ft, z["occ0"][r], cf=z["cf0"][r], kT=float(z["kT"][r]), eci=z["eci"][r],
+                          seed=2024, replica=g)
+        n = z["u"].shape[1]
+        tr = oc2.run_canonical(n, trace=True) if meta["mode"] == "canonical" else oc2.run_sgc(n, trace=True)
+        assert np.array_equal(tr[0], z["sites"][r]) and np.array_equal(tr[2], z["u"][r])
+        assert np.array_equal(tr[3], z["accepted"][r])
 
 
 @pytest.mark.parametrize("name", GOLDEN[:2])

@@ -32,7 +32,7 @@ def _chains(ft, symbols, kts, ids):
     return [OracleChain(ft, ft.occupancy(symbols), kT=kts[g], seed=SEED, replica=g) for g in ids]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, layout="contiguous"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
@@ -40,30 +40,38 @@ def _worker(rank, world, port, q):
     st, eci, symbols, ft = build(**BINARY)
     kts = np.geomspace(0.08, 0.01, N_TOTAL)
     r, w, _ = parallel.dist_info()
-    off, n_loc = parallel.shard_range(N_TOTAL, r, w)
-    chains = _chains(ft, symbols, kts, range(off, off + n_loc))
+    if layout == "contiguous":
+        off, n_loc = parallel.shard_range(N_TOTAL, r, w)
+        stride = 1
+    else:       # replica g on rank g mod world (what ParallelTempering uses)
+        off, stride, n_loc = parallel.shard_round_robin(N_TOTAL, r, w)
+    ids = [off + i * stride for i in range(n_loc)]
+    order = parallel.gather_index(N_TOTAL, w, stride)      # all-gather (rank-major) -> global order
+    chains = _chains(ft, symbols, kts, ids)
     slots = np.arange(N_TOTAL, dtype=np.int32)
     for rnd in range(5):
         for c in chains:
             c.run_canonical(150)
-        e_all = parallel.all_gather_array(np.array([c.e for c in chains]), w)
-        slots, _ = parallel.exchange_sweep(e_all, slots, kts, rnd % 2, SEED, rnd, _uniform)
-        for i, c in enumerate(chains):
-            c.kT = float(kts[slots[off + i]])
-    acc_all = parallel.all_gather_array(np.stack([c.acc for c in chains]), w)
-    e_all = parallel.all_gather_array(np.array([c.e for c in chains]), w)
+        e_all = parallel.all_gather_array(np.array([c.e for c in chains]), w)[order]
+        d = rnd % 2 if layout == "contiguous" else ce_oracle.pt_direction(SEED, rnd)
+        slots, _ = parallel.exchange_sweep(e_all, slots, kts, d, SEED, rnd, _uniform)
+        for g, c in zip(ids, chains):
+            c.kT = float(kts[slots[g]])
+    acc_all = parallel.all_gather_array(np.stack([c.acc for c in chains]), w)[order]
+    e_all = parallel.all_gather_array(np.array([c.e for c in chains]), w)[order]
     if rank == 0:
         q.put((slots, e_all, acc_all))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_parallel_tempering_gloo():
+@pytest.mark.parametrize("layout", ["contiguous", "round_robin"])
+def test_sharded_parallel_tempering_gloo(layout):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, layout)) for r in range(2)]
     for p in procs:
         p.start()
     import queue
@@ -88,7 +96,8 @@ def test_sharded_parallel_tempering_gloo():
     for rnd in range(5):
         for c in chains:
             c.run_canonical(150)
-        ref_slots, _ = ce_oracle.pt_exchange([c.e for c in chains], ref_slots, kts, rnd % 2, SEED, rnd)
+        d = rnd % 2 if layout == "contiguous" else ce_oracle.pt_direction(SEED, rnd)
+        ref_slots, _ = ce_oracle.pt_exchange([c.e for c in chains], ref_slots, kts, d, SEED, rnd)
         for g, c in enumerate(chains):
             c.kT = float(kts[ref_slots[g]])
     assert np.array_equal(slots, ref_slots)
@@ -98,6 +107,11 @@ def test_sharded_parallel_tempering_gloo():
 
 def test_shard_range_and_exchange_sweep_host():
     assert parallel.shard_range(512, 3, 8) == (192, 64)
+    assert parallel.shard_round_robin(512, 3, 8) == (3, 8, 64)
+    # replica g = 8 l + k is element l of rank k's block in an all-gather
+    gi = parallel.gather_index(512, 8, 8)
+    assert gi[3] == 3 * 64 and gi[8 + 3] == 3 * 64 + 1 and sorted(gi) == list(range(512))
+    assert np.array_equal(parallel.gather_index(6, 2, 1), np.arange(6))
     with pytest.raises(ValueError):
         parallel.shard_range(10, 0, 4)
     rng = np.random.default_rng(1)
