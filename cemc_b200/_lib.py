@@ -92,12 +92,15 @@ SIGNATURES = {
     "cemc_set_autotune": [_H, C.c_int],
     "cemc_get_variant": [_H, _i32p, _i32p],
     "cemc_last_variant": [_H, _i32p],
+    "cemc_batch_applicable": [_H, _i32p],
     "cemc_set_variant": [_H, C.c_int, C.c_int],
     "cemc_set_spin_kernel": [_H, C.c_int],
     "cemc_set_table_eval": [_H, C.c_int],
     "cemc_set_precision": [_H, C.c_int],
     "cemc_set_replica_order": [_H, _i32p],
     "cemc_get_batch_eval": [_H, _i32p],
+    "cemc_set_lattice_arithmetic": [_H, C.c_int],
+    "cemc_get_lattice_arithmetic": [_H, _i32p],
     "cemc_set_screen_slack": [_H, C.c_double],
     "cemc_debug_phase_cycles": [_H, _u64p],
     "cemc_selftest_division": [_H, C.c_uint64, C.c_int, C.c_int, _u64p],
@@ -126,6 +129,7 @@ SIGNATURES = {
     "cemc_run_canonical": [_H, C.c_int64],
     "cemc_set_trace": [_H, C.c_int64],
     "cemc_get_trace": [_H, C.c_int64, _i32p, _i8p, _f64p, _u8p, _f64p],
+    "cemc_set_observe": [_H, C.c_int],
     "cemc_reset_accumulators": [_H, _f64p],
     "cemc_get_accumulators": [_H, _f64p],
     "cemc_pt_exchange": [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -88,6 +88,8 @@ struct cemc_handle {
   double screen_slack = 1.0;          // testing: widen the Metropolis screening band
   bool autotune = true;               // pick the fastest kernel variant on long runs
   int tuned_sgc = -1, tuned_can = -1;  // variant chosen by the autotuner
+  bool lat_verified = false;          // `trans` is a periodic shift table: index arithmetic usable
+  bool observe = true;                // accumulate the Averager / SGCObserver sums during run_*
   int last_variant = -1;              // variant of the most recent Metropolis launch (cemc_last_variant)
   // tuning across short launches: next variant to time, ms per move of the timed ones
   int xt_next[2] = {0, 0};
@@ -689,6 +691,40 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   if (t.n_active != N) { if ((rc = dupload(h, &t.active, active))) return rc; }
   else t.active = nullptr;
   t.uniform_group = (tb->n_symm == 1 && t.n_active == N) ? 1 : 0;
+  // ---- translation-invariant lattice?  (hint from the host, verified entry by entry) ----
+  t.lat_ok = 0;
+  if (tb->lattice_dims && t.uniform_group) {
+    const long long L1 = tb->lattice_dims[0], L2 = tb->lattice_dims[1], L3 = tb->lattice_dims[2];
+    bool ok = L1 >= 1 && L2 >= 1 && L3 >= 1 && L1 < 1024 && L2 < 1024 && L3 < 1024 && L1 * L2 * L3 == N;
+    std::vector<uint32_t> shift(K, 0u);
+    for (int c = 0; c < K && ok; c++) {
+      const int s0 = tb->trans[c];                         // T(site 0, c): the shift itself
+      const int di = s0 / (int)(L2 * L3), dj = (s0 / (int)L3) % (int)L2, dk = s0 % (int)L3;
+      shift[c] = (uint32_t)di | ((uint32_t)dj << 10) | ((uint32_t)dk << 20);
+      for (int s = 0; s < N && ok; s++) {
+        const int i = s / (int)(L2 * L3), j = (s / (int)L3) % (int)L2, k = s % (int)L3;
+        const int want = (((i + di) % (int)L1) * (int)L2 + (j + dj) % (int)L2) * (int)L3 + (k + dk) % (int)L3;
+        if (tb->trans[(size_t)s * K + c] != want) ok = false;
+      }
+    }
+    if (ok) {
+      const uint32_t L23 = (uint32_t)(L2 * L3);
+      const uint32_t m23 = (uint32_t)((0x100000000ull + L23 - 1) / L23), m3 = (uint32_t)((0x100000000ull + L3 - 1) / (uint32_t)L3);
+      // the multiply-high division must be exact for every operand the kernels can form
+      for (uint32_t s = 0; s < (uint32_t)N && ok; s++) if ((uint32_t)(((unsigned long long)s * m23) >> 32) != s / L23) ok = false;
+      for (uint32_t r = 0; r < L23 && ok; r++) if ((uint32_t)(((unsigned long long)r * m3) >> 32) != r / (uint32_t)L3) ok = false;
+      if (L23 == 1) ok = false;       // m would not fit 32 bits
+      if (L3 == 1) ok = false;
+      if (ok) {
+        h->lat_verified = true;
+        // default: on when the table does not stay in L1 anyway (measured on B200: fcc 20^3 / 64^3
+        // gain 1-5 %, tables <= 128 KB -- fcc 10^3, 12^3 -- are L1 hits and lose ~1 %)
+        t.lat_ok = ((size_t)N * K * sizeof(int32_t) > 128 * 1024) ? 1 : 0; t.L1 = (uint32_t)L1; t.L2 = (uint32_t)L2; t.L3 = (uint32_t)L3; t.L23 = L23;
+        t.lat_m23 = m23; t.lat_m3 = m3;
+        if ((rc = dupload(h, &t.col_shift, shift))) return rc;
+      }
+    }
+  }
   t.prefetch_rows = ((size_t)32 * 2 * K * sizeof(int32_t) <= 24 * 1024) ? 1 : 0;
   {
     int8_t *al = nullptr, *ap = nullptr;
@@ -935,13 +971,44 @@ int cemc_set_autotune(cemc_handle *h, int on) {
   return 0;
 }
 
-static const int kNumVariants = 9;   // see launch_variant
+static const int kNumVariants = 10;  // see launch_variant
 
 int cemc_set_variant(cemc_handle *h, int sgc, int canonical) {
   if (!h) return fail("null handle");
   if (sgc < -1 || sgc >= kNumVariants || canonical < -1 || canonical >= kNumVariants) return fail("no such kernel variant");
   h->tuned_sgc = sgc;
   h->tuned_can = canonical;
+  return 0;
+}
+
+int cemc_set_lattice_arithmetic(cemc_handle *h, int on) {
+  if (!h) return fail("null handle");
+  h->t.lat_ok = (on != 0 && h->lat_verified) ? 1 : 0;
+  reset_tuning(h);
+  return 0;
+}
+
+int cemc_get_lattice_arithmetic(cemc_handle *h, int *on) {
+  if (!h || !on) return fail("null argument");
+  *on = h->t.lat_ok;
+  return 0;
+}
+
+int cemc_set_observe(cemc_handle *h, int on) {
+  if (!h) return fail("null handle");
+  h->observe = on != 0;
+  return 0;
+}
+
+static bool batch_applicable(const cemc_handle *h) {
+  const bool spin_eval = h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4;
+  return !(h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
+           h->t.KP > (spin_eval ? 64 : 32));
+}
+
+int cemc_batch_applicable(cemc_handle *h, int *yes) {
+  if (!h || !yes) return fail("null argument");
+  *yes = batch_applicable(h) ? 1 : 0;
   return 0;
 }
 
@@ -1191,7 +1258,7 @@ static int launch_spin(cemc_handle *h, const RunArgs &a) {
 static RunArgs run_args(cemc_handle *h, long long n_steps) {
   RunArgs a{};
   a.n_steps = n_steps; a.seed = h->seed; a.replica_offset = (uint32_t)h->replica_offset; a.replica_stride = (uint32_t)h->replica_stride;
-  a.observe = 1;
+  a.observe = h->observe ? 1 : 0;
   a.screen_slack = h->screen_slack;
   a.phase = h->d_phase;
   a.order = h->d_order;
@@ -1205,10 +1272,8 @@ static RunArgs run_args(cemc_handle *h, long long n_steps) {
 // speculative batch kernel with B moves per CTA and C CTAs per chain; -1 when not applicable
 template <int MODE>
 static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 1, int split = 0) {
-  const bool spin_eval = h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4;
   // K <= 31 translation columns (one per lane); the spin evaluation also takes 32..63 (two per lane)
-  if (h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
-      h->t.KP > (spin_eval ? 64 : 32)) return -1;
+  if (!batch_applicable(h)) return -1;
   BatchLaunch L{};
   L.mode = MODE; L.B = B; L.C = C; L.M = M; L.split = split; L.R = h->R; L.max_smem_optin = h->max_smem_optin;
   L.tree = ((h->order_mode == CEMC_ORDER_TREE) || h->integer_bf) ? 1 : 0;
@@ -1241,8 +1306,8 @@ static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 
 // Kernel variants of one sampler.  All of them produce the same trajectory bit for
 // bit, so the choice is a pure performance knob: 0 spin, 1..4 batch (B,C) =
 // (16,2) (16,1) (8,1) (4,1), 5 one move at a time (mc_kernel, always applicable),
-// 6..7 batch (8,1) / (16,1) with two moves per evaluation warp, 8 batch (16,2) with the two
-// changed sites of a swap split over the two CTAs (canonical only).
+// 6..7 retired, 8 / 9 batch (16,2) / (8,2) with the two changed sites of a swap split over the
+// two CTAs of a cluster (canonical only; 9 = short batches for hot chains on small cells).
 
 template <int MODE>
 static int launch_variant_raw(cemc_handle *h, const RunArgs &a, int v);
@@ -1262,10 +1327,11 @@ static int launch_variant_raw(cemc_handle *h, const RunArgs &a, int v) {
     case 2: return launch_batch<MODE>(h, a, 16, 1);
     case 3: return launch_batch<MODE>(h, a, 8, 1);
     case 4: return launch_batch<MODE>(h, a, 4, 1);
-    case 6: return launch_batch<MODE>(h, a, 8, 1, 2);
-    case 7: return launch_batch<MODE>(h, a, 16, 1, 2);
+    case 6: case 7: return -1;      // retired (two moves per evaluation warp: never the fastest)
     case 8: return (MODE == MODE_CANONICAL && (2 * h->R <= h->n_sms || h->cluster == 2))
                        ? launch_batch<MODE>(h, a, 16, 2, 1, 1) : -1;
+    case 9: return (MODE == MODE_CANONICAL && (2 * h->R <= h->n_sms || h->cluster == 2))
+                       ? launch_batch<MODE>(h, a, 8, 2, 1, 1) : -1;
     default: return launch_mc<MODE>(h, a, 0, h->R);
   }
 }
@@ -1276,7 +1342,7 @@ static bool variant_allowed(const cemc_handle *h, int v) {
   if (h->fp32 && !h->spin_ok && (v == 0 || v == 5)) return false;
   if (v == 0 && h->batch > 0) return false;       // an explicit batch size asks for the batch kernel
   if ((v >= 1 && v <= 4) || v >= 6) {
-    static const int Bs[9] = {0, 16, 16, 8, 4, 0, 8, 16, 16}, Cs[9] = {0, 2, 1, 1, 1, 0, 1, 1, 2};
+    static const int Bs[10] = {0, 16, 16, 8, 4, 0, 8, 16, 16, 8}, Cs[10] = {0, 2, 1, 1, 1, 0, 1, 1, 2, 2};
     if (h->batch > 0 && h->batch != Bs[v]) return false;
     if (h->cluster > 0 && h->cluster != Cs[v]) return false;
   }

@@ -378,6 +378,13 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // replay of recorded proposals / uniforms: the ring is filled from
   // rp_sites / rp_news / rp_u instead of the Philox stream; records hold sites, not list slots
   const bool replay = (a.rp_sites != nullptr);
+  // translation-invariant lattice: lane c derives T(site, c) from the site index (no table gather)
+  const bool lat_ok = t.lat_ok != 0;
+  const uint32_t my_shift = (lat_ok && lane < K) ? t.col_shift[lane] : 0u;
+  const uint32_t my_shift2 = (lat_ok && kWide && lane + 32 < K) ? t.col_shift[lane + 32] : 0u;
+  auto neighbour = [&](int site, int col, uint32_t shift) -> int {
+    return lat_ok ? lattice_neighbour(t, site, shift) : __ldg(&t.trans[(size_t)site * K + col]);   // :264
+  };
   // absolute slack of the Metropolis screen: rounding noise of the two ordered dot
   // products the reference subtracts, N * sum_i |eci_i| * max|cf| * O(n_eci * eps)
   double etol;
@@ -743,7 +750,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
               const int j = jb + je;
               uint32_t v = 0;
               if (lane < K) {
-                const int nbs = __ldg(&t.trans[(size_t)site[mi][j] * K + lane]);      // :264
+                const int nbs = neighbour(site[mi][j], lane, my_shift);
                 gs[mi][je] = nbs;
                 v = (uint32_t)s.occ[nbs];
                 if (j == 1 && nbs == site[mi][0]) v = (uint32_t)newv[mi][0];   // change 1 sees change 0 applied (:845-852)
@@ -753,7 +760,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
               if (kWide) {                         // columns 32 .. K-1 and the site itself in the upper half
                 uint32_t v1 = 0;
                 if (lane + 32 < K) {
-                  const int nbs = __ldg(&t.trans[(size_t)site[mi][j] * K + lane + 32]);
+                  const int nbs = neighbour(site[mi][j], lane + 32, my_shift2);
                   gs2[mi][je] = nbs;
                   v1 = (uint32_t)s.occ[nbs];
                   if (j == 1 && nbs == site[mi][0]) v1 = (uint32_t)newv[mi][0];
@@ -849,7 +856,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           const int j = jb + je;
           int v = 0;
           if (lane < K) {
-            const int nbs = __ldg(&t.trans[(size_t)sites[j] * K + lane]);        // :264
+            const int nbs = neighbour(sites[j], lane, my_shift);
             gsx[je] = nbs;
             v = s.occ[nbs];
             if (j && nbs == site0) v = new0;      // change 1 sees change 0 applied (:845-852)
@@ -967,7 +974,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           double *Vj = Vb + j * VS;
           const int sj = j ? site1 : site0;
           if (c < K) {
-            const int nbs = __ldg(&t.trans[(size_t)sj * K + c]);        // :264
+            const int nbs = neighbour(sj, c, my_shift);
             gsx[x] = nbs;
             int v = s.occ[nbs];
             if (j && nbs == site0) v = new0;    // change 1 sees change 0 applied (:845-852)

@@ -100,14 +100,15 @@ static int batch_launch_bc(const BatchLaunch &L) {
     if (L.B == 8) return batch_launch_wide<MODE, kTree, 7, EV>(L);
     return -1;
   }
-  if (L.split) return (L.B == 16 && L.C == 2) ? batch_launch_split<MODE, kTree, 15, EV>(L) : -1;
-  // L.B counts the warps of a CTA: B - 1 evaluation warps (moves per batch) + the observer
-  // warp; power-of-two CTAs get the full register budget (512 threads x 128 registers)
-  if (L.M == 2) {
-    if (L.B == 16 && L.C == 1) return batch_launch_b<MODE, kTree, 15, 1, EV, 2>(L);
-    if (L.B == 8 && L.C == 1) return batch_launch_b<MODE, kTree, 7, 1, EV, 2>(L);
+  if (L.split) {
+    if (L.C != 2) return -1;
+    if (L.B == 16) return batch_launch_split<MODE, kTree, 15, EV>(L);
+    if (L.B == 8) return batch_launch_split<MODE, kTree, 7, EV>(L);      // hot chains on small cells: short batches
     return -1;
   }
+  // L.B counts the warps of a CTA: B - 1 evaluation warps (moves per batch) + the observer
+  // warp; power-of-two CTAs get the full register budget (512 threads x 128 registers)
+  if (L.M != 1) return -1;      // two moves per evaluation warp: measured slower on every workload (round 1), retired
   if (L.B == 16 && L.C == 2) return batch_launch_b<MODE, kTree, 15, 2, EV>(L);
   if (L.B == 16 && L.C == 1) return batch_launch_b<MODE, kTree, 15, 1, EV>(L);
   if (L.B == 8 && L.C == 1) return batch_launch_b<MODE, kTree, 7, 1, EV>(L);

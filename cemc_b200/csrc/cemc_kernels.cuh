@@ -82,7 +82,27 @@ struct DeviceTables {    // device pointers, shared by all replicas
   int n_allowed;
   const int8_t *allowed;       // [128] species ids the sampler may insert
   const int8_t *allowed_pos;   // [128] position of a species in `allowed`, -1 if absent
+  // Translation-invariant lattice (verified against `trans` by cemc_create): site = (i L2 + j) L3 + k
+  // and T(site, col) = ((i + di) mod L1, (j + dj) mod L2, (k + dk) mod L3): the neighbour of a
+  // site is index arithmetic (0 bytes of table traffic) instead of a gather from L2.
+  int lat_ok;
+  uint32_t L1, L2, L3, L23;    // L23 = L2 * L3
+  uint32_t lat_m23, lat_m3;    // ceil(2^32 / L23), ceil(2^32 / L3): x / d == umulhi(x, m) (checked for all sites)
+  const uint32_t *col_shift;   // [K] di | dj << 10 | dk << 20
 };
+
+// T(site, col) of a translation-invariant lattice; `shift` = col_shift[col]
+__device__ __forceinline__ int lattice_neighbour(const DeviceTables &t, int site, uint32_t shift) {
+  const uint32_t i = __umulhi((uint32_t)site, t.lat_m23);
+  const uint32_t rem = (uint32_t)site - i * t.L23;
+  const uint32_t j = __umulhi(rem, t.lat_m3);
+  const uint32_t k = rem - j * t.L3;
+  uint32_t ni = i + (shift & 0x3ffu), nj = j + ((shift >> 10) & 0x3ffu), nk = k + (shift >> 20);
+  ni -= ni >= t.L1 ? t.L1 : 0u;
+  nj -= nj >= t.L2 ? t.L2 : 0u;
+  nk -= nk >= t.L3 ? t.L3 : 0u;
+  return (int)((ni * t.L2 + nj) * t.L3 + nk);
+}
 
 struct ReplicaState {    // device pointers, replica-major
   int8_t *occ;           // [R][N]

@@ -194,12 +194,14 @@ class Montecarlo(object):
     def _device_run(self, n):
         self._gpu.run_canonical(n)
 
-    def _sync_atoms(self):
+    def _sync_atoms(self, incremental=False):
         """Mirror device occupations into ``atoms``; returns the net changes since the
-        previous mirror.  Only the sites that differ are touched (vectorised compare)."""
+        previous mirror.  Only the sites that differ are touched (vectorised compare);
+        ``incremental``: trust the mirror kept by the running ``_steps`` call instead of
+        re-reading every ``atoms[i].symbol``."""
         occ = self._gpu.get_occupancy()[0]
         species = self._tables.species
-        mirror = getattr(self, "_occ_mirror", None)
+        mirror = getattr(self, "_occ_mirror", None) if incremental else None
         if mirror is None or len(mirror) != len(occ):
             mirror = self._tables.occupancy([a.symbol for a in self.atoms])
         changes = []
@@ -239,8 +241,11 @@ class Montecarlo(object):
         done = 0
         intervals = [iv for iv, _ in self.observers if self._is_host_observer(_)]
         if observe and intervals:
-            self._sync_atoms()
-            self._occ_at_start = self._occ_mirror       # snapshot for observers not called yet
+            # what the host (atoms, hence every observer not called yet) has seen so far
+            # (re-read from `atoms` once per call: the calculator's per-call API mutates them too)
+            mirror = self._tables.occupancy([a.symbol for a in self.atoms])
+            self._occ_mirror = mirror
+            self._occ_at_start = mirror
         chunk = min([self.chunk_size] + intervals) if observe else self.chunk_size
         while done < n:
             m = min(chunk, n - done)
@@ -255,7 +260,7 @@ class Montecarlo(object):
                 due = [o for iv, o in self.observers
                        if self._is_host_observer(o) and self.current_step % iv == 0]
                 if due:
-                    self._sync_atoms()                  # waits for the stream
+                    self._sync_atoms(incremental=True)  # waits for the stream
                     self.current_energy = float(self._gpu.get_energy()[0])
                     for o in due:
                         o(self._changes_for(o))

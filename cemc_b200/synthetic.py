@@ -318,6 +318,96 @@ def fcc_settings(L: int, species: Sequence[str] = ("Al", "Mg"),
     return st
 
 
+def layered_settings(L: int, species: Sequence[str] = ("Al", "Mg", "Si"),
+                     trans_matrix_format: str = "ndarray") -> SyntheticSettings:
+    """Two-sublattice crystal: simple cubic L^3 cell whose (001) layers alternate between two
+    inequivalent site types A (k even) and B (k odd) -- TWO translational symmetry groups
+    (``index_by_trans_symm``), each with its own ``cluster_info`` dict, the way ase.clease
+    describes a crystal with a basis (the reference selects the family table by the changed
+    site's group: cpp/src/ce_updater.cpp:379-384; 4-sublattice case in
+    tests/test_CE_updater.py:206-228).  Families (every physical cluster is listed once in
+    the table of EACH of its member sites, so incremental updates and the definition agree):
+
+      c2_d0000_0  A-A in-plane nearest neighbours     group 0 only, M = 4, equivalent vertices
+      c2_d0001_0  B-B in-plane nearest neighbours     group 1 only, M = 4, equivalent vertices
+      c2_d0002_0  A-B inter-layer nearest neighbours  both groups, M = 2; sorted order (A, B): the
+                                                      changed site is position 0 (A) or 1 (B)
+      c3_d0000_0  right-angle triplet (A corner, A', B above the corner): three inequivalent
+                  vertices, sorted (corner, far A, B); M = 16 seen from an A site (8 as the corner,
+                  8 as the far A: ``order`` [0,1,2] / [1,0,2]) and M = 8 from a B site ([1,2,0])
+    """
+    if L < 4 or L % 2:
+        raise ValueError("L must be even and >= 4")
+    N = L ** 3
+    species = list(species)
+    st = SyntheticSettings()
+    st.unique_elements = sorted(species)
+    st.num_unique_elements = len(species)
+    st.background_indices = []
+    st.basis_functions = basis_functions_for(st.unique_elements)
+    st.size = [L, L, L]
+    st.kwargs = dict(crystalstructure="layered_sc", size=[L, L, L], species=list(species))
+    ijk = np.stack(np.unravel_index(np.arange(N), (L, L, L)), axis=1)
+    st.index_by_trans_symm = [[int(s) for s in range(N) if ijk[s, 2] % 2 == 0],
+                              [int(s) for s in range(N) if ijk[s, 2] % 2 == 1]]
+
+    def col(o):
+        return ((o[0] % L) * L + (o[1] % L)) * L + (o[2] % L)
+
+    inplane = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0)]
+    updown = [(0, 0, 1), (0, 0, -1)]
+
+    def fam(prefix, n, g, indices, order, equiv, dia, descr):
+        return {"ref_indx": 0, "size": n, "max_cluster_dia": float(dia), "symm_group": g,
+                "name": prefix, "descriptor": descr, "indices": indices, "order": order,
+                "equiv_sites": equiv}
+
+    add = lambda a, b: (a[0] + b[0], a[1] + b[1], a[2] + b[2])      # noqa: E731
+    info0, info1 = {}, {}
+    info0["c2_d0000_0"] = fam("c2_d0000_0", 2, 0, [[col(o)] for o in inplane], [[0, 1]] * 4, [[0, 1]], 0.5, "AA")
+    info1["c2_d0001_0"] = fam("c2_d0001_0", 2, 1, [[col(o)] for o in inplane], [[0, 1]] * 4, [[0, 1]], 0.5, "BB")
+    info0["c2_d0002_0"] = fam("c2_d0002_0", 2, 0, [[col(o)] for o in updown], [[0, 1]] * 2, [], 0.5, "AB")
+    info1["c2_d0002_0"] = fam("c2_d0002_0", 2, 1, [[col(o)] for o in updown], [[1, 0]] * 2, [], 0.5, "AB")
+    # triplet seen from an A site: as the corner -> raw (ref, A', B) is already sorted; as the far A ->
+    # raw (ref, corner, B above the corner), sorted (corner, ref, B) = raw[1], raw[0], raw[2]
+    ind, order = [], []
+    for a in inplane:
+        for b in updown:
+            ind.append([col(a), col(b)]); order.append([0, 1, 2])
+    for a in inplane:
+        for b in updown:
+            ind.append([col(a), col(add(a, b))]); order.append([1, 0, 2])
+    info0["c3_d0000_0"] = fam("c3_d0000_0", 3, 0, ind, order, [], 0.7071, "AAB")
+    # seen from the B site: raw (ref, corner, far A), sorted (corner, far, B) = raw[1], raw[2], raw[0]
+    ind, order = [], []
+    for b in updown:
+        for a in inplane:
+            ind.append([col(b), col(add(b, a))]); order.append([1, 2, 0])
+    info1["c3_d0000_0"] = fam("c3_d0000_0", 3, 1, ind, order, [], 0.7071, "AAB")
+    st.cluster_info = [info0, info1]
+    st.max_cluster_dia = 0.7071
+    used = sorted({c for info in st.cluster_info for f in info.values() for sub in f["indices"] for c in sub})
+    if any(c == 0 for c in used):
+        raise ValueError("self interaction: cell too small")
+
+    def shifted(c):
+        cijk = np.array(np.unravel_index(c, (L, L, L)))
+        t = (ijk + cijk[None, :]) % L
+        return (t[:, 0] * L + t[:, 1]) * L + t[:, 2]
+    if trans_matrix_format == "ndarray":
+        tm = np.zeros((N, max(used) + 1), dtype=np.int32)
+        for c in used:
+            tm[:, c] = shifted(c)
+        st.trans_matrix = tm
+    elif trans_matrix_format == "list":
+        cm = {c: shifted(c).tolist() for c in used}
+        st.trans_matrix = [{c: cm[c][s] for c in used} for s in range(N)]
+    else:
+        raise ValueError(trans_matrix_format)
+    st.atoms = Atoms([st.unique_elements[0]] * N)
+    return st
+
+
 def random_symbols(settings: SyntheticSettings, conc: Dict[str, float],
                    seed: int, exact: bool = True) -> List[str]:
     """Random occupation at the stated composition (default_rng(seed))."""

@@ -41,6 +41,7 @@ class CemcTablesStruct(C.Structure):
         ("term_count", C.POINTER(C.c_int32)),
         ("term_deco_off", C.POINTER(C.c_int32)),
         ("deco", C.POINTER(C.c_int8)),
+        ("lattice_dims", C.POINTER(C.c_int32)),
     ]
 
 
@@ -267,6 +268,14 @@ class FlatTables(object):
                      if deco_rows else np.zeros((1, 4), dtype=np.int8))
         self.n_deco = len(deco_rows)
         self.background = sorted(bkg)
+        # hint for the index-arithmetic translation (verified by cemc_create against `trans`)
+        size = getattr(settings, "size", None)
+        self.lattice_dims = np.zeros(3, dtype=np.int32)
+        try:
+            if size is not None and len(size) == 3 and int(np.prod(size)) == N and not bkg:
+                self.lattice_dims = np.array([int(x) for x in size], dtype=np.int32)
+        except (TypeError, ValueError):
+            pass
 
     # ------------------------------------------------------------------
     def occupancy(self, symbols: Sequence[str]) -> np.ndarray:
@@ -321,5 +330,6 @@ class FlatTables(object):
         st.term_count = _ptr(self.term_count, C.c_int32)
         st.term_deco_off = _ptr(self.term_deco_off, C.c_int32)
         st.deco = _ptr(self.deco, C.c_int8)
+        st.lattice_dims = _ptr(self.lattice_dims, C.c_int32)
         st._keepalive = self  # arrays must outlive the struct
         return st

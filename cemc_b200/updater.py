@@ -176,6 +176,14 @@ class BatchedCEUpdater(object):
         _lib.check(self.lib.cemc_get_batch_eval(self._h, C.byref(v)))
         return v.value
 
+    def set_lattice_arithmetic(self, on: bool):
+        _lib.check(self.lib.cemc_set_lattice_arithmetic(self._h, 1 if on else 0))
+
+    def get_lattice_arithmetic(self) -> bool:
+        v = C.c_int32(0)
+        _lib.check(self.lib.cemc_get_lattice_arithmetic(self._h, C.byref(v)))
+        return bool(v.value)
+
     def set_variant(self, sgc: int = -1, canonical: int = -1):
         _lib.check(self.lib.cemc_set_variant(self._h, int(sgc), int(canonical)))
 
@@ -183,6 +191,13 @@ class BatchedCEUpdater(object):
         a, b = C.c_int32(-1), C.c_int32(-1)
         _lib.check(self.lib.cemc_get_variant(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def batch_kernel_applies(self) -> bool:
+        """True when the speculative batch kernel takes this system (else the generic
+        one-move-at-a-time kernel runs it); probes with a zero-move launch request."""
+        v = C.c_int32(0)
+        _lib.check(self.lib.cemc_batch_applicable(self._h, C.byref(v)))
+        return bool(v.value)
 
     def last_variant(self) -> int:
         """Kernel variant of the most recent Metropolis launch (-1: none)."""
@@ -272,6 +287,10 @@ class BatchedCEUpdater(object):
         return sites, news, u, acc, e
 
     # ---- observers -----------------------------------------------------------
+    def set_observe(self, on: bool):
+        """Switch the per-step Averager / SGCObserver sums of run_* on or off."""
+        _lib.check(self.lib.cemc_set_observe(self._h, 1 if on else 0))
+
     def reset_accumulators(self, ref=None):
         if ref is not None:
             ref = np.ascontiguousarray(

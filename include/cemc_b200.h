@@ -81,6 +81,11 @@ typedef struct cemc_tables {
   const int32_t *term_count;     /* [n_symm][n_eci] cluster_symm_group_count[prefix]*/
   const int32_t *term_deco_off;  /* [n_symm*n_eci + 1] range of rows in `deco`      */
   const int8_t  *deco;           /* [n_deco][4] equivalent decorations, stored order */
+  /* optional hint (may be NULL): the supercell is L1 x L2 x L3 primitive cells with
+   * site = (i L2 + j) L3 + k.  cemc_create CHECKS that every used translation-matrix
+   * column is a periodic shift on that grid; if so the kernels compute T(site, col)
+   * by index arithmetic instead of reading `trans` (same values, no table traffic).   */
+  const int32_t *lattice_dims;   /* [3] or NULL                                         */
 } cemc_tables;
 
 /* per-replica accumulator slots (doubles), see cemc_get_accumulators */
@@ -134,6 +139,8 @@ int cemc_set_autotune(cemc_handle *h, int on);
 int cemc_get_variant(cemc_handle *h, int *sgc, int *canonical);
 /* variant of the most recent Metropolis launch (run_sgc / run_canonical / replay), -1 = none */
 int cemc_last_variant(cemc_handle *h, int *variant);
+/* 1 when the speculative batch kernel applies to this system (size limits in DESIGN.md) */
+int cemc_batch_applicable(cemc_handle *h, int *yes);
 /* pin the variant per sampler (-1 = let the autotuner decide); inapplicable variants
  * fall back to the default preference order                                     */
 int cemc_set_variant(cemc_handle *h, int sgc, int canonical);
@@ -148,6 +155,11 @@ int cemc_set_table_eval(cemc_handle *h, int on);
 /* evaluation scheme the batch kernel uses for this system: 0 fp64 products, 1 binary
  * spin (XOR / popcount), 2 product tables, 3 fp32 product tables                    */
 int cemc_get_batch_eval(cemc_handle *h, int *ev);
+/* Translation by index arithmetic (cemc_tables.lattice_dims, verified at create): on by
+ * default when the table is a periodic shift table; 0 = gather T(site, col) from `trans`
+ * (same values: a pure performance knob / testing hook).  get: 1 when in use.            */
+int cemc_set_lattice_arithmetic(cemc_handle *h, int on);
+int cemc_get_lattice_arithmetic(cemc_handle *h, int *on);
 /* Precision of the cluster-product sums: 64 (default; bit-identical to the reference's
  * fp64 CEUpdater) or 32 = the fp32 variant: product tables and sums over sub-clusters
  * (spin_product_one_atom, ce_updater.cpp:244-285) in single precision, quotients, CF
@@ -228,6 +240,9 @@ int cemc_get_trace(cemc_handle *h, int64_t n_steps, int32_t *sites /*[R][n][2]*/
                    uint8_t *accepted /*[R][n]*/, double *e_after /*[R][n]*/);
 
 /* ---- observers (Averager / SGCObserver sums) ---- */
+/* 0: run_sgc / run_canonical skip the per-step sums (legs whose averages nobody reads:
+ * bias probes, equilibration windows, parallel-tempering burn-in); default 1             */
+int cemc_set_observe(cemc_handle *h, int on);
 int cemc_reset_accumulators(cemc_handle *h, const double *ref /*[R] or NULL (=1.0)*/);
 int cemc_get_accumulators(cemc_handle *h, double *acc /*[R][CEMC_ACC_STRIDE(D)]*/);
 

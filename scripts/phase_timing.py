@@ -17,9 +17,10 @@ for a_ in sys.argv[1:]:
     if a_.startswith("b="): batch = int(a_[2:])
     else: args.append(a_)
 for which in args or ["C2", "C3", "C3S"]:
-    w = wl.WORKLOADS[which.upper()]()
+    w = wl.c4_parallel_tempering(R=64, n_total=64) if which.upper() == "C4" else wl.WORKLOADS[which.upper()]()
     gpu = wl.make_updater(w)
     if batch is not None: gpu.set_batch(batch)
+    if os.environ.get("VARIANT"): gpu.set_variant(int(os.environ["VARIANT"]), int(os.environ["VARIANT"]))
     run = gpu.run_sgc if w.mode == "sgc" else gpu.run_canonical
     n = 20000
     run(n); gpu.synchronize()

@@ -9,7 +9,8 @@ from cemc_b200.tables import FlatTables
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN = ["almg_fcc4_canonical", "almg_fcc4_sgc", "almgsi_fcc4_canonical",
-          "almgsi_fcc4_sgc", "almgsi_fcc5_canonical_cold"]
+          "almgsi_fcc4_sgc", "almgsi_fcc5_canonical_cold",
+          "almgsi_layered4_sgc", "almgsi_layered6_canonical"]     # two symmetry groups
 
 # BASELINE-size fixtures: replicas of the bench workloads (configs[1], configs[2] and the
 # north-star 64-replica Al-Mg-Si SGC sweep) recorded from the compiled reference
@@ -20,8 +21,11 @@ KB = 8.617330337217213e-05   # eV/K (ase.units.kB, CODATA 2014)
 
 def build(L, species, families, conc, eci_kind="synthetic", seed=3,
           trans_matrix_format="auto"):
-    st = syn.fcc_settings(L, species, families,
-                          trans_matrix_format=trans_matrix_format)
+    if families == "layered":
+        st = syn.layered_settings(L, species)
+    else:
+        st = syn.fcc_settings(L, species, families,
+                              trans_matrix_format=trans_matrix_format)
     eci = syn.almg_ecis(st) if eci_kind == "almg" else \
         syn.synthetic_ecis(st, seed=1234)
     symbols = syn.random_symbols(st, conc, seed=seed)
@@ -32,7 +36,8 @@ def build(L, species, families, conc, eci_kind="synthetic", seed=3,
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     meta = json.loads(str(z["meta"]))
-    st = syn.fcc_settings(meta["L"], meta["species"], meta["families"])
+    st = syn.layered_settings(meta["L"], meta["species"]) if meta["families"] == "layered" else \
+        syn.fcc_settings(meta["L"], meta["species"], meta["families"])
     ft = FlatTables(st, meta["eci"], meta["symbols0"])
     assert ft.eci_names == meta["eci_names"]
     assert ft.species == meta["species_sorted"]
@@ -64,6 +69,10 @@ def load_golden_workload(name):
 
 BINARY = dict(L=4, species=["Al", "Mg"], families=["nn", "2nn", "tri", "tet"],
               conc={"Al": 0.5, "Mg": 0.5})
+# two translational symmetry groups with different cluster families (synthetic.layered_settings)
+LAYERED = dict(L=4, species=["Al", "Mg", "Si"], families="layered",
+               conc={"Al": 0.4, "Mg": 0.3, "Si": 0.3})
+LAYERED_BINARY = dict(L=4, species=["Al", "Mg"], families="layered", conc={"Al": 0.5, "Mg": 0.5})
 TERNARY = dict(L=4, species=["Al", "Mg", "Si"],
                families=["nn", "2nn", "tri", "iso", "tet"],
                conc={"Al": 0.5, "Mg": 0.25, "Si": 0.25})

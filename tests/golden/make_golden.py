@@ -36,11 +36,16 @@ CASES = [
      {"Al": 0.5, "Mg": 0.25, "Si": 0.25}, "synthetic", 0.05, "sgc", 1200),
     ("almgsi_fcc5_canonical_cold", 5, ["Al", "Mg", "Si"], ["nn", "2nn", "tri", "tet"],
      {"Al": 0.8, "Mg": 0.1, "Si": 0.1}, "synthetic", 0.008, "canonical", 1200),
+    # two translational symmetry groups (cemc_b200.synthetic.layered_settings; ce_updater.cpp:379-384)
+    ("almgsi_layered4_sgc", 4, ["Al", "Mg", "Si"], "layered",
+     {"Al": 0.4, "Mg": 0.3, "Si": 0.3}, "synthetic", 0.05, "sgc", 1200),
+    ("almgsi_layered6_canonical", 6, ["Al", "Mg", "Si"], "layered",
+     {"Al": 0.4, "Mg": 0.3, "Si": 0.3}, "synthetic", 0.04, "canonical", 1200),
 ]
 
 
 def build_case(L, species, families, conc, eci_kind, seed=3):
-    st = syn.fcc_settings(L, species, families)
+    st = syn.layered_settings(L, species) if families == "layered" else syn.fcc_settings(L, species, families)
     eci = syn.almg_ecis(st) if eci_kind == "almg" else syn.synthetic_ecis(st, seed=1234)
     symbols = syn.random_symbols(st, conc, seed=seed)
     ft = FlatTables(st, eci, symbols)

@@ -8,7 +8,8 @@ import re
 import numpy as np
 import pytest
 
-from cases import BINARY, GOLDEN, GOLDEN_WORKLOADS, TERNARY, build, load_golden, load_golden_workload
+from cases import (BINARY, GOLDEN, GOLDEN_WORKLOADS, LAYERED, LAYERED_BINARY, TERNARY, build, load_golden,
+                   load_golden_workload)
 from cemc_b200 import synthetic as syn
 from cemc_b200.tables import FlatTables, SelfInteractionError
 from oracle import ce_oracle, ref_driver
@@ -71,7 +72,9 @@ def test_oracle_proposals_reproduce_golden(name):
 
 @pytest.mark.skipif(not ref_driver.available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("case,mode", [(BINARY, "sgc"), (BINARY, "canonical"),
-                                       (TERNARY, "sgc"), (TERNARY, "canonical")])
+                                       (TERNARY, "sgc"), (TERNARY, "canonical"),
+                                       (LAYERED, "sgc"), (LAYERED, "canonical"),
+                                       (LAYERED_BINARY, "sgc"), (LAYERED_BINARY, "canonical")])
 def test_oracle_vs_compiled_reference(case, mode):
     st, eci, symbols, ft = build(**case)
     oc = OracleChain(ft, ft.occupancy(symbols), kT=0.04, seed=99, replica=1)
