@@ -129,9 +129,13 @@ SIGNATURES = {
     "cemc_run_canonical": [_H, C.c_int64],
     "cemc_set_trace": [_H, C.c_int64],
     "cemc_get_trace": [_H, C.c_int64, _i32p, _i8p, _f64p, _u8p, _f64p],
+    "cemc_energy_autocorrelation": [_H, C.c_int64, _f64p],
     "cemc_set_observe": [_H, C.c_int],
     "cemc_reset_accumulators": [_H, _f64p],
     "cemc_get_accumulators": [_H, _f64p],
+    "cemc_set_device_observers": [_H, C.c_int64, C.c_int, C.c_int64],
+    "cemc_reset_device_observers": [_H, _i8p],
+    "cemc_get_device_observers": [_H, _u64p, _f64p, _f64p, _f64p, _f64p, _i8p, _f64p, _f64p, C.c_int64],
     "cemc_pt_exchange": [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                          C.c_int, C.c_uint64, C.c_void_p],
     "cemc_energy_dev": [_H, C.POINTER(C.c_void_p)],

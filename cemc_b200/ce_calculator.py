@@ -172,44 +172,9 @@ class CE(object):
             atom.symbol = s
 
     def singlet2comp(self, singlets):
-        """Convert singlets to compositions (ce_calculator.py:450-518)."""
-        bfs = self.BC.basis_functions
-        if len(singlets.keys()) != len(bfs):
-            raise ValueError("The number singlet terms specified is different "
-                             "from the number of basis functions")
-        rhs = np.zeros(len(bfs))
-        spec_element = list(bfs[0].keys())[0]
-        for key, value in singlets.items():
-            dec = int(key[-1])
-            rhs[dec] = value - bfs[dec][spec_element]
-        matrix = np.zeros((len(bfs), len(bfs)))
-        for key in singlets.keys():
-            row = int(key[-1])
-            col = 0
-            for element in bfs[0].keys():
-                if element == spec_element:
-                    continue
-                matrix[row, col] = bfs[row][element] - bfs[row][spec_element]
-                col += 1
-        concs = np.linalg.solve(matrix, rhs)
-        eps = 1E-6
-        concs[(concs < 0.0) & (concs > -eps)] = 0.0
-        conc_spec_element = 1.0 - np.sum(concs)
-        if -eps < conc_spec_element < 0.0:
-            conc_spec_element = 0.0
-        if conc_spec_element > 1.0 or conc_spec_element < 0.0 or \
-                np.any(concs > 1.0) or np.any(concs < 0.0):
-            raise RuntimeError("Something went wrong when converting "
-                               "singlets to composition")
-        conc_dict = {}
-        counter = 0
-        for element in bfs[0].keys():
-            if element == spec_element:
-                conc_dict[element] = conc_spec_element
-            else:
-                conc_dict[element] = concs[counter]
-                counter += 1
-        return conc_dict
+        """Convert singlets ``{"c1_<d>": value}`` to concentrations (ce_calculator.py:450-518)."""
+        from .mcmc.stats import concentrations_from_named_singlets
+        return concentrations_from_named_singlets(self.BC.basis_functions, singlets)
 
     def set_singlets(self, singlets):
         self.set_composition(self.singlet2comp(singlets))

@@ -88,6 +88,12 @@ struct cemc_handle {
   double screen_slack = 1.0;          // testing: widen the Metropolis screening band
   bool autotune = true;               // pick the fastest kernel variant on long runs
   int tuned_sgc = -1, tuned_can = -1;  // variant chosen by the autotuner
+  // device-side state observers (cemc_set_device_observers)
+  long long obs_interval = 0, obs_step = 0, obs_capacity = 0;
+  int obs_flags = 0;
+  unsigned long long *ob_n = nullptr;
+  double *ob_cf_sum = nullptr, *ob_cf_sq = nullptr, *ob_best = nullptr, *ob_e = nullptr, *ob_order = nullptr;
+  int8_t *ob_best_occ = nullptr, *ob_occ_ref = nullptr;
   bool lat_verified = false;          // `trans` is a periodic shift table: index arithmetic usable
   bool observe = true;                // accumulate the Averager / SGCObserver sums during run_*
   int last_variant = -1;              // variant of the most recent Metropolis launch (cemc_last_variant)
@@ -324,6 +330,62 @@ __global__ void pt_exchange_kernel(int n_total, const double *energies, int32_t 
   __syncthreads();
   for (int r = threadIdx.x; r < R; r += blockDim.x) kT_local[r] = kT_of_slot[slot_of_replica[offset + r * stride]];
   if (threadIdx.x == 0 && n_accepted) { n_accepted[0] = s_acc; n_accepted[1] += s_acc; }
+}
+
+// Energy autocorrelation of the traced window, on the device (the trace never leaves it):
+// mean, variance and the first lag k with  sum_i d_i d_{i+k} / (n var) < 1/2,  d = E - mean
+// (the quantity Montecarlo._estimate_correlation_time derives its correlation time from,
+// cemc/mcmc/montecarlo.py:461-511).  One CTA per replica; lags are scanned in blocks of
+// blockDim.x until one falls below 1/2.  out[r] = {mean, var, first lag or -1, min ACF seen}.
+__global__ void autocorr_kernel(const double *trace, long long capacity, int n, double *out) {
+  const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const double *e = trace + (size_t)r * capacity;
+  __shared__ double red[256];
+  __shared__ int s_first;
+  __shared__ double s_min;
+  auto block_sum = [&](double v) {
+    red[tid] = v;
+    __syncthreads();
+    for (int s = nt / 2; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; __syncthreads(); }
+    const double t = red[0];
+    __syncthreads();
+    return t;
+  };
+  double acc = 0.0;
+  for (int i = tid; i < n; i += nt) acc += e[i];
+  const double mean = block_sum(acc) / (double)n;
+  acc = 0.0;
+  for (int i = tid; i < n; i += nt) { const double d = e[i] - mean; acc += d * d; }
+  const double var = block_sum(acc) / (double)n;
+  if (tid == 0) { s_first = 0x7fffffff; s_min = 1.0; }
+  __syncthreads();
+  if (var > 0.0) {
+    const double norm = 1.0 / ((double)n * var);
+    for (int k0 = 0; k0 < n; k0 += nt) {
+      const int k = k0 + tid;
+      if (k < n) {
+        double c = 0.0;
+        for (int i = 0; i + k < n; i++) c += (e[i] - mean) * (e[i + k] - mean);
+        c *= norm;
+        if (c < 0.5) atomicMin(&s_first, k);
+        // min over the scanned lags (only used for the "window too short" message)
+        unsigned long long *pm = reinterpret_cast<unsigned long long *>(&s_min);
+        unsigned long long old = *pm;
+        while (__longlong_as_double((long long)old) > c) {
+          const unsigned long long prev = atomicCAS(pm, old, (unsigned long long)__double_as_longlong(c));
+          if (prev == old) break;
+          old = prev;
+        }
+      }
+      __syncthreads();
+      if (s_first != 0x7fffffff) break;
+    }
+  }
+  if (tid == 0) {
+    out[4 * r] = mean; out[4 * r + 1] = var;
+    out[4 * r + 2] = s_first == 0x7fffffff ? -1.0 : (double)s_first;
+    out[4 * r + 3] = s_min;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -771,7 +833,8 @@ int cemc_destroy(cemc_handle *h) {
   cudaStreamSynchronize(h->stream);
   for (void *p : h->owned) cudaFree(p);
   void *extra[] = {h->d_sites, h->d_news, h->d_u, h->d_acc, h->d_e, h->tr_sites, h->tr_news,
-                   h->tr_u, h->tr_acc, h->tr_e, h->pt_scratch};
+                   h->tr_u, h->tr_acc, h->tr_e, h->pt_scratch, h->ob_n, h->ob_cf_sum, h->ob_cf_sq,
+                   h->ob_best, h->ob_e, h->ob_order, h->ob_best_occ, h->ob_occ_ref};
   for (void *p : extra) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1262,6 +1325,12 @@ static RunArgs run_args(cemc_handle *h, long long n_steps) {
   a.screen_slack = h->screen_slack;
   a.phase = h->d_phase;
   a.order = h->d_order;
+  if (h->obs_interval > 0) {
+    a.obs_interval = h->obs_interval; a.obs_origin = h->obs_step; a.obs_flags = h->obs_flags;
+    a.obs_capacity = h->obs_capacity; a.ob_n = h->ob_n; a.ob_cf_sum = h->ob_cf_sum; a.ob_cf_sq = h->ob_cf_sq;
+    a.ob_best = h->ob_best; a.ob_best_occ = h->ob_best_occ; a.ob_e = h->ob_e; a.ob_order = h->ob_order;
+    a.ob_occ_ref = h->ob_occ_ref;
+  }
   if (h->trace_capacity > 0) {
     a.tr_sites = h->tr_sites; a.tr_news = h->tr_news; a.tr_u = h->tr_u; a.tr_acc = h->tr_acc;
     a.tr_e = h->tr_e; a.tr_capacity = h->trace_capacity;
@@ -1315,7 +1384,10 @@ static int launch_variant_raw(cemc_handle *h, const RunArgs &a, int v);
 template <int MODE>
 static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
   const int rc = launch_variant_raw<MODE>(h, a, v);
-  if (rc == 0) h->last_variant = v;
+  if (rc == 0) {
+    h->last_variant = v;
+    if (a.obs_interval > 0) h->obs_step += a.n_steps;       // observer step counter (boundaries span launches)
+  }
   return rc;
 }
 
@@ -1341,6 +1413,7 @@ static bool variant_allowed(const cemc_handle *h, int v) {
   // the fp64 kernels would make the result depend on the tuner's timing
   if (h->fp32 && !h->spin_ok && (v == 0 || v == 5)) return false;
   if (v == 0 && h->batch > 0) return false;       // an explicit batch size asks for the batch kernel
+  if (v == 0 && h->obs_interval > 0) return false;   // the warp-per-replica kernel has no observer boundaries
   if ((v >= 1 && v <= 4) || v >= 6) {
     static const int Bs[10] = {0, 16, 16, 8, 4, 0, 8, 16, 16, 8}, Cs[10] = {0, 2, 1, 1, 1, 0, 1, 1, 2, 2};
     if (h->batch > 0 && h->batch != Bs[v]) return false;
@@ -1408,8 +1481,8 @@ static int run_tuned(cemc_handle *h, long long n_steps) {
   }
   if (done >= n_steps) return 0;
   RunArgs a = run_args(h, n_steps - done);
-  if (best >= 0) {
-    const int rc = launch_variant<MODE>(h, a, best);
+  if (best >= 0 && variant_allowed(h, best)) {       // (a tuned / pinned variant can become inapplicable:
+    const int rc = launch_variant<MODE>(h, a, best);  //  e.g. the spin kernel once device observers are on)
     if (rc != -1) return rc;
   }
   for (int v = 0; v < kNumVariants; v++) {          // default preference order
@@ -1597,6 +1670,22 @@ int cemc_get_trace(cemc_handle *h, int64_t n_steps, int32_t *sites, int8_t *news
   return 0;
 }
 
+int cemc_energy_autocorrelation(cemc_handle *h, int64_t n_steps, double *out) {
+  if (!h || !out) return fail("null argument");
+  if (n_steps < 2 || n_steps > h->trace_capacity) return fail("the trace does not hold that many steps");
+  if (n_steps > 0x7fffffff) return fail("window too long");
+  CU(cudaSetDevice(h->device));
+  double *d_out = nullptr;
+  CU(cudaMalloc((void **)&d_out, sizeof(double) * 4 * h->R));
+  autocorr_kernel<<<h->R, 256, 0, h->stream>>>(h->tr_e, h->trace_capacity, (int)n_steps, d_out);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, d_out, sizeof(double) * 4 * h->R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(d_out);
+  return 0;
+}
+
 // ---- the reference's per-call surface ---------------------------------------
 int cemc_trial_changes(cemc_handle *h, int replica, int n_changes, const int32_t *sites,
                        const int8_t *old_species, const int8_t *new_species, double *energy_out) {
@@ -1714,6 +1803,85 @@ int cemc_get_accumulators(cemc_handle *h, double *acc) {
   CU(cudaSetDevice(h->device));
   CU(cudaMemcpyAsync(acc, h->st.acc, sizeof(double) * h->R * h->acc_stride, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return check_status(h);
+}
+
+// ---- device-side state observers ---------------------------------------------------
+static void free_device_observers(cemc_handle *h) {
+  void **ps[] = {(void **)&h->ob_n, (void **)&h->ob_cf_sum, (void **)&h->ob_cf_sq, (void **)&h->ob_best,
+                 (void **)&h->ob_e, (void **)&h->ob_order, (void **)&h->ob_best_occ, (void **)&h->ob_occ_ref};
+  for (void **p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
+  h->obs_interval = 0; h->obs_flags = 0; h->obs_capacity = 0; h->obs_step = 0;
+}
+
+int cemc_reset_device_observers(cemc_handle *h, const int8_t *occ_ref) {
+  if (!h) return fail("null handle");
+  if (h->obs_interval <= 0) return fail("device observers are not enabled");
+  CU(cudaSetDevice(h->device));
+  const size_t R = (size_t)h->R, n = (size_t)h->t.n_eci, N = (size_t)h->t.N;
+  CU(cudaMemsetAsync(h->ob_n, 0, sizeof(unsigned long long) * R, h->stream));
+  CU(cudaMemsetAsync(h->ob_cf_sum, 0, sizeof(double) * R * n, h->stream));
+  CU(cudaMemsetAsync(h->ob_cf_sq, 0, sizeof(double) * R * n, h->stream));
+  CU(cudaMemsetAsync(h->ob_order, 0, sizeof(double) * R * 2, h->stream));
+  CU(cudaMemsetAsync(h->ob_e, 0, sizeof(double) * R * (size_t)std::max<long long>(h->obs_capacity, 1), h->stream));
+  std::vector<double> best(R * (1 + n), 0.0);
+  for (size_t r = 0; r < R; r++) best[r * (1 + n)] = INFINITY;      // LowestEnergyStructure.reset (:150)
+  CU(cudaMemcpyAsync(h->ob_best, best.data(), sizeof(double) * best.size(), cudaMemcpyHostToDevice, h->stream));
+  if (occ_ref) CU(cudaMemcpyAsync(h->ob_occ_ref, occ_ref, R * N, cudaMemcpyHostToDevice, h->stream));
+  else CU(cudaMemcpyAsync(h->ob_occ_ref, h->st.occ, R * N, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->ob_best_occ, h->st.occ, R * N, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));      // `best` / occ_ref are host buffers of this call
+  h->obs_step = 0;
+  return 0;
+}
+
+int cemc_set_device_observers(cemc_handle *h, int64_t interval, int flags, int64_t capacity) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  free_device_observers(h);
+  if (interval <= 0 || flags == 0) return 0;
+  if (flags & ~15) return fail("unknown observer flag");
+  if (capacity < 0) return fail("negative sample capacity");
+  const size_t R = (size_t)h->R, n = (size_t)h->t.n_eci, N = (size_t)h->t.N;
+  CU(cudaMalloc((void **)&h->ob_n, sizeof(unsigned long long) * R));
+  CU(cudaMalloc((void **)&h->ob_cf_sum, sizeof(double) * R * n));
+  CU(cudaMalloc((void **)&h->ob_cf_sq, sizeof(double) * R * n));
+  CU(cudaMalloc((void **)&h->ob_best, sizeof(double) * R * (1 + n)));
+  CU(cudaMalloc((void **)&h->ob_e, sizeof(double) * R * (size_t)std::max<int64_t>(capacity, 1)));
+  CU(cudaMalloc((void **)&h->ob_order, sizeof(double) * R * 2));
+  CU(cudaMalloc((void **)&h->ob_best_occ, R * N));
+  CU(cudaMalloc((void **)&h->ob_occ_ref, R * N));
+  h->obs_interval = interval; h->obs_flags = flags; h->obs_capacity = capacity;
+  return cemc_reset_device_observers(h, nullptr);
+}
+
+int cemc_get_device_observers(cemc_handle *h, uint64_t *n_samples, double *cf_sum, double *cf_sq,
+                              double *best_energy, double *best_cf, int8_t *best_occ,
+                              double *site_order, double *energies, int64_t n_energies) {
+  if (!h) return fail("null handle");
+  if (h->obs_interval <= 0) return fail("device observers are not enabled");
+  CU(cudaSetDevice(h->device));
+  const size_t R = (size_t)h->R, n = (size_t)h->t.n_eci, N = (size_t)h->t.N;
+  if (n_energies > h->obs_capacity) return fail("more energy samples requested than the capacity");
+  std::vector<double> best;
+  if (n_samples) CU(cudaMemcpyAsync(n_samples, h->ob_n, sizeof(uint64_t) * R, cudaMemcpyDeviceToHost, h->stream));
+  if (cf_sum) CU(cudaMemcpyAsync(cf_sum, h->ob_cf_sum, sizeof(double) * R * n, cudaMemcpyDeviceToHost, h->stream));
+  if (cf_sq) CU(cudaMemcpyAsync(cf_sq, h->ob_cf_sq, sizeof(double) * R * n, cudaMemcpyDeviceToHost, h->stream));
+  if (best_energy || best_cf) {
+    best.resize(R * (1 + n));
+    CU(cudaMemcpyAsync(best.data(), h->ob_best, sizeof(double) * best.size(), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (best_occ) CU(cudaMemcpyAsync(best_occ, h->ob_best_occ, R * N, cudaMemcpyDeviceToHost, h->stream));
+  if (site_order) CU(cudaMemcpyAsync(site_order, h->ob_order, sizeof(double) * R * 2, cudaMemcpyDeviceToHost, h->stream));
+  if (energies && n_energies > 0)
+    CU(cudaMemcpy2DAsync(energies, sizeof(double) * (size_t)n_energies, h->ob_e, sizeof(double) * (size_t)h->obs_capacity,
+                         sizeof(double) * (size_t)n_energies, R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (size_t r = 0; r < R && !best.empty(); r++) {
+    if (best_energy) best_energy[r] = best[r * (1 + n)];
+    if (best_cf) memcpy(best_cf + r * n, &best[r * (1 + n) + 1], sizeof(double) * n);
+  }
   return check_status(h);
 }
 

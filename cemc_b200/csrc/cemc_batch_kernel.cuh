@@ -378,6 +378,12 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // replay of recorded proposals / uniforms: the ring is filled from
   // rp_sites / rp_news / rp_u instead of the Philox stream; records hold sites, not list slots
   const bool replay = (a.rp_sites != nullptr);
+  // observer boundaries (cemc_set_device_observers): batches end on them, so that the bookkeeper
+  // sees the chain's state of the boundary step (the occupations only change in the D phase)
+  // (32-bit countdowns: intervals >= 2^30 steps never fire inside one launch segment anyway)
+  const int ob_iv = (a.obs_interval > 0 && a.obs_interval < (1ll << 30)) ? (int)a.obs_interval : 0;
+  int to_ob = ob_iv > 0 ? ob_iv - (int)(a.obs_origin % ob_iv) : 0x7fffffff;     // moves until the next boundary
+  int bk_to_ob = to_ob;                                                         // the bookkeeper's lagging copy
   // translation-invariant lattice: lane c derives T(site, c) from the site index (no table gather)
   const bool lat_ok = t.lat_ok != 0;
   const uint32_t my_shift = (lat_ok && lane < K) ? t.col_shift[lane] : 0u;
@@ -584,6 +590,13 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     }
     __syncwarp();
     CEMC_OTICK(17);
+    if (ob_iv > 0) {
+      bk_to_ob -= nd;
+      if (bk_to_ob <= 0) {               // the batch ended on an observer boundary
+        bk_to_ob += ob_iv;
+        observer_boundary(a, r, lane, n_eci, N, s.Ch + (nd - 1) * 32, e_cur, s.occ);
+      }
+    }
     if (!observe) return;
     if (ref_is_one) {            // Averager reference value 1: value / ref is the value itself
       int b = 0;
@@ -634,7 +647,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   long long sdone = 0;                 // moves decided so far
 
   while (sdone < a.n_steps) {
-    const int nb = (int)((a.n_steps - sdone) < BT ? (a.n_steps - sdone) : BT);
+    int nb = (int)((a.n_steps - sdone) < BT ? (a.n_steps - sdone) : BT);
+    if (to_ob < nb) nb = to_ob;
     if (remote && tid == 0) mbar_expect_tx(s.mbar + 2, 8u);          // this batch's decision record
     CEMC_TICK(0);
 
@@ -1256,6 +1270,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       const int2 ct = (kAsync && crank == 1) ? ct_early : *reinterpret_cast<const int2 *>(s.ctl);
       bk_nd = ct.x; bk_am = (uint32_t)ct.y; bk_base = sdone;
       sdone += ct.x;
+      if (ob_iv > 0) { to_ob -= ct.x; if (to_ob <= 0) to_ob += ob_iv; }
       par ^= 1;
     }
     CEMC_TICK(4);

@@ -89,10 +89,16 @@ class SGCObserver(MCObserver):
 
 
 # ---- observers of the chain state ---------------------------------
-# Called at their ``interval`` like in the reference: the samplers stop the device loop on
-# the boundary, mirror the occupations into ``atoms`` and pass the NET changes since the
-# previous call (``Montecarlo._steps``).  All four only look at the state on the boundary
-# (energy, CFs, symbols), which is what the reference's versions see at that step too.
+# All of them only look at the state on their boundary (energy, CFs, symbols), which is what
+# the reference's versions see at that step too.  Two ways of running them:
+#   * on the DEVICE (``device_flag``): when every attached observer is one of these and they
+#     share one interval, the kernels fold them every ``interval`` steps
+#     (include/cemc_b200.h, cemc_set_device_observers) and ``load_device`` mirrors the sums
+#     back once per launch chunk -- the device loop never stops for an observer;
+#   * on the HOST (``__call__``), like in the reference: the samplers stop the device loop on
+#     the boundary, mirror the occupations into ``atoms`` and pass the NET changes since the
+#     observer's previous call (``Montecarlo._steps``); used for mixed intervals or when a
+#     user-defined observer is attached as well.
 
 class PairCorrelationObserver(MCObserver):
     """Thermal average and spread of the pair correlation functions
@@ -119,6 +125,15 @@ class PairCorrelationObserver(MCObserver):
             v = now[k]
             self.cf[k] += v
             self.cf_squared[k] += v * v
+
+    device_flag = 1            # CEMC_OBS_CF_SUMS
+
+    def load_device(self, mc, blk, n, new_energies):
+        idx = self.ce_calc.updater.tables.eci_index
+        self.n_entries = n
+        for k in self._names:
+            self.cf[k] = float(blk["cf_sum"][0, idx[k]])
+            self.cf_squared[k] = float(blk["cf_sq"][0, idx[k]])
 
     def get_averages(self):
         return {k: v / self.n_entries for k, v in self.cf.items()}
@@ -152,6 +167,20 @@ class LowestEnergyStructure(MCObserver):
         self.lowest_energy = self.mc_obj.current_energy
         self.lowest_energy_cf = self.ce_calc.get_cf()
         self.atoms = self.mc_obj.atoms.copy()
+        self.lowest_energy_atoms = self.atoms
+
+    device_flag = 2            # CEMC_OBS_LOWEST
+
+    def load_device(self, mc, blk, n, new_energies):
+        e = float(blk["best_energy"][0])
+        if n == 0 or not np.isfinite(e) or (self.atoms is not None and e >= self.lowest_energy):
+            return
+        tables = self.ce_calc.updater.tables
+        self.lowest_energy = e
+        self.lowest_energy_cf = {name: float(v) for name, v in zip(tables.eci_names, blk["best_cf"][0])}
+        self.atoms = self.mc_obj.atoms.copy()
+        for atom, sym in zip(self.atoms, tables.symbols_of(blk["best_occ"][0])):
+            atom.symbol = sym
         self.lowest_energy_atoms = self.atoms
 
     def __call__(self, system_changes):
@@ -198,6 +227,13 @@ class SiteOrderParameter(MCObserver):
         self.avg_num_changed += self.current_num_changed
         self.avg_num_changed_sq += self.current_num_changed ** 2
 
+    device_flag = 8            # CEMC_OBS_SITE_ORDER (reference configuration: ``orig_symbols``)
+
+    def load_device(self, mc, blk, n, new_energies):
+        self.num_calls = n
+        self.avg_num_changed = float(blk["site_order"][0, 0])
+        self.avg_num_changed_sq = float(blk["site_order"][0, 1])
+
     def get_averages(self):
         avg = float(self.avg_num_changed) / self.num_calls
         var = max(float(self.avg_num_changed_sq) / self.num_calls - avg ** 2, 0.0)
@@ -212,6 +248,11 @@ class EnergyEvolution(MCObserver):
         self.name = "EnergyEvolution"
         self.mc = mc_obj
         self.energies = []
+
+    device_flag = 4            # CEMC_OBS_ENERGY
+
+    def load_device(self, mc, blk, n, new_energies):
+        self.energies.extend(new_energies)
 
     def __call__(self, system_changes):
         self.energies.append(self.mc.current_energy_without_vib())
@@ -259,8 +300,16 @@ class EnergyHistogram(MCObserver):
             self._histogram[self._get_indx(e)] += 1
         self.sample_in_buffer = False
 
+    device_flag = 4            # CEMC_OBS_ENERGY
+
+    def load_device(self, mc, blk, n, new_energies):
+        for E in new_energies:
+            self._add(E)
+
     def __call__(self, system_changes):
-        E = self.mc.current_energy_without_vib()
+        self._add(self.mc.current_energy_without_vib())
+
+    def _add(self, E):
         if self.sample_in_buffer:
             self.buffer[self._next] = E
             self._next += 1

@@ -24,6 +24,7 @@ import time
 
 import numpy as np
 
+from . import stats
 from .averager import Averager
 from .mc_observers import MCObserver  # noqa: F401
 
@@ -43,9 +44,7 @@ class CanNotFindLegalMoveError(Exception):
 
 
 def _norm_ppf(p):
-    """Inverse normal CDF (scipy.stats.norm.ppf without importing scipy early)."""
-    from scipy import stats
-    return stats.norm.ppf(p)
+    return stats.normal_quantile(p)
 
 
 class Montecarlo(object):
@@ -182,6 +181,7 @@ class Montecarlo(object):
         """Reset counters and averages (montecarlo.py:335-351)."""
         for interval, obs in self.observers:
             obs.reset()
+        self._reset_device_observers()
         self.current_step = 0
         self.num_accepted = 0
         self.mean_energy.clear()
@@ -236,8 +236,81 @@ class Montecarlo(object):
         self.energy_squared.set_sums(acc[2], acc[0])
         return acc
 
+    # ---- observers folded on the device (cemc_set_device_observers) -------------------
+    OBS_RING = 4096                 # energy samples kept on the device between two read-backs
+
+    def _device_observer_plan(self):
+        """(interval, flags) when EVERY attached observer is one of the fixed-semantics state
+        observers and they share one interval: the kernels then fold them every `interval` steps
+        and the host never stops the device loop.  None: the observers are called on the host."""
+        obs = self._state_observers()
+        if not obs:
+            return None
+        ivs = {iv for iv, _ in obs}
+        if len(ivs) != 1 or any(getattr(o, "device_flag", 0) == 0 for _, o in obs):
+            return None
+        flags = 0
+        for _, o in obs:
+            flags |= o.device_flag
+        return int(next(iter(ivs))), flags
+
+    def _state_observers(self):
+        """Attached observers except the per-step accumulators the kernels always keep
+        (SGCObserver: ``device_backed``)."""
+        return [(iv, o) for iv, o in self.observers if self._is_host_observer(o)]
+
+    def _arm_device_observers(self):
+        plan = self._device_observer_plan()
+        if plan == getattr(self, "_dev_obs_plan", None):
+            return plan
+        if plan is None:
+            self._gpu.set_device_observers(0, 0)
+        else:
+            self._gpu.set_device_observers(plan[0], plan[1], self.OBS_RING)
+        self._dev_obs_plan = plan
+        self._dev_obs_pulled = 0
+        self._reset_device_observers()
+        return plan
+
+    def _reset_device_observers(self):
+        if getattr(self, "_dev_obs_plan", None) is None:
+            return
+        ref = None
+        for _, o in self._state_observers():
+            if getattr(o, "orig_symbols", None) is not None:
+                ref = self._tables.occupancy(list(o.orig_symbols))[None]
+        self._gpu.reset_device_observers(ref)
+        self._dev_obs_pulled = 0
+
+    def _pull_device_observers(self):
+        """Mirror the device-side observer block into the attached observer objects."""
+        blk = self._gpu.get_device_observers()
+        n = int(blk["n_samples"][0])
+        cap = blk["energies"].shape[1]
+        if n - self._dev_obs_pulled > cap:
+            raise RuntimeError("device observer ring overflow")
+        new_e = [float(blk["energies"][0, k % cap]) for k in range(self._dev_obs_pulled, n)]
+        self._dev_obs_pulled = n
+        for _, o in self._state_observers():
+            o.load_device(self, blk, n, new_e)
+
     def _steps(self, n, observe=True):
         """n trial moves on the device, observers at their intervals."""
+        plan = self._arm_device_observers() if observe else None
+        if plan is not None:
+            chunk = max(plan[0], min(self.chunk_size, plan[0] * (self.OBS_RING // 2)))
+            done = 0
+            while done < n:
+                m = min(chunk, n - done)
+                self._device_run(m)
+                done += m
+                self.current_step += m
+                self._pull_device_observers()          # one read-back per chunk, not per interval
+            self.current_energy = float(self._gpu.get_energy()[0])
+            return
+        if getattr(self, "_dev_obs_plan", None) is not None and not observe:
+            self._gpu.set_device_observers(0, 0)       # legs nobody observes (bias probe, equilibration)
+            self._dev_obs_plan = None
         done = 0
         intervals = [iv for iv, _ in self.observers if self._is_host_observer(_)]
         if observe and intervals:
@@ -278,116 +351,105 @@ class Montecarlo(object):
         return self.current_energy, self.num_accepted > before
 
     # ---- correlation time / equilibration (montecarlo.py:461-697) --------------------
+    # The statistics themselves live in ``stats.py`` and work on device-side sums: the energy
+    # trace of the correlation-time window never leaves the GPU (cemc_energy_autocorrelation)
+    # and a window of the equilibration loop is one launch plus one read of the Averager sums.
     def _estimate_correlation_time(self, window_length=1000, restart=False):
         self.log("*********** Estimating correlation time ***************")
+        fresh = restart or not self.corrtime_energies
         if restart:
             self.corrtime_energies = []
+        self._gpu.set_observe(False)
         self._gpu.set_trace(window_length)
         self._device_run(window_length)
-        self._gpu.synchronize()
         self.current_step += window_length
-        e = self._gpu.get_trace(window_length)[4][0]
+        if fresh:
+            mean, var, lag, _ = self._gpu.energy_autocorrelation(window_length)[0]
+            self.corrtime_energies = [mean]            # the trace itself stays on the device
+        else:
+            # appended windows (restart=False, montecarlo.py:466-470): the whole record is needed
+            self.corrtime_energies += [float(x) for x in self._gpu.get_trace(window_length)[4][0]]
+            d = np.array(self.corrtime_energies) - np.mean(self.corrtime_energies)
+            var = float(np.mean(d * d))
+            acf = np.correlate(d, d, mode="full")[len(d) - 1:]
+            below = np.nonzero(acf < 0.5 * window_length * var)[0] if var > 0.0 else []
+            lag = float(below[0]) if len(below) else -1.0
         self._gpu.set_trace(0)
+        self._gpu.set_observe(True)
         self.current_energy = float(self._gpu.get_energy()[0])
-        self.corrtime_energies += [float(x) for x in e]
-        energies = np.array(self.corrtime_energies)
-        mean = np.mean(energies)
-        energy_dev = energies - mean
-        var = np.var(energy_dev)
-        auto_corr = np.correlate(energy_dev, energy_dev, mode="full")
-        auto_corr = auto_corr[int(len(auto_corr) / 2):]
-        self.correlation_info = {"correlation_time_found": False,
-                                 "correlation_time": 0.0, "msg": ""}
+        info = {"correlation_time_found": False, "correlation_time": 0.0, "msg": ""}
         if var == 0.0:
-            self.correlation_info["msg"] = "Zero variance leads to infinite correlation time"
-            self.correlation_info["correlation_time_found"] = True
-            self.correlation_info["correlation_time"] = window_length
-            return self.correlation_info
-        auto_corr /= (window_length * var)
-        if np.min(auto_corr) > 0.5:
-            self.correlation_info["msg"] = "Window is too short. Add more samples"
-            self.correlation_info["correlation_time"] = window_length
-            return self.correlation_info
-        indx = 0
-        for i in range(len(auto_corr)):
-            if auto_corr[i] < 0.5:
-                indx = i
-                break
-        rho = 2.0 ** (-1.0 / indx)
-        tau = -1.0 / np.log(rho)
-        self.correlation_info["correlation_time"] = tau
-        self.correlation_info["correlation_time_found"] = True
-        self.log("Estimated correlation time: {}".format(tau))
-        return self.correlation_info
+            info.update(msg="Zero variance leads to infinite correlation time",
+                        correlation_time_found=True, correlation_time=window_length)
+        else:
+            tau, found = stats.correlation_time(lag, window_length)
+            info["correlation_time"] = float(tau) if found else window_length
+            info["correlation_time_found"] = bool(found)
+            if not found:
+                info["msg"] = "Window is too short. Add more samples"
+            else:
+                self.log("Estimated correlation time: {}".format(float(tau)))
+        if info["msg"]:
+            self.log(info["msg"])
+        self.correlation_info = info
+        return info
+
+    def _known_correlation_time(self):
+        info = self.correlation_info
+        return info["correlation_time"] if info and info["correlation_time_found"] else None
 
     def _get_var_average_energy(self):
-        U = self.mean_energy.mean
-        E_sq = self.energy_squared.mean
-        var = (E_sq - U ** 2)
-        nproc = 1
-        if var < 0.0:
-            var = np.abs(var)
-        no_corr_info = self.correlation_info is None
-        cr_time_found = (not no_corr_info) and self.correlation_info["correlation_time_found"]
-        if no_corr_info or not cr_time_found:
-            return var / (self.current_step * nproc)
-        tau = self.correlation_info["correlation_time"]
-        if tau < 1.0:
-            tau = 1.0
-        return 2.0 * var * tau / (self.current_step * nproc)
+        return float(stats.variance_of_mean(self.mean_energy.mean, self.energy_squared.mean,
+                                            self.current_step, self._known_correlation_time()))
 
     def _composition_reached_equillibrium(self, prev_composition, var_prev,
                                           confidence_level=0.05):
-        return True, prev_composition, var_prev, 0.0
+        return True, prev_composition, var_prev, 0.0       # fixed composition (:528-539)
 
     def _equillibriate(self, window_length="auto", confidence_level=0.05,
                        maxiter=1000, mode="stat_equiv"):
-        """Run MC until two consecutive windows have statistically equal mean
-        energies (montecarlo.py:541-697); each window is one device launch."""
+        """Run windows of ``window_length`` moves (one launch each) until the mean energies of
+        two consecutive windows agree at ``confidence_level`` -- and, for the SGC sampler, the
+        average singlets do too (montecarlo.py:541-697).  ``equil_history`` records
+        (mean, variance of the mean, z) of every window for inspection / tests."""
         if mode not in ("stat_equiv", "fixed"):
             raise ValueError("Equilibration mode has to be one of ['stat_equiv', 'fixed']")
         if window_length == "auto":
             window_length = 10 * len(self.atoms)
         self.reset()
+        self.equil_history = []
         if mode == "fixed":
             self._steps(window_length, observe=False)
             return
-        E_prev = None
-        var_E_prev = None
-        min_percentile = _norm_ppf(confidence_level)
-        max_percentile = _norm_ppf(1.0 - confidence_level)
+        previous = None
         composition, var_comp = [], []
-        energy_conv = False
-        for it in range(maxiter):
+        energy_ok = False
+        for window in range(maxiter):
             self.reset()
             self._steps(window_length, observe=False)
             self._pull_averages()
             self._on_window_done()
-            E_new = self.mean_energy.mean
-            var_E_new = self._get_var_average_energy()
-            comp_conv, composition, var_comp, comp_quant = \
-                self._composition_reached_equillibrium(
-                    composition, var_comp, confidence_level=confidence_level)
-            if E_prev is None:
-                E_prev, var_E_prev = E_new, var_E_new
+            now = (self.mean_energy.mean, self._get_var_average_energy())
+            comp_ok, composition, var_comp, comp_z = self._composition_reached_equillibrium(
+                composition, var_comp, confidence_level=confidence_level)
+            if previous is None:
+                previous = now
+                self.equil_history.append((now[0], now[1], None))
                 continue
-            var_diff = var_E_new + var_E_prev
-            diff = E_new - E_prev
-            if var_diff < 1E-6:
-                z_diff = 0.0
-                comp_conv = True
-            else:
-                z_diff = diff / np.sqrt(var_diff)
-            if min_percentile < z_diff < max_percentile:
-                energy_conv = True
-            if energy_conv and comp_conv:
+            z, frozen = stats.z_score(now[0], now[1], previous[0], previous[1])
+            self.equil_history.append((now[0], now[1], float(z)))
+            if frozen:
+                self.log("Zero variance. System does not move.")
+                comp_ok = True
+            energy_ok = energy_ok or bool(stats.inside(z, confidence_level))
+            if energy_ok and comp_ok:
                 self.log("System reached equillibrium in {} mc steps".format(
-                    (it + 1) * window_length))
+                    (window + 1) * window_length))
                 self.mean_energy.clear()
                 self.energy_squared.clear()
                 self.current_step = 0
                 return
-            E_prev, var_E_prev = E_new, var_E_new
+            previous = now
         raise DidNotReachEquillibriumError("Did not manage to reach equillibrium!")
 
     def _on_window_done(self):
@@ -416,9 +478,8 @@ class Montecarlo(object):
 
     def _has_converged_prec_mode(self, prec=0.01, confidence_level=0.05,
                                  log_status=False):
-        percentile = _norm_ppf(1.0 - confidence_level)
-        var_E = self._get_var_average_energy()
-        return var_E < (prec / percentile) ** 2
+        """std of the mean energy below prec / z_{1-confidence} (montecarlo.py:699-730)."""
+        return self._get_var_average_energy() < (prec / stats.normal_quantile(1.0 - confidence_level)) ** 2
 
     # ---- the run ---------------------------------------------------------------------
     def runMC(self, mode="fixed", steps=10, verbose=False, equil=True,

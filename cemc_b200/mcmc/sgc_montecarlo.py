@@ -9,6 +9,7 @@ step.
 import numpy as np
 
 from . import montecarlo as mc
+from . import stats
 from .mc_observers import SGCObserver
 from .montecarlo import KB
 
@@ -71,47 +72,30 @@ class SGCMonteCarlo(mc.Montecarlo):
         self._pull_averages()
 
     # ---- variances / equilibrium of the composition (:86-221) --------------------
+    def _mean_singlets(self):
+        n = self.averager.counter
+        return self.averager.singlets / n, self.averager.quantities["singlets_sq"] / n, n
+
     def _get_var_average_singlets(self):
-        N = self.averager.counter
-        singlets = self.averager.quantities["singlets"] / N
-        singlets_sq = self.averager.quantities["singlets_sq"] / N
-        var_n = singlets_sq - singlets ** 2
-        nproc = 1
-        no_corr_info = self.correlation_info is None
-        corr_time_found = (not no_corr_info) and self.correlation_info["correlation_time_found"]
-        if no_corr_info or not corr_time_found:
-            return var_n / (N * nproc)
-        if not np.all(var_n > 0.0):
-            var_n = np.abs(var_n)
-        tau = self.correlation_info["correlation_time"]
-        if tau < 1.0:
-            tau = 1.0
-        return 2.0 * var_n * tau / (N * nproc)
+        mean, mean_sq, n = self._mean_singlets()
+        return stats.variance_of_mean(mean, mean_sq, n, self._known_correlation_time(),
+                                      fold_negative=False)
 
     def _composition_reached_equillibrium(self, prev_composition, var_prev,
                                           confidence_level=0.05):
-        min_percentile = mc._norm_ppf(confidence_level)
-        max_percentile = mc._norm_ppf(1.0 - confidence_level)
-        N = self.averager.counter
-        singlets = self.averager.singlets / N
-        var_n = self._get_var_average_singlets()
+        """Window test on the average singlets (sgc_montecarlo.py:172-210): returns
+        (converged, singlets, variances, largest z)."""
+        singlets = self._mean_singlets()[0]
+        var_n = np.maximum(self._get_var_average_singlets(), 0.0)
         if len(prev_composition) != len(singlets):
-            return False, singlets, var_n, 0.0
-        var_n[var_n < 0.0] = 0.0
-        diff = singlets - prev_composition
-        var_diff = var_n + var_prev
-        if len(var_diff[var_diff > 0.0]) == 0:
-            return True, singlets, var_n, 0.0
-        z = np.abs(diff[var_diff > 0.0]) / np.sqrt(var_diff[var_diff > 0.0])
-        z = np.max(z)
-        converged = bool(min_percentile < z < max_percentile)
-        return converged, singlets, var_n, z
+            return False, singlets, var_n, 0.0               # first window: nothing to compare with
+        agree, z = stats.singlets_agree(singlets, var_n, prev_composition, var_prev, confidence_level)
+        return agree, singlets, var_n, z
 
     def _has_converged_prec_mode(self, prec=0.01, confidence_level=0.05,
                                  log_status=False):
-        percentile = mc._norm_ppf(1.0 - confidence_level)
-        var_n = self._get_var_average_singlets()
-        return bool(np.max(var_n) < (prec / percentile) ** 2)
+        limit = (prec / stats.normal_quantile(1.0 - confidence_level)) ** 2
+        return bool(np.max(self._get_var_average_singlets()) < limit)
 
     # ---- chemical potential (:219-278) ----------------------------------------------
     @property
@@ -187,46 +171,33 @@ class SGCMonteCarlo(mc.Montecarlo):
         self._pull_averages()
 
     def singlet2composition(self, avg_singlets):
+        """Concentrations from the average singlets (sgc_montecarlo.py:380-396)."""
         bf = self.atoms.get_calculator().BC.basis_functions
-        matrix = np.zeros((len(self.symbols), len(self.symbols)))
-        index = {s: i for i, s in enumerate(self.symbols)}
-        for i, b in enumerate(bf):
-            for s, col in index.items():
-                matrix[i, col] = b[s]
-        matrix[-1, :] = 1.0
-        rhs = np.zeros(len(self.symbols))
-        rhs[:-1] = avg_singlets
-        rhs[-1] = 1.0
-        x = np.linalg.solve(matrix, rhs)
-        return {s + "_conc": x[i] for s, i in index.items()}
+        return stats.concentrations_from_singlets(bf, list(self.symbols), avg_singlets)
 
     def get_thermodynamic(self, reset_ecis=True):
-        """Thermodynamic quantities (sgc_montecarlo.py:398-448)."""
-        N = self.averager.counter
-        quantities = {}
-        singlets = self.averager.singlets / N
-        singlets_sq = self.averager.quantities["singlets_sq"] / N
-        quantities["sgc_energy"] = self.averager.energy.mean + self.energy_bias
-        quantities["sgc_heat_capacity"] = self.averager.energy_sq.mean - \
-            self.averager.energy.mean ** 2
-        quantities["sgc_heat_capacity"] /= (KB * self.T ** 2)
-        quantities["energy"] = self.averager.energy.mean + self.energy_bias
+        """Thermodynamic quantities of the run, under the reference's keys
+        (sgc_montecarlo.py:398-448): the SGC energy / heat capacity come from the SGCObserver
+        sums, the internal energy adds back mu * <singlet> * N for every chemical potential."""
+        mean, mean_sq, n = self._mean_singlets()
+        e_avg, e_sq = self.averager.energy.mean, self.averager.energy_sq.mean
         natoms = len(self.atoms)
-        for i in range(len(self.chem_pots)):
-            quantities["energy"] += self.chem_pots[i] * singlets[i] * natoms
-        quantities["temperature"] = self.T
-        quantities["n_mc_steps"] = self.averager.counter
-        for i in range(len(singlets)):
-            quantities["singlet_{}".format(self.chem_pot_names[i])] = singlets[i]
-            quantities["var_singlet_{}".format(self.chem_pot_names[i])] = \
-                singlets_sq[i] - singlets[i] ** 2
-            quantities["mu_{}".format(self.chem_pot_names[i])] = self.chem_pots[i]
-        quantities.update(self.meta_info)
+        q = {"sgc_energy": e_avg + self.energy_bias,
+             "sgc_heat_capacity": (e_sq - e_avg ** 2) / (KB * self.T ** 2),
+             "energy": e_avg + self.energy_bias,
+             "temperature": self.T,
+             "n_mc_steps": n}
+        for name, mu, m, m2 in zip(self.chem_pot_names, self.chem_pots, mean, mean_sq):
+            q["energy"] += mu * m * natoms
+            q["singlet_" + name] = m
+            q["var_singlet_" + name] = m2 - m ** 2
+            q["mu_" + name] = mu
+        q.update(self.meta_info)
         try:
-            quantities.update(self.singlet2composition(singlets))
-        except Exception as exc:           # same behaviour as the reference (:440-444)
+            q.update(self.singlet2composition(mean))
+        except Exception as exc:           # the reference reports and carries on (:440-444)
             print("Could not find average singlets!")
             print(exc)
         if reset_ecis:
             self._reset_eci_to_original(self.atoms.get_calculator().eci)
-        return quantities
+        return q

@@ -286,6 +286,13 @@ class BatchedCEUpdater(object):
             _p(u, C.c_double), _p(acc, C.c_uint8), _p(e, C.c_double)))
         return sites, news, u, acc, e
 
+    def energy_autocorrelation(self, n: int):
+        """[R, 4]: mean, variance, first lag with normalised autocorrelation < 1/2 (or -1),
+        smallest normalised autocorrelation seen -- of the energies traced by the last run."""
+        out = np.zeros((self.R, 4), dtype=np.float64)
+        _lib.check(self.lib.cemc_energy_autocorrelation(self._h, C.c_int64(int(n)), _p(out, C.c_double)))
+        return out
+
     # ---- observers -----------------------------------------------------------
     def set_observe(self, on: bool):
         """Switch the per-step Averager / SGCObserver sums of run_* on or off."""
@@ -303,6 +310,39 @@ class BatchedCEUpdater(object):
         _lib.check(self.lib.cemc_get_accumulators(self._h,
                                                   _p(acc, C.c_double)))
         return acc
+
+    # ---- device-side state observers ---------------------------------------------
+    OBS_CF_SUMS, OBS_LOWEST, OBS_ENERGY, OBS_SITE_ORDER = 1, 2, 4, 8
+
+    def set_device_observers(self, interval: int, flags: int, capacity: int = 0):
+        _lib.check(self.lib.cemc_set_device_observers(self._h, C.c_int64(int(interval)),
+                                                      int(flags), C.c_int64(int(capacity))))
+        self._obs_capacity = int(capacity) if interval > 0 and flags else 0
+
+    def reset_device_observers(self, occ_ref=None):
+        if occ_ref is not None:
+            occ_ref = np.ascontiguousarray(occ_ref, dtype=np.int8).reshape(self.R, self.N)
+        _lib.check(self.lib.cemc_reset_device_observers(self._h, _p(occ_ref, C.c_int8)))
+
+    def get_device_observers(self):
+        """dict: n_samples [R], cf_sum / cf_sq [R, n_eci], best_energy [R], best_cf [R, n_eci],
+        best_occ [R, N], site_order [R, 2] (sum, sum of squares), energies [R, capacity] (ring:
+        the energy of boundary k is energies[:, k % capacity])."""
+        n = np.zeros(self.R, dtype=np.uint64)
+        _lib.check(self.lib.cemc_get_device_observers(self._h, _p(n, C.c_uint64), None, None, None, None,
+                                                      None, None, None, C.c_int64(0)))
+        ne = int(getattr(self, "_obs_capacity", 0))      # the whole ring; sample k sits at k % capacity
+        out = dict(n_samples=n, cf_sum=np.zeros((self.R, self.n_eci)), cf_sq=np.zeros((self.R, self.n_eci)),
+                   best_energy=np.zeros(self.R), best_cf=np.zeros((self.R, self.n_eci)),
+                   best_occ=np.zeros((self.R, self.N), dtype=np.int8), site_order=np.zeros((self.R, 2)),
+                   energies=np.zeros((self.R, max(ne, 1))))
+        _lib.check(self.lib.cemc_get_device_observers(
+            self._h, None, _p(out["cf_sum"], C.c_double), _p(out["cf_sq"], C.c_double),
+            _p(out["best_energy"], C.c_double), _p(out["best_cf"], C.c_double),
+            _p(out["best_occ"], C.c_int8), _p(out["site_order"], C.c_double),
+            _p(out["energies"], C.c_double) if ne else None, C.c_int64(ne)))
+        out["energies"] = out["energies"][:, :ne]
+        return out
 
     # ---- parallel tempering -----------------------------------------------------
     def energy_dev_ptr(self) -> int:

@@ -239,12 +239,44 @@ int cemc_get_trace(cemc_handle *h, int64_t n_steps, int32_t *sites /*[R][n][2]*/
                    int8_t *new_species /*[R][n][2]*/, double *uniforms /*[R][n]*/,
                    uint8_t *accepted /*[R][n]*/, double *e_after /*[R][n]*/);
 
+/* Statistics of the energies traced by the last run (cemc_set_trace), computed on the
+ * device so that the trace stays there: out[r] = {mean, variance, first lag k with
+ * autocorrelation(k) / (n var) < 1/2 or -1, smallest normalised autocorrelation seen}
+ * -- what Montecarlo._estimate_correlation_time (cemc/mcmc/montecarlo.py:461-511) needs. */
+int cemc_energy_autocorrelation(cemc_handle *h, int64_t n_steps, double *out /*[R][4]*/);
+
 /* ---- observers (Averager / SGCObserver sums) ---- */
 /* 0: run_sgc / run_canonical skip the per-step sums (legs whose averages nobody reads:
  * bias probes, equilibration windows, parallel-tempering burn-in); default 1             */
 int cemc_set_observe(cemc_handle *h, int on);
 int cemc_reset_accumulators(cemc_handle *h, const double *ref /*[R] or NULL (=1.0)*/);
 int cemc_get_accumulators(cemc_handle *h, double *acc /*[R][CEMC_ACC_STRIDE(D)]*/);
+
+/* ---- device-side state observers ----
+ * Observers of the chain state with fixed semantics, folded on the device every `interval`
+ * steps of run_sgc / run_canonical (no host round trip per interval; boundaries are counted
+ * across launches from the last reset):
+ *   CEMC_OBS_CF_SUMS    sum and sum of squares of every CF    PairCorrelationObserver  cemc/mcmc/mc_observers.py:81-136
+ *   CEMC_OBS_LOWEST     lowest energy on a boundary, its CFs
+ *                       and occupations (strictly lower wins)   LowestEnergyStructure    :138-183
+ *   CEMC_OBS_ENERGY     the energy on every boundary            EnergyEvolution / EnergyHistogram  :689-761
+ *   CEMC_OBS_SITE_ORDER number of sites differing from a
+ *                       reference configuration, sum / sum^2    SiteOrderParameter       :614-686          */
+enum cemc_observer_flag {
+  CEMC_OBS_CF_SUMS = 1, CEMC_OBS_LOWEST = 2, CEMC_OBS_ENERGY = 4, CEMC_OBS_SITE_ORDER = 8
+};
+/* interval <= 0 or flags == 0 switches them off; capacity = length of the per-replica ring of
+ * energy samples (sample k is stored at k % capacity: read it back before it wraps)           */
+int cemc_set_device_observers(cemc_handle *h, int64_t interval, int flags, int64_t capacity);
+/* zero the sums and the boundary counter; occ_ref [R][N] = reference configuration of
+ * CEMC_OBS_SITE_ORDER (NULL: the current occupations)                                         */
+int cemc_reset_device_observers(cemc_handle *h, const int8_t *occ_ref);
+/* any output pointer may be NULL                                                              */
+int cemc_get_device_observers(cemc_handle *h, uint64_t *n_samples /*[R]*/, double *cf_sum /*[R][n_eci]*/,
+                              double *cf_sq /*[R][n_eci]*/, double *best_energy /*[R]*/,
+                              double *best_cf /*[R][n_eci]*/, int8_t *best_occ /*[R][N]*/,
+                              double *site_order /*[R][2]*/, double *energies /*[R][n_energies]*/,
+                              int64_t n_energies);
 
 /* ---- parallel tempering ---- */
 /* One exchange sweep over temperature slots.  slot_of_replica[g] for all

@@ -10,6 +10,7 @@ from cemc_b200.ce_calculator import CE, get_atoms_with_ce_calc
 from cemc_b200.mcmc import (MCParameterSweep, Montecarlo, ParallelTempering,
                             SGCMonteCarlo, TooFewElementsError)
 from cemc_b200.mcmc.montecarlo import KB
+from cemc_b200.mcmc.mc_observers import MCObserver
 from oracle import ce_oracle
 from oracle.ce_oracle import OracleChain
 
@@ -268,10 +269,14 @@ def test_checkpoint_roundtrip(cuda_device, tmp_path):
     assert abs(calc2.get_energy() - calc.get_energy()) < 1e-12
 
 
-def test_state_observers_match_oracle(cuda_device):
+@pytest.mark.parametrize("where,variant", [("device", -1), ("device", 1), ("device", 3), ("device", 5), ("device", 9),
+                                           ("host", -1)])
+def test_state_observers_match_oracle(cuda_device, where, variant):
     """PairCorrelationObserver / LowestEnergyStructure / SiteOrderParameter / EnergyEvolution /
     EnergyHistogram see, on their interval boundaries, exactly the state
-    the oracle chain has after the same number of moves."""
+    the oracle chain has after the same number of moves -- folded on the device by the kernels'
+    bookkeeping warp (no launch boundary per interval), or called on the host when a
+    user-defined observer is attached as well."""
     from cemc_b200.mcmc import (EnergyEvolution, EnergyHistogram, LowestEnergyStructure,
                                 PairCorrelationObserver, SiteOrderParameter)
     st, eci, symbols, ft, atoms, calc = make_ce(TERNARY, seed=9)
@@ -283,7 +288,24 @@ def test_state_observers_match_oracle(cuda_device):
     order, evo, hist = SiteOrderParameter(atoms), EnergyEvolution(mc), EnergyHistogram(mc, buffer_size=8, n_bins=5)
     for o in (pair, low, order, evo, hist):
         mc.attach(o, interval=iv)
+    seen = []
+    if where == "host":
+        class Mine(MCObserver):
+            def __call__(self, system_changes):
+                seen.append(len(system_changes))
+        mc.attach(Mine(), interval=iv)
+    if variant >= 0:
+        mc._gpu.set_variant(variant, variant)
+    l0 = mc._gpu.launch_count()
     mc.runMC(steps=steps, equil=False)
+    launches = mc._gpu.launch_count() - l0
+    if where == "device":
+        assert mc._device_observer_plan() == (iv, 1 | 2 | 4 | 8)
+        assert launches < steps // iv            # the device loop did not stop on the boundaries
+        if variant >= 0:
+            assert mc._gpu.last_variant() == variant
+    else:
+        assert mc._device_observer_plan() is None and len(seen) == steps // iv
 
     # the same run on the oracle, stopped on the same boundaries
     oc = OracleChain(ft, ft.occupancy(symbols), cf=cf0, kT=T * KB, seed=77, ref=e0)
@@ -324,3 +346,63 @@ def test_state_observers_match_oracle(cuda_device):
     assert h.sum() == ncall and len(h) == 5
     assert hist.Emin == min(energies[:8]) and hist.Emax == max(energies[:8])
     del occ_start
+
+
+def test_equilibration_decisions_match_oracle(cuda_device):
+    """The equilibration phase of runMC -- correlation time from the device-side energy
+    autocorrelation (the trace never leaves the GPU), then windows until two consecutive mean
+    energies agree -- takes the decisions the reference's logic takes on the oracle chain:
+    same correlation time, same number of windows, same (mean, variance, z) per window
+    (cemc/mcmc/montecarlo.py:461-511, :541-697; restated in oracle/sampler_oracle.py)."""
+    from oracle import sampler_oracle
+    st, eci, symbols, ft, atoms, calc = make_ce(TERNARY, seed=4)
+    cf0 = calc.updater.batch.get_cf()[0]
+    e0 = calc.get_energy()
+    T, window = 900.0, 700
+    mc = Montecarlo(atoms, T, seed=31)
+    mc.runMC(steps=500, equil=True, equil_params={"window_length": window, "confidence_level": 0.3})
+    hist = mc.equil_history
+    assert len(hist) >= 2
+
+    oc = OracleChain(ft, ft.occupancy(symbols), cf=cf0, kT=T * KB, seed=31, ref=e0)
+    oc.run_canonical(1)                                      # runMC's first _mc_step (:765)
+    tr = oc.run_canonical(1000, trace=True)                  # correlation-time window (:461-470)
+    info = sampler_oracle.correlation_info(tr[4], 1000)
+    assert mc.correlation_info["correlation_time_found"] == info["correlation_time_found"]
+    assert mc.correlation_info["correlation_time"] == pytest.approx(info["correlation_time"], rel=1e-12)
+    want = sampler_oracle.equilibrate(oc, oc.run_canonical, window, 0.3, info, e0)
+    assert len(hist) == len(want)                            # same number of windows
+    for (e_g, v_g, z_g), (e_o, v_o, z_o) in zip(hist, want):
+        assert e_g == e_o                                    # the sums are bit-identical
+        assert v_g == pytest.approx(v_o, rel=1e-12)
+        assert (z_g is None and z_o is None) or z_g == pytest.approx(z_o, rel=1e-9, abs=1e-12)
+    # ... and the chain itself: after equilibration runMC probes the bias (1000 moves) and samples
+    oc.run_canonical(1000)
+    bias = oc.e
+    e = oc.eci.copy()
+    e[ft.eci_index["c0"]] -= bias / ft.N
+    oc.set_ecis(e)
+    oc.run_canonical(500)
+    assert [a.symbol for a in mc.atoms] == ft.symbols_of(oc.occ)
+
+
+def test_energy_autocorrelation_kernel(cuda_device):
+    """cemc_energy_autocorrelation against numpy on the same traced window, several replicas."""
+    st, eci, symbols, ft = build(**BINARY)
+    from cemc_b200.updater import BatchedCEUpdater
+    R, n = 3, 900
+    gpu = BatchedCEUpdater(ft, R)
+    occ = np.stack([ft.occupancy(syn.random_symbols(st, BINARY["conc"], seed=50 + r)) for r in range(R)])
+    gpu.set_occupancy(occ); gpu.recompute_cf(); gpu.set_kT([0.02, 0.05, 0.5]); gpu.seed(12)
+    gpu.set_trace(n)
+    gpu.run_canonical(n)
+    out = gpu.energy_autocorrelation(n)
+    e = gpu.get_trace(n)[4]
+    for r in range(R):
+        d = e[r] - e[r].mean()
+        var = np.mean(d * d)
+        acf = np.correlate(d, d, mode="full")[n - 1:] / (n * var)
+        first = int(np.nonzero(acf < 0.5)[0][0])
+        assert out[r, 0] == pytest.approx(e[r].mean(), rel=1e-13)
+        assert out[r, 1] == pytest.approx(var, rel=1e-10)
+        assert int(out[r, 2]) == first
