@@ -647,7 +647,7 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   std::vector<int4> tb_task;
   std::vector<double> tb_tab;
   {
-    bool ok = (tb->n_symm == 1 && n_eci <= 32 && K <= 31 && S <= 9);
+    bool ok = (tb->n_symm == 1 && n_eci <= 32 && K <= 63 && S <= 9);      // K > 31: two columns per lane
     auto power = [&](int e) { int v = 1; for (int q = 0; q < e; q++) v *= S; return v; };
     std::vector<std::vector<std::vector<int>>> fam_decos(tb->n_fam);     // distinct decorations per family
     std::vector<std::pair<int, int>> task_fd;                            // task -> (family, decoration index)
@@ -1065,8 +1065,10 @@ int cemc_set_observe(cemc_handle *h, int on) {
 
 static bool batch_applicable(const cemc_handle *h) {
   const bool spin_eval = h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4;
+  const bool tab_eval = h->tab_ok && (h->fp32 || !h->no_tab);
+  // K <= 31 translation columns (one per lane); the spin and table evaluations also take 32..63
   return !(h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
-           h->t.KP > (spin_eval ? 64 : 32));
+           h->t.KP > ((spin_eval || tab_eval) ? 64 : 32));
 }
 
 int cemc_batch_applicable(cemc_handle *h, int *yes) {

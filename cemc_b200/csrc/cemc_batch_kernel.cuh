@@ -195,7 +195,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   constexpr int BT = BW * M;                     // moves per batch over the whole cluster
   constexpr int NJE = kSplit ? 1 : NJ;           // changed sites one warp evaluates
   static_assert(BT <= 32, "one decision lane per move");
-  static_assert(!kWide || EV == EV_SPIN, "two columns per lane: spin evaluation only");
+  static_assert(!kWide || EV != EV_PRODUCT, "two columns per lane: spin and table evaluation");
   const int crank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int r = a.order ? a.order[blockIdx.x / C] : (int)(blockIdx.x / C);
   const int tid = threadIdx.x, nthr = (B + 1) * 32;
@@ -827,7 +827,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     for (int mi = 0; mi < M; mi++) {
       const int b = warp + mi * BW;             // warp w evaluates moves w, w + BW, ...
       if (is_obs || (b >= nb && !kAsync)) break;   // async protocol: fixed byte count per batch, evaluate anyway
-      int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check); host: NJ*KP <= 64
+      int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check): columns 0..31 (and the site itself)
+      int gsy[2] = {-1, -1};      // kWide: columns 32..K-1 and the site itself
       const uint4 rec0 = s.ring[(int)((sdone + b) & 127) * 2];
       int site0, site1 = -1, new0, new1 = 0, old0, old1 = 0, slot0 = -1, slot1 = -1;
       if (replay) {                                     // recorded sites / new species
@@ -868,19 +869,33 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
         for (int je = 0; je < NJE; je++) {
           const int j = jb + je;
-          int v = 0;
+          int v = 0, v2 = 0;
           if (lane < K) {
             const int nbs = neighbour(sites[j], lane, my_shift);
             gsx[je] = nbs;
             v = s.occ[nbs];
             if (j && nbs == site0) v = new0;      // change 1 sees change 0 applied (:845-852)
           } else if (lane == K) gsx[je] = sites[j];
+          if (kWide) {                            // 32 <= K <= 63: a second column per lane
+            if (lane + 32 < K) {
+              const int nbs = neighbour(sites[j], lane + 32, my_shift2);
+              gsy[je] = nbs;
+              v2 = s.occ[nbs];
+              if (j && nbs == site0) v2 = new0;
+            } else if (lane + 32 == K) gsy[je] = sites[j];
+          }
+          auto occ_of_col = [&](uint32_t col) -> int {
+            const int a1 = __shfl_sync(0xffffffffu, v, (int)(col & 31u));
+            if (!kWide) return a1;
+            const int a2 = __shfl_sync(0xffffffffu, v2, (int)(col & 31u));
+            return (col & 32u) ? a2 : a1;
+          };
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             if (q < t_rounds) {
-              const int va = __shfl_sync(0xffffffffu, v, (int)(tdx[q] & 0xffu));
-              const int vb = __shfl_sync(0xffffffffu, v, (int)((tdx[q] >> 8) & 0xffu));
-              const int vc = __shfl_sync(0xffffffffu, v, (int)((tdx[q] >> 16) & 0xffu));
+              const int va = occ_of_col(tdx[q] & 0xffu);
+              const int vb = occ_of_col((tdx[q] >> 8) & 0xffu);
+              const int vc = occ_of_col((tdx[q] >> 16) & 0xffu);
               const uint32_t rest = (uint32_t)va * (tdy[q] & 0xffu) + (uint32_t)vb * ((tdy[q] >> 8) & 0xffu) +
                                     (uint32_t)vc * ((tdy[q] >> 16) & 0xffu);
               const uint32_t wr = tdy[q] >> 24, nd = tdx[q] >> 24;    // nd: decorations per table row
@@ -1114,7 +1129,6 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       {
         int sk0, sk1;
         changed_sites(b, sk0, sk1);
-        const int gsy[2] = {-1, -1};
         const uint32_t m = conflict_mask(b, gsx, sk0, sk1, gsy);
         if (lane == 0) put_cm(b, m);
       }

@@ -80,11 +80,13 @@ static int batch_launch_split(const BatchLaunch &L) {
   }
 }
 
-// 32 <= K <= 63 translation columns (spin evaluation, one CTA per chain, shared-memory state)
+// 32 <= K <= 63 translation columns (spin / table evaluation, one CTA per chain, shared-memory state)
 template <int MODE, bool kTree, int B, int EV>
 static int batch_launch_wide(const BatchLaunch &L) {
-  if constexpr (EV == EV_SPIN) {
-    const size_t sm = batch_smem_layout<B, B>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, nullptr, false, L.sp.wq);
+  if constexpr (EV != EV_PRODUCT) {
+    const TabTables *tb = (EV == EV_TAB || EV == EV_TAB32) ? &L.tb : nullptr;
+    const size_t sm = batch_smem_layout<B, B>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, tb, EV == EV_TAB32,
+                                              EV == EV_SPIN ? L.sp.wq : 0);
     if (sm > (size_t)L.max_smem_optin) return -1;
     return batch_launch_kc<MODE, kTree, B, true, 1, EV, 1, false, true>(L, sm);
   } else {

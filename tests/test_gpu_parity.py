@@ -965,3 +965,28 @@ def test_lattice_arithmetic_rejects_non_lattice_tables(cuda_device):
     gpu.set_occupancy(ft.occupancy(symbols)[None]); gpu.set_cf(chain.cf[None]); gpu.set_kT([0.05]); gpu.seed(3)
     gpu.run_sgc(500); chain.run_sgc(500)
     assert_state_equal(gpu, [chain])
+
+
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+@pytest.mark.parametrize("batch", [8, 16])
+def test_table_evaluation_wide_columns(cuda_device, batch, mode):
+    """Ternary system with all six cluster families (K = 42 translation columns, 27 ECIs): the
+    table evaluation of the batch kernel takes two columns per lane (32 <= K <= 63)."""
+    case = dict(L=5, species=["Al", "Mg", "Si"], families=["nn", "2nn", "3nn", "tri", "iso", "tet"],
+                conc={"Al": 0.5, "Mg": 0.25, "Si": 0.25})
+    st, eci, symbols, ft = build(**case)
+    assert ft.K == 42 and ft.n_eci <= 32
+    syms = [syn.random_symbols(st, case["conc"], seed=90 + r) for r in range(3)]
+    gpu, chains = make_pair(ft, syms, [0.02, 0.05, 0.12], seed=77)
+    assert gpu.batch_kernel_applies() and gpu.get_batch_eval() == 2
+    gpu.set_batch(batch)
+    n = 1200
+    gpu.set_trace(n)
+    (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+    assert gpu.last_variant() == (2 if batch == 16 else 3)
+    tr = gpu.get_trace(n)
+    for r, c in enumerate(chains):
+        o = c.run_sgc(n, trace=True) if mode == "sgc" else c.run_canonical(n, trace=True)
+        assert np.array_equal(tr[3][r], o[3]) and np.array_equal(tr[4][r], o[4])
+    assert_state_equal(gpu, chains)
+    assert np.array_equal(gpu.get_accumulators(), np.stack([c.acc for c in chains]))
