@@ -647,7 +647,8 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   std::vector<int4> tb_task;
   std::vector<double> tb_tab;
   {
-    bool ok = (tb->n_symm == 1 && n_eci <= 32 && K <= 63 && S <= 9);      // K > 31: two columns per lane
+    bool ok = (tb->n_symm == 1 && n_eci <= 64 && K <= 63 && S <= 9 &&      // K > 31: two columns per lane;
+               (n_eci <= 32 || K <= 31));                                 // n_eci > 32: two ECIs per lane
     auto power = [&](int e) { int v = 1; for (int q = 0; q < e; q++) v *= S; return v; };
     std::vector<std::vector<std::vector<int>>> fam_decos(tb->n_fam);     // distinct decorations per family
     std::vector<std::pair<int, int>> task_fd;                            // task -> (family, decoration index)
@@ -1067,7 +1068,9 @@ static bool batch_applicable(const cemc_handle *h) {
   const bool spin_eval = h->spin_ok && !h->no_spin && h->t.allowed_identity && h->spin.n_rounds <= 4;
   const bool tab_eval = h->tab_ok && (h->fp32 || !h->no_tab);
   // K <= 31 translation columns (one per lane); the spin and table evaluations also take 32..63
-  return !(h->force_generic || h->t.n_eci > 32 || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
+  // up to 32 ECIs (one per lane); the table / product evaluations also take 33..64 (two per lane, K <= 31)
+  if (h->t.n_eci > 32 && (h->t.n_eci > 64 || spin_eval || h->t.KP > 32)) return false;
+  return !(h->force_generic || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
            h->t.KP > ((spin_eval || tab_eval) ? 64 : 32));
 }
 

@@ -92,7 +92,8 @@ struct BatchSmem {
 };
 
 // B = moves evaluated by this CTA, BT = moves per batch over the whole cluster
-template <int B, int BT = B>
+// E = ECIs per lane (ECI i lives in lane i % 32, slot i / 32): rows of per-ECI data are 32 E wide
+template <int B, int BT = B, int E = 1>
 __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char *base,
                                                     const DeviceTables &t, bool canonical,
                                                     bool state_in_smem = true,
@@ -121,13 +122,13 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE16(ttask, int4, tb ? t.n_tasks_total : 0);
   o = align_up(o, 16);                     // code words are read four at a time
   CEMC_TAKE(codes, uint32_t, tb ? B * nj * tb->n_sub : 0);
-  CEMC_TAKE(sq, double, 2 * BT * 2 * 32);      // double buffered: the bookkeeper reads batch k during batch k+1
-  CEMC_TAKE(pub, double, 34);
+  CEMC_TAKE(sq, double, 2 * BT * 2 * 32 * E);  // double buffered: the bookkeeper reads batch k during batch k+1
+  CEMC_TAKE(pub, double, 32 * E + 2);
   CEMC_TAKE(qtab, double, spin_wq * 64);      // spin evaluation: quotient table [new species][count][ECI lane]
   CEMC_TAKE(dEa, double, BT);
   CEMC_TAKE(dEb, double, BT);
-  CEMC_TAKE(Pm, double, BT * 33);
-  CEMC_TAKE(Ch, double, BT * 32);
+  CEMC_TAKE(Pm, double, BT * (32 * E + 1));
+  CEMC_TAKE(Ch, double, BT * 32 * E);
   CEMC_TAKE(obE, double, BT);
   CEMC_TAKE(bf, double, t.D * t.S);
   CEMC_TAKE16(items, uint4, tb ? 0 : t.n_items_total);
@@ -180,8 +181,10 @@ __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, 
 // swap then costs an evaluation warp what a one-site flip costs, instead of twice that.
 // kWide (spin evaluation only): 32 <= K <= 63 translation columns -- every lane gathers two columns
 // (lane, lane + 32), the occupation mask has 64 bits.
-template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV, int M = 1, bool kSplit = false, bool kWide = false>
-__global__ void __launch_bounds__((B + 1) * 32, (EV != EV_PRODUCT && B <= 8) ? 2 : 1)
+// E (table / product evaluation, C = 1): ECIs per lane -- up to 32 E ECIs (quaternary systems,
+// ternary systems with many families); ECI i is slot i / 32 of lane i % 32.
+template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV, int M = 1, bool kSplit = false, bool kWide = false, int E = 1>
+__global__ void __launch_bounds__((B + 1) * 32, (EV != EV_PRODUCT && B <= 8 && E == 1) ? 2 : 1)
 batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTables sp, TabTables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   namespace cg = cooperative_groups;
@@ -195,6 +198,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   constexpr int BT = BW * M;                     // moves per batch over the whole cluster
   constexpr int NJE = kSplit ? 1 : NJ;           // changed sites one warp evaluates
   static_assert(BT <= 32, "one decision lane per move");
+  static_assert(E == 1 || (C == 1 && EV != EV_SPIN && M == 1), "several ECIs per lane: one CTA per chain, table / product evaluation");
+  constexpr int LW = 32 * E;                     // width of a row of per-ECI values
   static_assert(!kWide || EV != EV_PRODUCT, "two columns per lane: spin and table evaluation");
   const int crank = C > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int r = a.order ? a.order[blockIdx.x / C] : (int)(blockIdx.x / C);
@@ -215,7 +220,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   int32_t *g_list = st.list + (size_t)r * N;
   int32_t *g_loc = st.loc + (size_t)r * N;
   BatchSmem s;
-  batch_smem_layout<B, BT>(&s, smem_raw, t, kCanon, kStateSmem, kTab ? &tb : nullptr, kTab32, kSpin ? sp.wq : 0);
+  batch_smem_layout<B, BT, E>(&s, smem_raw, t, kCanon, kStateSmem, kTab ? &tb : nullptr, kTab32, kSpin ? sp.wq : 0);
   if (!kStateSmem) { s.occ = g_occ; s.list = g_list; }
   // CTA 0's copies of the arrays the deciding warp reads (DSMEM when C > 1)
   BatchSmem s0 = s;
@@ -263,8 +268,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     r_ctl = mapa_u32(smem_u32(s.ctl), 1);
   }
   // results of one evaluated move -> CTA 0 (b = move of the batch, pp = batch parity)
-  auto put_sq = [&](int pp, int b, int half, double q) {          // per-ECI quotient, lane = ECI
-    const int idx = pp * (BT * 64) + b * 64 + half * 32 + lane;
+  auto put_sq = [&](int pp, int b, int half, double q, int e = 0) {   // per-ECI quotient, (lane, e) = ECI e * 32 + lane
+    const int idx = pp * (BT * 2 * LW) + b * 2 * LW + half * LW + e * 32 + lane;
     if (remote) st_async_f64(r_sq + (uint32_t)idx * 8u, q, rE); else s0.sq[idx] = q;
   };
   auto put_de = [&](int b, double de) {                            // lane 0
@@ -340,20 +345,27 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 
   // ---- lane i owns ECI i (every warp: per-ECI quotients; warp 0: CF vector) -------
   const double dN = (double)(unsigned)N;
-  int f_kind = 0, f_d = 0, f_t0 = 0, f_nd = 0, my_singlet = -1;
-  double f_scale = 0.0, f_den = 1.0, f_rden = 1.0, eci_reg = 0.0, cf_reg = 0.0;
+  int f_kind[E], f_d[E], f_t0[E], f_nd[E], my_singlet = -1;
+  double f_scale[E], f_den[E], f_rden[E], eci_reg[E], cf_reg[E];
   double aE0 = 0.0, aE1 = 0.0, aE2 = 0.0, aS0 = 0.0, aS1 = 0.0, aS2 = 0.0;
-  if (lane < n_eci) {
-    const int4 f = t.fin_i[lane];
-    f_kind = f.x; f_d = f.y; f_t0 = f.z; f_nd = f.w - f.z;
-    const double2 fd = t.fin_d[lane];
-    f_scale = fd.x;
-    f_den = (f_kind == 1) ? dN : fd.y;
-    f_rden = __ddiv_rn(1.0, f_den);
-    eci_reg = st.eci[(size_t)r * n_eci + lane];
-    cf_reg = st.cf[(size_t)r * n_eci + lane];
-    for (int d = 0; d < t.n_singlets; d++) if (t.singlet_idx[d] == lane) my_singlet = d;
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    f_kind[e] = 0; f_d[e] = 0; f_t0[e] = 0; f_nd[e] = 0;
+    f_scale[e] = 0.0; f_den[e] = 1.0; f_rden[e] = 1.0; eci_reg[e] = 0.0; cf_reg[e] = 0.0;
+    const int i = e * 32 + lane;
+    if (i < n_eci) {
+      const int4 f = t.fin_i[i];
+      f_kind[e] = f.x; f_d[e] = f.y; f_t0[e] = f.z; f_nd[e] = f.w - f.z;
+      const double2 fd = t.fin_d[i];
+      f_scale[e] = fd.x;
+      f_den[e] = (f_kind[e] == 1) ? dN : fd.y;
+      f_rden[e] = __ddiv_rn(1.0, f_den[e]);
+      eci_reg[e] = st.eci[(size_t)r * n_eci + i];
+      cf_reg[e] = st.cf[(size_t)r * n_eci + i];
+    }
   }
+  // singlets are the ECIs right after c0 in name order (c0 < c1_* < c2_*): slot 0 of their lanes
+  for (int d = 0; d < t.n_singlets; d++) if (t.singlet_idx[d] == lane) my_singlet = d;
   if (is_obs && crank == 0) {
     const double *ag = st.acc + (size_t)r * acc_stride;
     if (my_singlet >= 0) { aS0 = ag[3 + 3 * my_singlet]; aS1 = ag[4 + 3 * my_singlet]; aS2 = ag[5 + 3 * my_singlet]; }
@@ -395,7 +407,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // products the reference subtracts, N * sum_i |eci_i| * max|cf| * O(n_eci * eps)
   double etol;
   {
-    double sa = lane < n_eci ? fabs(eci_reg) * fmax(1.0, fabs(cf_reg)) : 0.0;
+    double sa = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; e++) sa += fabs(eci_reg[e]) * fmax(1.0, fabs(cf_reg[e]));      // 0 beyond n_eci
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
     etol = 1e-13 * dN * sa * 16.0 * a.screen_slack;
@@ -430,7 +444,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int cnt = 0; cnt < sp.wq; cnt++) {
           const int dsig = 2 * sp.b0 * (1 - 2 * nw);                 // old = 1 - new
           const int num = s_coef * dsig * (s_msub - 2 * cnt);
-          s.qtab[(nw * sp.wq + cnt) * 32 + lane] = cnt <= s_msub ? exact_div((double)num, f_den, f_rden) : 0.0;
+          s.qtab[(nw * sp.wq + cnt) * 32 + lane] = cnt <= s_msub ? exact_div((double)num, f_den[0], f_rden[0]) : 0.0;
         }
     }
   }
@@ -512,9 +526,10 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #else
 #define CEMC_OTICK(slot) do { } while (0)
 #endif
-    const double *sqp = s.sq + pp * (BT * 64);
-    double c = cf_reg;
-    {
+    const double *sqp = s.sq + pp * (BT * 2 * LW);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      double c = cf_reg[e];
       // fully unrolled over the batch: compile-time addresses and mask bits, loads of a
       // group of G moves up front; the only serial chain is the DADDs of accepted moves
       constexpr int G = (BT % 5 == 0) ? 5 : (BT % 7 == 0) ? 7 : 3;
@@ -525,22 +540,23 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           double qa[G], qb[G];
 #pragma unroll
           for (int x = 0; x < G; x++) {
-            qa[x] = sqp[(b0 + x) * 64 + lane];
-            qb[x] = kCanon ? sqp[(b0 + x) * 64 + 32 + lane] : 0.0;
+            qa[x] = sqp[(b0 + x) * 2 * LW + e * 32 + lane];
+            qb[x] = kCanon ? sqp[(b0 + x) * 2 * LW + LW + e * 32 + lane] : 0.0;
           }
 #pragma unroll
           for (int x = 0; x < G; x++) {
             if (accmask & (1u << (b0 + x))) {                  // warp-uniform
-              if (f_kind > 0) {                                // kinds 0 / -1: copied (:360,:382)
+              if (f_kind[e] > 0) {                             // kinds 0 / -1: copied (:360,:382)
                 c = __dadd_rn(c, qa[x]);                       // :404
                 if (kCanon) c = __dadd_rn(c, qb[x]);
               }
-              s.Pm[(b0 + x) * 33 + lane] = __dmul_rn(eci_reg, c);
+              s.Pm[(b0 + x) * (LW + 1) + e * 32 + lane] = __dmul_rn(eci_reg[e], c);
             }
-            s.Ch[(b0 + x) * 32 + lane] = c;                    // entries >= nd are never read
+            s.Ch[(b0 + x) * LW + e * 32 + lane] = c;           // entries >= nd are never read
           }
         }
       }
+      if (accmask) { cf_reg[e] = c; s.pub[e * 32 + lane] = c; }
     }
     __syncwarp();
     CEMC_OTICK(16);
@@ -548,7 +564,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     const bool my_acc = lane < nd && ((accmask >> lane) & 1u);
     double E_l = 0.0;
     if (my_acc) {
-      const double *pm = s.Pm + lane * 33;
+      const double *pm = s.Pm + lane * (LW + 1);
       double e = 0.0;
       // groups of four, loads up front: the entries of lanes >= n_eci are +0.0 products
       // (eci = cf = 0), and adding +0.0 leaves every partial sum bit for bit (the sum
@@ -573,9 +589,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     if (accmask) {
       const int last = 31 - __clz(accmask);
       e_cur = __shfl_sync(0xffffffffu, E_l, last);
-      cf_reg = c;
-      s.pub[lane] = c;
-      if (lane == 0) s.pub[32] = e_cur;
+      if (lane == 0) s.pub[LW] = e_cur;
     }
     if (lane < nd) s.obE[lane] = E_after;
     if (tracing && lane < nd && base + lane < a.tr_capacity) {
@@ -594,7 +608,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       bk_to_ob -= nd;
       if (bk_to_ob <= 0) {               // the batch ended on an observer boundary
         bk_to_ob += ob_iv;
-        observer_boundary(a, r, lane, n_eci, N, s.Ch + (nd - 1) * 32, e_cur, s.occ);
+        observer_boundary(a, r, lane, n_eci, N, s.Ch + (nd - 1) * LW, e_cur, s.occ);
       }
     }
     if (!observe) return;
@@ -603,7 +617,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       for (; b + 3 < nd; b += 4) {
         double Eb[4], cb[4];
 #pragma unroll
-        for (int x = 0; x < 4; x++) { Eb[x] = s.obE[b + x]; cb[x] = s.Ch[(b + x) * 32 + lane]; }
+        for (int x = 0; x < 4; x++) { Eb[x] = s.obE[b + x]; cb[x] = s.Ch[(b + x) * LW + lane]; }
 #pragma unroll
         for (int x = 0; x < 4; x++) {
           aE0 = __dadd_rn(aE0, 1.0);
@@ -615,7 +629,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         }
       }
       for (; b < nd; b++) {
-        const double Eb = s.obE[b], cb = s.Ch[b * 32 + lane];
+        const double Eb = s.obE[b], cb = s.Ch[b * LW + lane];
         aE0 = __dadd_rn(aE0, 1.0);
         aE1 = __dadd_rn(aE1, Eb);
         aE2 = __dadd_rn(aE2, __dmul_rn(Eb, Eb));
@@ -625,7 +639,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       }
     } else {
       for (int b = 0; b < nd; b++) {
-        const double Eb = s.obE[b], cb = s.Ch[b * 32 + lane];
+        const double Eb = s.obE[b], cb = s.Ch[b * LW + lane];
         const double e2 = __dmul_rn(Eb, Eb);
         aE0 = __dadd_rn(aE0, 1.0);
         aE1 = __dadd_rn(aE1, exact_div(Eb, ref, rref));
@@ -640,7 +654,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 
   long long fill_end = 0;              // records of steps [sdone, fill_end) are in the ring
   if (is_obs) { produce32(0); produce32(32); produce32(64); }
-  if (is_obs && crank == 0) { s.pub[lane] = cf_reg; if (lane == 0) s.pub[32] = e_cur; }
+  if (is_obs && crank == 0) {
+#pragma unroll
+    for (int e = 0; e < E; e++) s.pub[e * 32 + lane] = cf_reg[e];
+    if (lane == 0) s.pub[LW] = e_cur;
+  }
   fill_end = 96;
   csync();
 
@@ -803,7 +821,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         }
         double de[M];
 #pragma unroll
-        for (int mi = 0; mi < M; mi++) de[mi] = f_kind > 0 ? eci_reg * (qv[mi][0] + qv[mi][1]) : 0.0;   // screen only
+        for (int mi = 0; mi < M; mi++) de[mi] = f_kind[0] > 0 ? eci_reg[0] * (qv[mi][0] + qv[mi][1]) : 0.0;   // screen only
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -966,30 +984,34 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         CEMC_TICK(7);
         // per-ECI quotients (:393-402): lane i = ECI i, this warp's changed site(s)
         {
-          double num[NJE];
+          double de = 0.0;                                    // screen only
 #pragma unroll
-          for (int je = 0; je < NJE; je++) num[je] = 0.0;
-          if (f_kind == 1) {                                  // :366-371
+          for (int e = 0; e < E; e++) {
+            double num[NJE];
 #pragma unroll
-            for (int je = 0; je < NJE; je++)
-              num[je] = __dsub_rn(s.bf[f_d * S + news[jb + je]], s.bf[f_d * S + olds[jb + je]]);
-          } else if (f_kind == 2) {
-            for (int q = 0; q < f_nd; q++) {                  // :397
+            for (int je = 0; je < NJE; je++) num[je] = 0.0;
+            if (f_kind[e] == 1) {                             // :366-371
 #pragma unroll
-              for (int je = 0; je < NJE; je++) num[je] = __dadd_rn(num[je], db[je * max_tasks + f_t0 + q]);
+              for (int je = 0; je < NJE; je++)
+                num[je] = __dsub_rn(s.bf[f_d[e] * S + news[jb + je]], s.bf[f_d[e] * S + olds[jb + je]]);
+            } else if (f_kind[e] == 2) {
+              for (int q = 0; q < f_nd[e]; q++) {             // :397
+#pragma unroll
+                for (int je = 0; je < NJE; je++) num[je] = __dadd_rn(num[je], db[je * max_tasks + f_t0[e] + q]);
+              }
+#pragma unroll
+              for (int je = 0; je < NJE; je++) num[je] = __dmul_rn(num[je], f_scale[e]);   // :400
             }
+            double qsum = 0.0;
 #pragma unroll
-            for (int je = 0; je < NJE; je++) num[je] = __dmul_rn(num[je], f_scale);      // :400
+            for (int je = 0; je < NJE; je++) {
+              const double qj = exact_div(num[je], f_den[e], f_rden[e]);         // :402
+              put_sq(par, b, jb + je, qj, e);
+              qsum += qj;
+            }
+            if (!kCanon) put_sq(par, b, 1, 0.0, e);
+            if (f_kind[e] > 0) de += eci_reg[e] * qsum;
           }
-          double qsum = 0.0;
-#pragma unroll
-          for (int je = 0; je < NJE; je++) {
-            const double qj = exact_div(num[je], f_den, f_rden);                 // :402
-            put_sq(par, b, jb + je, qj);
-            qsum += qj;
-          }
-          if (!kCanon) put_sq(par, b, 1, 0.0);
-          double de = f_kind > 0 ? eci_reg * qsum : 0.0;      // screen only
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
           if (lane == 0) put_de(b, de * dN);
@@ -1101,25 +1123,29 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       __syncwarp();
       // P2c: per-ECI quotients (:393-402): lane i = ECI i, both changed sites
       {
-        double num0 = 0.0, num1 = 0.0;
-        if (f_kind == 1) {                                  // :366-371
-          num0 = __dsub_rn(Vb[RB + D + f_d], Vb[RB + f_d]);
-          if (kCanon) num1 = __dsub_rn(Vb[VS + RB + D + f_d], Vb[VS + RB + f_d]);
-        } else if (f_kind == 2) {
-          for (int q = 0; q < f_nd; q++) {                  // :397
-            num0 = __dadd_rn(num0, db[f_t0 + q]);
-            if (kCanon) num1 = __dadd_rn(num1, db[max_tasks + f_t0 + q]);
-          }
-          num0 = __dmul_rn(num0, f_scale);                  // :400
-          num1 = __dmul_rn(num1, f_scale);
-        }
-        const double qa = exact_div(num0, f_den, f_rden);                     // :402
-        const double qb = kCanon ? exact_div(num1, f_den, f_rden) : 0.0;
-        put_sq(par, b, 0, qa);
-        put_sq(par, b, 1, qb);
         // state-independent energy change of this move, N * sum_i eci_i (q0_i + q1_i):
         // only used to SCREEN the Metropolis test (any summation order will do)
-        double de = f_kind > 0 ? eci_reg * (qa + qb) : 0.0;
+        double de = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          double num0 = 0.0, num1 = 0.0;
+          if (f_kind[e] == 1) {                               // :366-371
+            num0 = __dsub_rn(Vb[RB + D + f_d[e]], Vb[RB + f_d[e]]);
+            if (kCanon) num1 = __dsub_rn(Vb[VS + RB + D + f_d[e]], Vb[VS + RB + f_d[e]]);
+          } else if (f_kind[e] == 2) {
+            for (int q = 0; q < f_nd[e]; q++) {               // :397
+              num0 = __dadd_rn(num0, db[f_t0[e] + q]);
+              if (kCanon) num1 = __dadd_rn(num1, db[max_tasks + f_t0[e] + q]);
+            }
+            num0 = __dmul_rn(num0, f_scale[e]);               // :400
+            num1 = __dmul_rn(num1, f_scale[e]);
+          }
+          const double qa = exact_div(num0, f_den[e], f_rden[e]);               // :402
+          const double qb = kCanon ? exact_div(num1, f_den[e], f_rden[e]) : 0.0;
+          put_sq(par, b, 0, qa, e);
+          put_sq(par, b, 1, qb, e);
+          if (f_kind[e] > 0) de += eci_reg[e] * (qa + qb);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
         if (lane == 0) put_de(b, de * dN);
@@ -1177,15 +1203,21 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         // move 0 is inconclusive: exact path (rare) -- ordered dot (named_array.cpp:27-31)
         // and the reference expression (montecarlo.py:951-956) on the current state, which
         // the bookkeeper published after the previous batch
-        double cn = s.pub[lane];
-        const double e_old = s.pub[32];
-        if (f_kind > 0) {
-          cn = __dadd_rn(cn, s.sq[par * (BT * 64) + lane]);
-          if (kCanon) cn = __dadd_rn(cn, s.sq[par * (BT * 64) + 32 + lane]);
+        const double e_old = s.pub[LW];
+        double p[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          double cn = s.pub[e * 32 + lane];
+          if (f_kind[e] > 0) {
+            cn = __dadd_rn(cn, s.sq[par * (BT * 2 * LW) + e * 32 + lane]);
+            if (kCanon) cn = __dadd_rn(cn, s.sq[par * (BT * 2 * LW) + LW + e * 32 + lane]);
+          }
+          p[e] = __dmul_rn(eci_reg[e], cn);
         }
-        const double p = __dmul_rn(eci_reg, cn);
         double e_new = 0.0;
-        for (int i = 0; i < n_eci4; i++) e_new = __dadd_rn(e_new, __shfl_sync(0xffffffffu, p, i));
+#pragma unroll
+        for (int e = 0; e < E; e++)          // ECI order: slot 0 of lanes 0..31, then slot 1, ...
+          for (int i = 0; i < 32 && e * 32 + i < n_eci4; i++) e_new = __dadd_rn(e_new, __shfl_sync(0xffffffffu, p[e], i));
         e_new = __dmul_rn(e_new, dN);
         const double ub = __shfl_sync(0xffffffffu, u_l, 0);
         if (metropolis(e_new, e_old, ub, kT, rkT)) tm |= 1u; else tm &= ~1u;
@@ -1302,7 +1334,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     double *aw = st.acc + (size_t)r * acc_stride;
     if (lane == 0) { aw[0] = aE0; aw[1] = aE1; aw[2] = aE2; }
     if (my_singlet >= 0) { aw[3 + 3 * my_singlet] = aS0; aw[4 + 3 * my_singlet] = aS1; aw[5 + 3 * my_singlet] = aS2; }
-    if (lane < n_eci) st.cf[(size_t)r * n_eci + lane] = cf_reg;
+#pragma unroll
+    for (int e = 0; e < E; e++) if (e * 32 + lane < n_eci) st.cf[(size_t)r * n_eci + e * 32 + lane] = cf_reg[e];
     if (lane == 0) st.e_cur[r] = e_cur;
   }
   if (is_decider) {

@@ -30,9 +30,9 @@ int batch_launch_spin(const BatchLaunch &L);
 int batch_launch_tab(const BatchLaunch &L);
 int batch_launch_tab32(const BatchLaunch &L);
 
-template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M, bool kSplit = false, bool kWide = false>
+template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M, bool kSplit = false, bool kWide = false, int E = 1>
 static int batch_launch_kc(const BatchLaunch &L, size_t sm) {
-  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV, M, kSplit, kWide>;
+  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV, M, kSplit, kWide, E>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return 1000 + (int)e;
   cudaLaunchConfig_t cfg{};
@@ -94,8 +94,28 @@ static int batch_launch_wide(const BatchLaunch &L) {
   }
 }
 
+// 33..64 ECIs: two per lane (table / product evaluation, one CTA per chain, shared-memory state)
+template <int MODE, bool kTree, int B, int EV>
+static int batch_launch_e2(const BatchLaunch &L) {
+  if constexpr (EV != EV_SPIN) {
+    const TabTables *tb = (EV == EV_TAB || EV == EV_TAB32) ? &L.tb : nullptr;
+    const size_t sm = batch_smem_layout<B, B, 2>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, true, tb, EV == EV_TAB32, 0);
+    if (sm > (size_t)L.max_smem_optin) return -1;
+    return batch_launch_kc<MODE, kTree, B, true, 1, EV, 1, false, false, 2>(L, sm);
+  } else {
+    return -1;
+  }
+}
+
 template <int MODE, bool kTree, int EV>
 static int batch_launch_bc(const BatchLaunch &L) {
+  if (L.t.n_eci > 32) {
+    if (L.t.n_eci > 64 || L.split || L.M != 1 || L.C != 1 || L.t.K > 31) return -1;
+    if (L.B == 16) return batch_launch_e2<MODE, kTree, 15, EV>(L);
+    if (L.B == 8) return batch_launch_e2<MODE, kTree, 7, EV>(L);
+    if (L.B == 4) return batch_launch_e2<MODE, kTree, 3, EV>(L);      // large product programs: scratch of 3 moves fits
+    return -1;
+  }
   if (L.t.K > 31) {
     if (L.split || L.M != 1 || L.C != 1) return -1;
     if (L.B == 16) return batch_launch_wide<MODE, kTree, 15, EV>(L);

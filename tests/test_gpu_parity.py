@@ -990,3 +990,45 @@ def test_table_evaluation_wide_columns(cuda_device, batch, mode):
         assert np.array_equal(tr[3][r], o[3]) and np.array_equal(tr[4][r], o[4])
     assert_state_equal(gpu, chains)
     assert np.array_equal(gpu.get_accumulators(), np.stack([c.acc for c in chains]))
+
+
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+@pytest.mark.parametrize("system,batch", [("quaternary_products", 4), ("quinary_tables", 8), ("quinary_tables", 16)])
+def test_two_ecis_per_lane(cuda_device, system, batch, mode):
+    """33..64 ECIs: the batch kernel keeps two ECIs per lane (CF vector, quotients, ordered
+    energy dot over both slots).  Quaternary standard families = 41 ECIs (fp64 product
+    evaluation: the quadruplet tables do not fit), quinary pairs + triplets = 45 ECIs (product
+    tables).  Trajectory, trace, CFs, energies and observer sums equal the oracle's."""
+    if system == "quaternary_products":
+        species, fams, ev = ["Al", "Cu", "Mg", "Si"], ["nn", "2nn", "tri", "tet"], 0
+    else:
+        species, fams, ev = ["Al", "Cu", "Mg", "Si", "Zn"], ["nn", "2nn", "tri"], 2
+    conc = {s: 1.0 / len(species) for s in species}
+    st, eci, symbols, ft = build(4, species, fams, conc)
+    assert 32 < ft.n_eci <= 64
+    syms = [syn.random_symbols(st, conc, seed=40 + r) for r in range(3)]
+    gpu, chains = make_pair(ft, syms, [0.03, 0.06, 0.15], seed=55)
+    assert gpu.batch_kernel_applies() and gpu.get_batch_eval() == ev
+    gpu.set_batch(batch)
+    n = 1000
+    gpu.set_trace(n)
+    gpu.reset_accumulators()
+    (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+    if system == "quaternary_products" and mode == "canonical":
+        assert gpu.last_variant() == 5       # the product scratch of two changed sites does not fit: generic kernel
+    else:
+        assert gpu.last_variant() == {16: 2, 8: 3, 4: 4}[batch]
+    tr = gpu.get_trace(n)
+    for r, c in enumerate(chains):
+        o = c.run_sgc(n, trace=True) if mode == "sgc" else c.run_canonical(n, trace=True)
+        assert np.array_equal(tr[3][r], o[3]) and np.array_equal(tr[4][r], o[4])
+    assert_state_equal(gpu, chains)
+    assert np.array_equal(gpu.get_accumulators(), np.stack([c.acc for c in chains]))
+    # forced exact decisions (the screen always defers): the ordered dot over both ECI slots
+    gpu2, chains2 = make_pair(ft, syms, [0.03, 0.06, 0.15], seed=56)
+    gpu2.set_batch(batch)
+    gpu2.set_screen_slack(1e30)
+    (gpu2.run_sgc if mode == "sgc" else gpu2.run_canonical)(300)
+    for c in chains2:
+        (c.run_sgc if mode == "sgc" else c.run_canonical)(300)
+    assert_state_equal(gpu2, chains2)
