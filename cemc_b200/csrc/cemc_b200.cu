@@ -91,13 +91,18 @@ struct cemc_handle {
   // device-side state observers (cemc_set_device_observers)
   long long obs_interval = 0, obs_step = 0, obs_capacity = 0;
   int obs_flags = 0;
-  unsigned long long *ob_n = nullptr;
+  int obs_ring = 0;                   // snapshots per replica between two folds
+  unsigned long long *ob_n = nullptr, *ob_folded = nullptr;
+  double *ob_snap_cf = nullptr, *ob_snap_e = nullptr;
+  int8_t *ob_snap_occ = nullptr;
   double *ob_cf_sum = nullptr, *ob_cf_sq = nullptr, *ob_best = nullptr, *ob_e = nullptr, *ob_order = nullptr;
   int8_t *ob_best_occ = nullptr, *ob_occ_ref = nullptr;
   bool lat_verified = false;          // `trans` is a periodic shift table: index arithmetic usable
   bool observe = true;                // accumulate the Averager / SGCObserver sums during run_*
   int last_variant = -1;              // variant of the most recent Metropolis launch (cemc_last_variant)
   // tuning across short launches: next variant to time, ms per move of the timed ones
+  int lt_next[2] = {0, 0}, lt_best[2] = {-1, -1};     // tuning on long launches, resumable across calls
+  float lt_best_ms[2] = {1e30f, 1e30f};
   int xt_next[2] = {0, 0};
   float xt_ms[2][16];
   int cluster = 0;                    // CTAs per chain in the batch kernel (0 = auto, 1, 2)
@@ -134,6 +139,7 @@ static int h2d_staged(cemc_handle *h, cemc_handle::Staging &st, void *dst, const
 static void reset_tuning(cemc_handle *h) {
   h->tuned_sgc = h->tuned_can = -1;
   h->xt_next[0] = h->xt_next[1] = 0;
+  h->lt_next[0] = h->lt_next[1] = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -643,38 +649,48 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   // occupations, multiplied in the reference's order (plain IEEE double products: the
   // bits the reference computes).  Decorations are the fastest index, so the lanes of
   // one family (one lane per decoration) read one contiguous row.
+  // Several translational symmetry groups (crystals with a basis): one descriptor block and one
+  // task list per group -- the evaluation picks them by the changed site's group
+  // (ce_updater.cpp:379-384); family ids are already unique per (group, prefix).
   std::vector<uint2> tb_desc;
   std::vector<int4> tb_task;
   std::vector<double> tb_tab;
   {
-    bool ok = (tb->n_symm == 1 && n_eci <= 64 && K <= 63 && S <= 9 &&      // K > 31: two columns per lane;
+    bool ok = (n_eci <= 64 && K <= 63 && S <= 9 &&                        // K > 31: two columns per lane;
                (n_eci <= 32 || K <= 31));                                 // n_eci > 32: two ECIs per lane
     auto power = [&](int e) { int v = 1; for (int q = 0; q < e; q++) v *= S; return v; };
     std::vector<std::vector<std::vector<int>>> fam_decos(tb->n_fam);     // distinct decorations per family
-    std::vector<std::pair<int, int>> task_fd;                            // task -> (family, decoration index)
-    for (int i = 0; i < n_eci && ok; i++) {
-      if (tb->eci_kind[i] != CEMC_ECI_CLUSTER) continue;
-      const int fam = tb->term_fam[i];
-      if (fam < 0) continue;
-      const int n = tb->fam_size[fam];
-      for (int e = tb->term_deco_off[i]; e < tb->term_deco_off[i + 1]; e++) {
-        std::vector<int> key;
-        for (int k = 0; k < n; k++) key.push_back(tb->deco[4 * e + k]);
-        auto &fd = fam_decos[fam];
-        int idx = (int)(std::find(fd.begin(), fd.end(), key) - fd.begin());
-        if (idx == (int)fd.size()) fd.push_back(key);
-        task_fd.push_back(std::make_pair(fam, idx));
+    std::vector<int> fam_group(tb->n_fam, -1);
+    std::vector<std::pair<int, int>> task_fd;                            // task -> (family, decoration index), task order of fin_i
+    for (int g = 0; g < tb->n_symm && ok; g++)
+      for (int i = 0; i < n_eci && ok; i++) {
+        if (tb->eci_kind[i] != CEMC_ECI_CLUSTER) continue;
+        const int term = g * n_eci + i;
+        const int fam = tb->term_fam[term];
+        if (fam < 0) continue;
+        if (fam_group[fam] >= 0 && fam_group[fam] != g) { ok = false; break; }     // one table per (group, family)
+        fam_group[fam] = g;
+        const int n = tb->fam_size[fam];
+        for (int e = tb->term_deco_off[term]; e < tb->term_deco_off[term + 1]; e++) {
+          std::vector<int> key;
+          for (int k = 0; k < n; k++) key.push_back(tb->deco[4 * e + k]);
+          auto &fd = fam_decos[fam];
+          int idx = (int)(std::find(fd.begin(), fd.end(), key) - fd.begin());
+          if (idx == (int)fd.size()) fd.push_back(key);
+          task_fd.push_back(std::make_pair(fam, idx));
+        }
       }
-    }
     std::vector<int> sub_base(tb->n_fam, 0), tab_base(tb->n_fam, 0);
+    std::vector<std::vector<uint2>> desc_g(tb->n_symm);
     for (int fam = 0; fam < tb->n_fam && ok; fam++) {
       const int nd = (int)fam_decos[fam].size();
       if (!nd) continue;
+      std::vector<uint2> &dg = desc_g[fam_group[fam]];
       const int n = tb->fam_size[fam], M = tb->fam_nsub[fam];
       const int32_t *pos = tb->fam_pos + tb->fam_pos_off[fam];
       const int n_codes = power(n);
       if (nd > 255 || (n_codes + 1) * nd * 8 > 65536) { ok = false; break; }
-      sub_base[fam] = (int)tb_desc.size();
+      sub_base[fam] = (int)dg.size();
       for (int m = 0; m < M; m++) {
         uint32_t cols = (uint32_t)nd << 24, wts = 0; int nn = 0;
         for (int k = 0; k < n; k++) {
@@ -682,11 +698,11 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
           if (p == CEMC_POS_REF) wts |= (uint32_t)power(k) << 24;
           else { cols |= (uint32_t)p << (8 * nn); wts |= (uint32_t)power(k) << (8 * nn); nn++; }
         }
-        tb_desc.push_back(make_uint2(cols, wts));
+        dg.push_back(make_uint2(cols, wts));
       }
       // padding to a multiple of 8 sub-clusters: weights 0 mark the entry, x = byte offset of
       // the table's all-zero row (adding +0.0 never changes a sum that started at +0.0)
-      while (tb_desc.size() % 8) tb_desc.push_back(make_uint2((uint32_t)(n_codes * nd * 8), 0u));
+      while (dg.size() % 8) dg.push_back(make_uint2((uint32_t)(n_codes * nd * 8), 0u));
       tab_base[fam] = (int)tb_tab.size();
       for (int code = 0; code < n_codes; code++)
         for (int e = 0; e < nd; e++) {
@@ -702,13 +718,17 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
     }
     for (auto &fd : task_fd)
       tb_task.push_back(make_int4((tab_base[fd.first] + fd.second) * 8, sub_base[fd.first], (tb->fam_nsub[fd.first] + 7) & ~7, 0));
-    if (tb_desc.size() > 128 || tb_tab.size() * 8 > 96 * 1024 || tb_task.empty()) ok = false;
+    size_t max_sub = 0;
+    for (auto &dg : desc_g) max_sub = std::max(max_sub, dg.size());
+    if (max_sub > 128 || tb_tab.size() * 8 > 96 * 1024 || tb_task.empty()) ok = false;
     if (ok && (int)tb_task.size() != (int)task_sum.size()) ok = false;      // same task numbering as fin_i
     h->tab_ok = ok;
-    h->tab.n_sub = (int)tb_desc.size();
-    h->tab.n_rounds = ((int)tb_desc.size() + 31) / 32;
+    h->tab.n_sub = (int)max_sub;
+    h->tab.n_rounds = ((int)max_sub + 31) / 32;
     h->tab.n_tab = (int)tb_tab.size();
-    tb_desc.resize((size_t)std::max(1, h->tab.n_rounds) * 32, make_uint2(0u, 0u));   // never read by a task
+    const size_t stride = (size_t)std::max(1, h->tab.n_rounds) * 32;          // descriptors of group g at g * stride
+    tb_desc.assign(stride * tb->n_symm, make_uint2(0u, 0u));                  // (entries past a group's count: never read by a task)
+    for (int g = 0; g < tb->n_symm; g++) std::copy(desc_g[g].begin(), desc_g[g].end(), tb_desc.begin() + g * stride);
   }
 
   std::vector<int32_t> trans(tb->trans, tb->trans + (size_t)N * K);
@@ -756,7 +776,7 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   t.uniform_group = (tb->n_symm == 1 && t.n_active == N) ? 1 : 0;
   // ---- translation-invariant lattice?  (hint from the host, verified entry by entry) ----
   t.lat_ok = 0;
-  if (tb->lattice_dims && t.uniform_group) {
+  if (tb->lattice_dims && t.n_active == N) {
     const long long L1 = tb->lattice_dims[0], L2 = tb->lattice_dims[1], L3 = tb->lattice_dims[2];
     bool ok = L1 >= 1 && L2 >= 1 && L3 >= 1 && L1 < 1024 && L2 < 1024 && L3 < 1024 && L1 * L2 * L3 == N;
     std::vector<uint32_t> shift(K, 0u);
@@ -780,9 +800,10 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
       if (L3 == 1) ok = false;
       if (ok) {
         h->lat_verified = true;
-        // default: on when the table does not stay in L1 anyway (measured on B200: fcc 20^3 / 64^3
-        // gain 1-5 %, tables <= 128 KB -- fcc 10^3, 12^3 -- are L1 hits and lose ~1 %)
-        t.lat_ok = ((size_t)N * K * sizeof(int32_t) > 128 * 1024) ? 1 : 0; t.L1 = (uint32_t)L1; t.L2 = (uint32_t)L2; t.L3 = (uint32_t)L3; t.L23 = L23;
+        // default: on for tables of several MB (measured on B200: fcc 64^3, 19 MB, gains 5 %; fcc 20^3,
+        // 576 KB, gains 1 % -- less than the ~5 % the kernels with the optional code paths compiled in
+        // (kX) lose; tables <= 128 KB -- fcc 10^3, 12^3 -- are L1 hits and lose ~1 %)
+        t.lat_ok = ((size_t)N * K * sizeof(int32_t) > ((size_t)4 << 20)) ? 1 : 0; t.L1 = (uint32_t)L1; t.L2 = (uint32_t)L2; t.L3 = (uint32_t)L3; t.L23 = L23;
         t.lat_m23 = m23; t.lat_m3 = m3;
         if ((rc = dupload(h, &t.col_shift, shift))) return rc;
       }
@@ -834,7 +855,8 @@ int cemc_destroy(cemc_handle *h) {
   cudaStreamSynchronize(h->stream);
   for (void *p : h->owned) cudaFree(p);
   void *extra[] = {h->d_sites, h->d_news, h->d_u, h->d_acc, h->d_e, h->tr_sites, h->tr_news,
-                   h->tr_u, h->tr_acc, h->tr_e, h->pt_scratch, h->ob_n, h->ob_cf_sum, h->ob_cf_sq,
+                   h->tr_u, h->tr_acc, h->tr_e, h->pt_scratch, h->ob_n, h->ob_folded, h->ob_snap_cf,
+                   h->ob_snap_e, h->ob_snap_occ, h->ob_cf_sum, h->ob_cf_sq,
                    h->ob_best, h->ob_e, h->ob_order, h->ob_best_occ, h->ob_occ_ref};
   for (void *p : extra) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1070,7 +1092,9 @@ static bool batch_applicable(const cemc_handle *h) {
   // K <= 31 translation columns (one per lane); the spin and table evaluations also take 32..63
   // up to 32 ECIs (one per lane); the table / product evaluations also take 33..64 (two per lane, K <= 31)
   if (h->t.n_eci > 32 && (h->t.n_eci > 64 || spin_eval || h->t.KP > 32)) return false;
-  return !(h->force_generic || !h->t.uniform_group || h->t.S > 8 || h->batch < 0 ||
+  // several translational symmetry groups: table evaluation only; background sites: generic kernel
+  if (h->t.n_active != h->t.N || (h->t.n_symm > 1 && !tab_eval)) return false;
+  return !(h->force_generic || h->t.S > 8 || h->batch < 0 ||
            h->t.KP > ((spin_eval || tab_eval) ? 64 : 32));
 }
 
@@ -1332,9 +1356,8 @@ static RunArgs run_args(cemc_handle *h, long long n_steps) {
   a.order = h->d_order;
   if (h->obs_interval > 0) {
     a.obs_interval = h->obs_interval; a.obs_origin = h->obs_step; a.obs_flags = h->obs_flags;
-    a.obs_capacity = h->obs_capacity; a.ob_n = h->ob_n; a.ob_cf_sum = h->ob_cf_sum; a.ob_cf_sq = h->ob_cf_sq;
-    a.ob_best = h->ob_best; a.ob_best_occ = h->ob_best_occ; a.ob_e = h->ob_e; a.ob_order = h->ob_order;
-    a.ob_occ_ref = h->ob_occ_ref;
+    a.obs_ring = h->obs_ring; a.ob_n = h->ob_n; a.ob_snap_cf = h->ob_snap_cf; a.ob_snap_e = h->ob_snap_e;
+    a.ob_snap_occ = h->ob_snap_occ;
   }
   if (h->trace_capacity > 0) {
     a.tr_sites = h->tr_sites; a.tr_news = h->tr_news; a.tr_u = h->tr_u; a.tr_acc = h->tr_acc;
@@ -1350,6 +1373,7 @@ static int launch_batch(cemc_handle *h, const RunArgs &a, int B, int C, int M = 
   if (!batch_applicable(h)) return -1;
   BatchLaunch L{};
   L.mode = MODE; L.B = B; L.C = C; L.M = M; L.split = split; L.R = h->R; L.max_smem_optin = h->max_smem_optin;
+  L.extras = (a.rp_sites != nullptr || h->t.lat_ok || a.obs_interval > 0) ? 1 : 0;
   L.tree = ((h->order_mode == CEMC_ORDER_TREE) || h->integer_bf) ? 1 : 0;
   L.stream = h->stream; L.t = h->t; L.st = h->st; L.a = a; L.acc_stride = h->acc_stride;
   L.sp = h->spin; L.tb = h->tab;
@@ -1388,12 +1412,31 @@ static int launch_variant_raw(cemc_handle *h, const RunArgs &a, int v);
 
 template <int MODE>
 static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
-  const int rc = launch_variant_raw<MODE>(h, a, v);
-  if (rc == 0) {
-    h->last_variant = v;
-    if (a.obs_interval > 0) h->obs_step += a.n_steps;       // observer step counter (boundaries span launches)
+  if (a.obs_interval <= 0) {
+    const int rc = launch_variant_raw<MODE>(h, a, v);
+    if (rc == 0) h->last_variant = v;
+    return rc;
   }
-  return rc;
+  // device observers: a launch must not cross more boundaries than the snapshot ring holds; after
+  // every launch the (tiny) fold kernel turns the snapshots into the observers' sums, in order
+  const long long cap = (long long)h->obs_ring * a.obs_interval;
+  long long done = 0;
+  while (done < a.n_steps) {
+    RunArgs part = a;
+    part.n_steps = std::min<long long>(a.n_steps - done, cap);
+    part.obs_origin = h->obs_step;
+    const int rc = launch_variant_raw<MODE>(h, part, v);
+    if (rc) return rc;
+    h->last_variant = v;
+    h->obs_step += part.n_steps;                           // observer step counter (boundaries span launches)
+    done += part.n_steps;
+    ObserverSums o{h->ob_folded, h->ob_cf_sum, h->ob_cf_sq, h->ob_best, h->ob_best_occ, h->ob_e,
+                   h->obs_capacity, h->ob_order, h->ob_occ_ref};
+    observer_fold_kernel<<<h->R, 32, 0, h->stream>>>(part, o, h->t.n_eci, h->t.N);
+    h->launches++;
+    CU(cudaGetLastError());
+  }
+  return 0;
 }
 
 template <int MODE>
@@ -1433,31 +1476,46 @@ static bool variant_allowed(const cemc_handle *h, int v) {
 template <int MODE>
 static int run_tuned(cemc_handle *h, long long n_steps) {
   int &best = (MODE == MODE_SGC) ? h->tuned_sgc : h->tuned_can;
-  const long long seg = 2048;
+  const int md = (MODE == MODE_SGC) ? 0 : 1;
+  const long long seg = 2048, warm = seg / 4;
   long long done = 0;
-  if (best < 0 && h->autotune && h->trace_capacity == 0 && n_steps >= 8 * seg) {
-    float best_ms = 1e30f;
-    for (int v = 0; v < kNumVariants; v++) {
+  int provisional = -1;
+  // Long launches: every applicable variant gets an untimed warm-up launch (first-use costs) and
+  // two timed segments of which the faster one counts (one sample alone is at the mercy of a
+  // noisy neighbour).  The tuning moves are part of the run -- never more than n_steps: what
+  // does not fit this call continues in the next one (lt_next), the rest of this call runs on
+  // the fastest variant so far.
+  if (best < 0 && h->autotune && h->trace_capacity == 0 && n_steps >= warm + seg) {
+    int &next = h->lt_next[md];
+    if (next == 0) { h->lt_best_ms[md] = 1e30f; h->lt_best[md] = -1; }
+    while (next < kNumVariants && n_steps - done >= warm + seg) {
+      const int v = next++;
       if (!variant_allowed(h, v)) continue;
-      // untimed warm-up launch (first-use costs of the variant), then the timed segment
-      int rc = launch_variant<MODE>(h, run_args(h, seg / 4), v);
+      int rc = launch_variant<MODE>(h, run_args(h, warm), v);
       if (rc == -1) continue;
       if (rc) return rc;
-      CU(cudaEventRecord(h->tv0, h->stream));
-      rc = launch_variant<MODE>(h, run_args(h, seg), v);
-      if (rc) return rc;
-      CU(cudaEventRecord(h->tv1, h->stream));
-      CU(cudaEventSynchronize(h->tv1));
-      float ms = 0.f;
-      CU(cudaEventElapsedTime(&ms, h->tv0, h->tv1));
-      done += seg + seg / 4;
-      if (ms < best_ms) { best_ms = ms; best = v; }
+      done += warm;
+      float ms = 1e30f;
+      for (int rep_ = 0; rep_ < 2 && n_steps - done >= seg; rep_++) {
+        CU(cudaEventRecord(h->tv0, h->stream));
+        rc = launch_variant<MODE>(h, run_args(h, seg), v);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->tv1, h->stream));
+        CU(cudaEventSynchronize(h->tv1));
+        float m1 = 0.f;
+        CU(cudaEventElapsedTime(&m1, h->tv0, h->tv1));
+        ms = std::min(ms, m1);
+        done += seg;
+      }
+      if (ms < h->lt_best_ms[md]) { h->lt_best_ms[md] = ms; h->lt_best[md] = v; }
     }
+    if (next >= kNumVariants) best = h->lt_best[md];
+    else provisional = h->lt_best[md];
   }
   // short launches (e.g. the 1728-move legs between parallel-tempering exchanges): tune
   // across calls -- every call runs one untested variant (a quarter of the moves untimed
   // as warm-up, the rest timed); when all are timed the fastest is kept
-  if (best < 0 && done == 0 && h->autotune && h->trace_capacity == 0 && n_steps >= 256 && n_steps < 8 * seg) {
+  if (best < 0 && done == 0 && h->autotune && h->trace_capacity == 0 && n_steps >= 256 && n_steps < warm + seg) {
     int &next = h->xt_next[MODE == MODE_SGC ? 0 : 1];
     float *xms = h->xt_ms[MODE == MODE_SGC ? 0 : 1];
     while (next < kNumVariants) {
@@ -1486,6 +1544,10 @@ static int run_tuned(cemc_handle *h, long long n_steps) {
   }
   if (done >= n_steps) return 0;
   RunArgs a = run_args(h, n_steps - done);
+  if (best < 0 && provisional >= 0) {                // tuning continues in the next call
+    const int rc = launch_variant<MODE>(h, a, provisional);
+    if (rc != -1) return rc;
+  }
   if (best >= 0 && variant_allowed(h, best)) {       // (a tuned / pinned variant can become inapplicable:
     const int rc = launch_variant<MODE>(h, a, best);  //  e.g. the spin kernel once device observers are on)
     if (rc != -1) return rc;
@@ -1550,7 +1612,7 @@ int cemc_replay(cemc_handle *h, int n_steps, const int32_t *sites, const int8_t 
     else all2 = false;
   }
   int launched = -1;
-  if (valid && (all1 || all2) && h->t.uniform_group) {
+  if (valid && (all1 || all2) && h->t.n_active == h->t.N) {
     if (all2) { if ((rc = ensure_tracker(h))) return rc; }      // offsets read at kernel start
     const int pinned = all1 ? h->tuned_sgc : h->tuned_can;
     for (int k = -1; k < kNumVariants && launched < 0; k++) {
@@ -1813,10 +1875,11 @@ int cemc_get_accumulators(cemc_handle *h, double *acc) {
 
 // ---- device-side state observers ---------------------------------------------------
 static void free_device_observers(cemc_handle *h) {
-  void **ps[] = {(void **)&h->ob_n, (void **)&h->ob_cf_sum, (void **)&h->ob_cf_sq, (void **)&h->ob_best,
+  void **ps[] = {(void **)&h->ob_n, (void **)&h->ob_folded, (void **)&h->ob_snap_cf, (void **)&h->ob_snap_e,
+                 (void **)&h->ob_snap_occ, (void **)&h->ob_cf_sum, (void **)&h->ob_cf_sq, (void **)&h->ob_best,
                  (void **)&h->ob_e, (void **)&h->ob_order, (void **)&h->ob_best_occ, (void **)&h->ob_occ_ref};
   for (void **p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
-  h->obs_interval = 0; h->obs_flags = 0; h->obs_capacity = 0; h->obs_step = 0;
+  h->obs_interval = 0; h->obs_flags = 0; h->obs_capacity = 0; h->obs_step = 0; h->obs_ring = 0;
 }
 
 int cemc_reset_device_observers(cemc_handle *h, const int8_t *occ_ref) {
@@ -1825,6 +1888,7 @@ int cemc_reset_device_observers(cemc_handle *h, const int8_t *occ_ref) {
   CU(cudaSetDevice(h->device));
   const size_t R = (size_t)h->R, n = (size_t)h->t.n_eci, N = (size_t)h->t.N;
   CU(cudaMemsetAsync(h->ob_n, 0, sizeof(unsigned long long) * R, h->stream));
+  CU(cudaMemsetAsync(h->ob_folded, 0, sizeof(unsigned long long) * R, h->stream));
   CU(cudaMemsetAsync(h->ob_cf_sum, 0, sizeof(double) * R * n, h->stream));
   CU(cudaMemsetAsync(h->ob_cf_sq, 0, sizeof(double) * R * n, h->stream));
   CU(cudaMemsetAsync(h->ob_order, 0, sizeof(double) * R * 2, h->stream));
@@ -1849,7 +1913,16 @@ int cemc_set_device_observers(cemc_handle *h, int64_t interval, int flags, int64
   if (flags & ~15) return fail("unknown observer flag");
   if (capacity < 0) return fail("negative sample capacity");
   const size_t R = (size_t)h->R, n = (size_t)h->t.n_eci, N = (size_t)h->t.N;
+  // snapshot ring: 32 boundaries per launch (fewer when the occupation snapshots would get large)
+  const bool need_occ = (flags & (CEMC_OBS_LOWEST | CEMC_OBS_SITE_ORDER)) != 0;
+  int ring = 32;
+  while (ring > 2 && need_occ && (size_t)ring * R * N > ((size_t)512 << 20)) ring /= 2;
+  h->obs_ring = ring;
   CU(cudaMalloc((void **)&h->ob_n, sizeof(unsigned long long) * R));
+  CU(cudaMalloc((void **)&h->ob_folded, sizeof(unsigned long long) * R));
+  CU(cudaMalloc((void **)&h->ob_snap_cf, sizeof(double) * R * ring * n));
+  CU(cudaMalloc((void **)&h->ob_snap_e, sizeof(double) * R * ring));
+  if (need_occ) CU(cudaMalloc((void **)&h->ob_snap_occ, R * ring * N));
   CU(cudaMalloc((void **)&h->ob_cf_sum, sizeof(double) * R * n));
   CU(cudaMalloc((void **)&h->ob_cf_sq, sizeof(double) * R * n));
   CU(cudaMalloc((void **)&h->ob_best, sizeof(double) * R * (1 + n)));

@@ -183,7 +183,11 @@ __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, 
 // (lane, lane + 32), the occupation mask has 64 bits.
 // E (table / product evaluation, C = 1): ECIs per lane -- up to 32 E ECIs (quaternary systems,
 // ternary systems with many families); ECI i is slot i / 32 of lane i % 32.
-template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV, int M = 1, bool kSplit = false, bool kWide = false, int E = 1>
+// kX: the rarely used sources / sinks are compiled in -- replay of recorded proposals, translation by
+// index arithmetic, observer boundaries.  Their mere presence costs the plain kernels ~10 % (code
+// size and registers: 114 -> 126 on the bench kernel, measured A/B), so the flavours the benchmarks
+// run exist in both forms and the host picks kX = true only when one of the three is in use.
+template <int MODE, bool kTree, int B, bool kStateSmem, int C, int EV, int M = 1, bool kSplit = false, bool kWide = false, int E = 1, bool kX = true>
 __global__ void __launch_bounds__((B + 1) * 32, (EV != EV_PRODUCT && B <= 8 && E == 1) ? 2 : 1)
 batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTables sp, TabTables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -337,7 +341,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       }
   }
   mbar_wait(s.mbar, 0);                        // every staged byte has landed
-  if (kCanon && n_present < 2 && a.rp_sites == nullptr) {   // TooFewElementsError, montecarlo.py:310
+  if (kCanon && n_present < 2 && (!kX || a.rp_sites == nullptr)) {   // TooFewElementsError, montecarlo.py:310
     if (tid == 0) st.status[r] = 2;
     return;
   }
@@ -364,6 +368,17 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       cf_reg[e] = st.cf[(size_t)r * n_eci + i];
     }
   }
+  // Several translational symmetry groups (table evaluation only): the per-ECI constants depend
+  // on the changed site's group and are read per evaluation; f_any = the ECI takes part in some
+  // group (a group that lacks the family contributes a quotient of +0.0)
+  const bool multi = kTab && t.n_symm > 1;
+  bool f_any[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    f_any[e] = f_kind[e] > 0;
+    if (multi && e * 32 + lane < n_eci)
+      for (int g = 1; g < t.n_symm; g++) f_any[e] = f_any[e] || (t.fin_i[g * n_eci + e * 32 + lane].x > 0);
+  }
   // singlets are the ECIs right after c0 in name order (c0 < c1_* < c2_*): slot 0 of their lanes
   for (int d = 0; d < t.n_singlets; d++) if (t.singlet_idx[d] == lane) my_singlet = d;
   if (is_obs && crank == 0) {
@@ -389,15 +404,21 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   const int n_allowed = t.n_allowed;
   // replay of recorded proposals / uniforms: the ring is filled from
   // rp_sites / rp_news / rp_u instead of the Philox stream; records hold sites, not list slots
-  const bool replay = (a.rp_sites != nullptr);
+  // (mode flags pinned in ONE register: tested in every evaluation, and a kernel parameter would
+  // be re-read from the constant bank each time -- LDCU + a dependent uniform branch)
+  const int mflags = !kX ? 0 : pin_reg((a.rp_sites != nullptr ? 1 : 0) | (t.lat_ok != 0 ? 2 : 0) |
+                                       ((a.obs_interval > 0 && a.obs_interval < (1ll << 30)) ? 4 : 0));
+  const bool replay = (mflags & 1) != 0;
   // observer boundaries (cemc_set_device_observers): batches end on them, so that the bookkeeper
   // sees the chain's state of the boundary step (the occupations only change in the D phase)
   // (32-bit countdowns: intervals >= 2^30 steps never fire inside one launch segment anyway)
-  const int ob_iv = (a.obs_interval > 0 && a.obs_interval < (1ll << 30)) ? (int)a.obs_interval : 0;
-  int to_ob = ob_iv > 0 ? ob_iv - (int)(a.obs_origin % ob_iv) : 0x7fffffff;     // moves until the next boundary
-  int bk_to_ob = to_ob;                                                         // the bookkeeper's lagging copy
+  // ONE countdown register: moves until the next boundary -- as seen by the deciding / evaluation
+  // warps (they cut the batch there), and, in the observer warp, the bookkeeper's copy that lags
+  // one batch behind (that warp never needs the batch length); the interval itself is re-read
+  // from the kernel parameters on the rare update.
+  int to_ob = (mflags & 4) ? (int)(a.obs_interval - a.obs_origin % a.obs_interval) : 0x7fffffff;
   // translation-invariant lattice: lane c derives T(site, c) from the site index (no table gather)
-  const bool lat_ok = t.lat_ok != 0;
+  const bool lat_ok = (mflags & 2) != 0;
   const uint32_t my_shift = (lat_ok && lane < K) ? t.col_shift[lane] : 0u;
   const uint32_t my_shift2 = (lat_ok && kWide && lane + 32 < K) ? t.col_shift[lane + 32] : 0u;
   auto neighbour = [&](int site, int col, uint32_t shift) -> int {
@@ -546,7 +567,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
           for (int x = 0; x < G; x++) {
             if (accmask & (1u << (b0 + x))) {                  // warp-uniform
-              if (f_kind[e] > 0) {                             // kinds 0 / -1: copied (:360,:382)
+              if (f_any[e]) {                                  // kinds 0 / -1: copied (:360,:382)
                 c = __dadd_rn(c, qa[x]);                       // :404
                 if (kCanon) c = __dadd_rn(c, qb[x]);
               }
@@ -604,11 +625,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     }
     __syncwarp();
     CEMC_OTICK(17);
-    if (ob_iv > 0) {
-      bk_to_ob -= nd;
-      if (bk_to_ob <= 0) {               // the batch ended on an observer boundary
-        bk_to_ob += ob_iv;
-        observer_boundary(a, r, lane, n_eci, N, s.Ch + (nd - 1) * LW, e_cur, s.occ);
+    if (mflags & 4) {
+      to_ob -= nd;                       // (observer warp: the lagging copy)
+      if (to_ob <= 0) {                  // the batch ended on an observer boundary
+        to_ob += (int)a.obs_interval;
+        observer_snapshot(a, r, lane, n_eci, N, s.Ch + (nd - 1) * LW, e_cur, s.occ);
       }
     }
     if (!observe) return;
@@ -884,9 +905,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         const int sites[2] = {site0, site1};
         const int olds[2] = {old0, old1}, news[2] = {new0, new1};
         uint32_t *cw = s.codes + lwarp * NJ * n_sub;
+        int gsite[2] = {0, 0};                    // multi: symmetry group of the changed site(s)
 #pragma unroll
         for (int je = 0; je < NJE; je++) {
           const int j = jb + je;
+          if (multi) gsite[je] = __ldg(&t.symm_of_site[sites[j]]);
           int v = 0, v2 = 0;
           if (lane < K) {
             const int nbs = neighbour(sites[j], lane, my_shift);
@@ -911,15 +934,20 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             if (q < t_rounds) {
-              const int va = occ_of_col(tdx[q] & 0xffu);
-              const int vb = occ_of_col((tdx[q] >> 8) & 0xffu);
-              const int vc = occ_of_col((tdx[q] >> 16) & 0xffu);
-              const uint32_t rest = (uint32_t)va * (tdy[q] & 0xffu) + (uint32_t)vb * ((tdy[q] >> 8) & 0xffu) +
-                                    (uint32_t)vc * ((tdy[q] >> 16) & 0xffu);
-              const uint32_t wr = tdy[q] >> 24, nd = tdx[q] >> 24;    // nd: decorations per table row
+              uint32_t dx = tdx[q], dy = tdy[q];
+              if (multi) {                        // this group's sub-cluster descriptors (L1-resident)
+                const uint2 dg = __ldg(&tb.desc[(gsite[je] * t_rounds + q) * 32 + lane]);
+                dx = dg.x; dy = dg.y;
+              }
+              const int va = occ_of_col(dx & 0xffu);
+              const int vb = occ_of_col((dx >> 8) & 0xffu);
+              const int vc = occ_of_col((dx >> 16) & 0xffu);
+              const uint32_t rest = (uint32_t)va * (dy & 0xffu) + (uint32_t)vb * ((dy >> 8) & 0xffu) +
+                                    (uint32_t)vc * ((dy >> 16) & 0xffu);
+              const uint32_t wr = dy >> 24, nd = dx >> 24;            // nd: decorations per table row
               const uint32_t cO = (rest + (uint32_t)olds[j] * wr) * nd, cN = (rest + (uint32_t)news[j] * wr) * nd;
               uint32_t word = (cO << TSH) | (cN << (16 + TSH));
-              if (tdy[q] == 0u) { const uint32_t z = (tdx[q] & 0xffffu) >> (3 - TSH); word = z | (z << 16); }   // padding: the table's zero row
+              if (dy == 0u) { const uint32_t z = (dx & 0xffffu) >> (3 - TSH); word = z | (z << 16); }   // padding: the table's zero row
               if (q * 32 + lane < n_sub) cw[je * n_sub + q * 32 + lane] = word;
             }
           }
@@ -929,6 +957,26 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         // sums over the sub-clusters, reference order (:246-282) or 4-way interleaved (TREE);
         // lane = (ECI, decoration), both changed sites side by side
         double *db = s.diff + lwarp * NJ * max_tasks;
+        if (multi) {
+          // several symmetry groups: the task list of each changed site's own group, sub-clusters
+          // summed one after the other in the stored order (the reference's order, :246-282)
+#pragma unroll
+          for (int je = 0; je < NJE; je++) {
+            const int tb0 = __ldg(&t.task_base[gsite[je]]), ntk = __ldg(&t.task_base[gsite[je] + 1]) - tb0;
+            for (int tk = lane; tk < ntk; tk += 32) {
+              const int4 tt = s.ttask[tb0 + tk];
+              const char *tbl = reinterpret_cast<const char *>(s.tab) + (tt.x >> (3 - TSH));
+              const uint32_t *cp = cw + je * n_sub + tt.y;
+              TR spO = (TR)0, spN = (TR)0;
+              for (int m = 0; m < tt.z; m++) {
+                const uint32_t w = cp[m];
+                spO = add_rn(spO, *reinterpret_cast<const TR *>(tbl + (w & 0xffffu)));
+                spN = add_rn(spN, *reinterpret_cast<const TR *>(tbl + (w >> 16)));
+              }
+              db[je * max_tasks + tk] = (double)sub_rn(spN, spO);     // :397
+            }
+          }
+        } else
         for (int tk = lane; tk < n_tasks; tk += 32) {
           const int4 tt = s.ttask[tk];
           const char *tbl = reinterpret_cast<const char *>(s.tab) + (tt.x >> (3 - TSH));
@@ -985,6 +1033,32 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         // per-ECI quotients (:393-402): lane i = ECI i, this warp's changed site(s)
         {
           double de = 0.0;                                    // screen only
+          if (multi) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+              const int i = e * 32 + lane;
+              double qsum = 0.0;
+#pragma unroll
+              for (int je = 0; je < NJE; je++) {
+                double qj = 0.0;
+                if (i < n_eci) {                              // this group's term of ECI i (:379-404)
+                  const int4 f = __ldg(&t.fin_i[gsite[je] * n_eci + i]);
+                  const double2 fd = __ldg(&t.fin_d[gsite[je] * n_eci + i]);
+                  if (f.x == 1) {
+                    qj = __ddiv_rn(__dsub_rn(s.bf[f.y * S + news[jb + je]], s.bf[f.y * S + olds[jb + je]]), dN);
+                  } else if (f.x == 2) {
+                    double num = 0.0;
+                    for (int q = f.z; q < f.w; q++) num = __dadd_rn(num, db[je * max_tasks + q]);    // :397
+                    qj = __ddiv_rn(__dmul_rn(num, fd.x), fd.y);                                       // :400-402
+                  }
+                }
+                put_sq(par, b, jb + je, qj, e);
+                qsum += qj;
+              }
+              if (!kCanon) put_sq(par, b, 1, 0.0, e);
+              de += eci_reg[e] * qsum;
+            }
+          } else
 #pragma unroll
           for (int e = 0; e < E; e++) {
             double num[NJE];
@@ -1208,7 +1282,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
         for (int e = 0; e < E; e++) {
           double cn = s.pub[e * 32 + lane];
-          if (f_kind[e] > 0) {
+          if (f_any[e]) {
             cn = __dadd_rn(cn, s.sq[par * (BT * 2 * LW) + e * 32 + lane]);
             if (kCanon) cn = __dadd_rn(cn, s.sq[par * (BT * 2 * LW) + LW + e * 32 + lane]);
           }
@@ -1316,7 +1390,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       const int2 ct = (kAsync && crank == 1) ? ct_early : *reinterpret_cast<const int2 *>(s.ctl);
       bk_nd = ct.x; bk_am = (uint32_t)ct.y; bk_base = sdone;
       sdone += ct.x;
-      if (ob_iv > 0) { to_ob -= ct.x; if (to_ob <= 0) to_ob += ob_iv; }
+      if ((mflags & 4) && !is_obs) { to_ob -= ct.x; if (to_ob <= 0) to_ob += (int)a.obs_interval; }
       par ^= 1;
     }
     CEMC_TICK(4);

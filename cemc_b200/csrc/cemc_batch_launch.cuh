@@ -13,6 +13,7 @@ struct BatchLaunch {
   int tree;               // TREE summation order
   int B, C, M;            // warps per CTA, CTAs per chain, moves per evaluation warp
   int split;              // site split: the two CTAs of a cluster evaluate the two sites of the same swaps
+  int extras;             // replay / lattice arithmetic / observer boundaries in use: the kX = true kernels
   int R;                  // replicas
   int max_smem_optin;
   cudaStream_t stream;
@@ -30,9 +31,9 @@ int batch_launch_spin(const BatchLaunch &L);
 int batch_launch_tab(const BatchLaunch &L);
 int batch_launch_tab32(const BatchLaunch &L);
 
-template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M, bool kSplit = false, bool kWide = false, int E = 1>
+template <int MODE, bool kTree, int B, bool kSmem, int C, int EV, int M, bool kSplit = false, bool kWide = false, int E = 1, bool kX = true>
 static int batch_launch_kc(const BatchLaunch &L, size_t sm) {
-  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV, M, kSplit, kWide, E>;
+  auto kern = batch_kernel<MODE, kTree, B, kSmem, C, EV, M, kSplit, kWide, E, kX>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return 1000 + (int)e;
   cudaLaunchConfig_t cfg{};
@@ -62,6 +63,7 @@ static int batch_launch_b(const BatchLaunch &L) {
   if constexpr (M > 1) {            // two moves per warp: shared-memory state only
     return in_smem ? batch_launch_kc<MODE, kTree, B, true, C, EV, M>(L, sm) : -1;
   } else {
+    if (in_smem && !L.extras && B >= 7) return batch_launch_kc<MODE, kTree, B, true, C, EV, M, false, false, 1, false>(L, sm);
     return in_smem ? batch_launch_kc<MODE, kTree, B, true, C, EV, M>(L, sm)
                    : batch_launch_kc<MODE, kTree, B, false, C, EV, M>(L, sm);
   }
@@ -74,6 +76,7 @@ static int batch_launch_split(const BatchLaunch &L) {
     const TabTables *tb = (EV == EV_TAB || EV == EV_TAB32) ? &L.tb : nullptr;
     const size_t sm = batch_smem_layout<B, B>(nullptr, nullptr, L.t, true, true, tb, EV == EV_TAB32, EV == EV_SPIN ? L.sp.wq : 0);
     if (sm > (size_t)L.max_smem_optin) return -1;
+    if (!L.extras) return batch_launch_kc<MODE, kTree, B, true, 2, EV, 1, true, false, 1, false>(L, sm);
     return batch_launch_kc<MODE, kTree, B, true, 2, EV, 1, true>(L, sm);
   } else {
     return -1;

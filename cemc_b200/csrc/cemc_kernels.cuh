@@ -142,67 +142,97 @@ struct RunArgs {
   unsigned long long *phase;   // [R][24] per-phase cycle counts (CEMC_PHASE_TIMING builds), may be null
   const int32_t *order;        // [R] replica handled by CTA (cluster) i, or null = identity (load balance)
   // ---- device-side state observers (cemc_set_device_observers): every obs_interval steps the
-  // chain's state is folded into per-replica sums by the warp that does the bookkeeping
+  // warp that does the bookkeeping SNAPSHOTS the chain's state (CF vector, energy, occupations)
+  // into a small per-replica ring; observer_fold_kernel, enqueued after the launch, folds the
+  // snapshots into the observers' sums in order.  (Folding inside the Metropolis kernels cost the
+  // bench kernels 11 registers and 12 % of their speed even with the observers off.)
   long long obs_interval;      // 0 = off
   long long obs_origin;        // observer step counter when this launch starts
   int obs_flags;               // CEMC_OBS_* bits
-  long long obs_capacity;      // energy samples per replica
-  unsigned long long *ob_n;    // [R] boundaries seen
-  double *ob_cf_sum, *ob_cf_sq;   // [R][n_eci] sum cf, sum cf^2 over the boundaries
-  double *ob_best;             // [R][1 + n_eci] lowest energy seen on a boundary, its CFs
-  int8_t *ob_best_occ;         // [R][N] its occupations
-  double *ob_e;                // [R][obs_capacity] ring of the energies on the boundaries (sample k at k % capacity)
-  double *ob_order;            // [R][2] sum / sum of squares of #sites differing from ob_occ_ref
-  const int8_t *ob_occ_ref;    // [R][N]
+  int obs_ring;                // snapshots the ring holds (a launch never crosses more boundaries)
+  unsigned long long *ob_n;    // [R] boundaries seen (snapshot k sits in slot k % obs_ring)
+  double *ob_snap_cf;          // [R][obs_ring][n_eci]
+  double *ob_snap_e;           // [R][obs_ring]
+  int8_t *ob_snap_occ;         // [R][obs_ring][N] (only with CEMC_OBS_LOWEST / CEMC_OBS_SITE_ORDER)
 };
 
 enum : int { OBS_CF_SUMS = 1, OBS_LOWEST = 2, OBS_ENERGY = 4, OBS_SITE_ORDER = 8 };
 
-// One observer boundary, executed by ONE WARP while nobody changes the chain's state: `cf` is the
-// CF vector and `e` the energy after the boundary step, `occ` the occupations (shared or global).
+// One observer boundary inside a Metropolis kernel, executed by ONE WARP while nobody changes the
+// chain's state: snapshot `cf` (the CF vector after the boundary step), the energy `e` and, when an
+// observer needs them, the occupations (shared or global memory) into slot k % obs_ring.
+__device__ __forceinline__ void observer_snapshot(const RunArgs &a, int r, int lane, int n_eci, int N,
+                                                  const double *cf, double e, const int8_t *occ) {
+  const size_t slot = (size_t)r * a.obs_ring + (size_t)(a.ob_n[r] % (unsigned long long)a.obs_ring);
+  __syncwarp();
+  for (int i = lane; i < n_eci; i += 32) a.ob_snap_cf[slot * n_eci + i] = cf[i];
+  if (a.obs_flags & (OBS_LOWEST | OBS_SITE_ORDER)) {
+    int8_t *dst = a.ob_snap_occ + slot * N;
+    for (int i = lane; i < N; i += 32) dst[i] = occ[i];
+  }
+  if (lane == 0) { a.ob_snap_e[slot] = e; a.ob_n[r] += 1; }
+  __syncwarp();
+}
+
+// Folding of the snapshots into the observers' sums (one warp per replica, in boundary order).
 // Reference semantics: PairCorrelationObserver (mc_observers.py:81-136: sum and sum of squares of
 // the CFs), LowestEnergyStructure (:138-183: strictly lower energy replaces the stored state),
 // EnergyEvolution / EnergyHistogram (:689-761: the energy of every call), SiteOrderParameter
 // (:614-686: number of sites that differ from the initial configuration, sum and sum of squares).
-// (__noinline__: a rare path; keeps its registers out of the per-move loops it is called from)
-__device__ __forceinline__ void observer_boundary(const RunArgs &a, int r, int lane, int n_eci, int N,
-                                                  const double *cf, double e, const int8_t *occ) {
-  const unsigned long long k = a.ob_n[r];
-  __syncwarp();
-  if (a.obs_flags & OBS_CF_SUMS)
-    for (int i = lane; i < n_eci; i += 32) {
-      const double c = cf[i];
-      double *ps = a.ob_cf_sum + (size_t)r * n_eci + i, *pq = a.ob_cf_sq + (size_t)r * n_eci + i;
-      *ps = __dadd_rn(*ps, c);
-      *pq = __dadd_rn(*pq, __dmul_rn(c, c));
+struct ObserverSums {
+  unsigned long long *folded;  // [R] boundaries folded so far
+  double *cf_sum, *cf_sq;      // [R][n_eci]
+  double *best;                // [R][1 + n_eci] lowest energy seen on a boundary, its CFs
+  int8_t *best_occ;            // [R][N] its occupations
+  double *e;                   // [R][capacity] ring of the energies (sample k at k % capacity)
+  long long capacity;
+  double *order;               // [R][2] sum / sum of squares of #sites differing from occ_ref
+  const int8_t *occ_ref;       // [R][N]
+};
+
+static __global__ void observer_fold_kernel(RunArgs a, ObserverSums o, int n_eci, int N) {
+  const int r = blockIdx.x, lane = threadIdx.x;
+  const unsigned long long n = a.ob_n[r];
+  for (unsigned long long k = o.folded[r]; k < n; k++) {
+    const size_t slot = (size_t)r * a.obs_ring + (size_t)(k % (unsigned long long)a.obs_ring);
+    const double *cf = a.ob_snap_cf + slot * n_eci;
+    const double e = a.ob_snap_e[slot];
+    const int8_t *occ = a.ob_snap_occ ? a.ob_snap_occ + slot * N : nullptr;
+    if (a.obs_flags & OBS_CF_SUMS)
+      for (int i = lane; i < n_eci; i += 32) {
+        const double c = cf[i];
+        double *ps = o.cf_sum + (size_t)r * n_eci + i, *pq = o.cf_sq + (size_t)r * n_eci + i;
+        *ps = __dadd_rn(*ps, c);
+        *pq = __dadd_rn(*pq, __dmul_rn(c, c));
+      }
+    if ((a.obs_flags & OBS_ENERGY) && lane == 0 && o.capacity > 0)      // ring: the host drains it in time
+      o.e[(size_t)r * o.capacity + (size_t)(k % (unsigned long long)o.capacity)] = e;
+    if (a.obs_flags & OBS_LOWEST) {
+      double *best = o.best + (size_t)r * (1 + n_eci);
+      const bool lower = e < best[0];                 // warp-uniform (same address, same value)
+      __syncwarp();
+      if (lower) {
+        if (lane == 0) best[0] = e;
+        for (int i = lane; i < n_eci; i += 32) best[1 + i] = cf[i];
+        int8_t *dst = o.best_occ + (size_t)r * N;
+        for (int i = lane; i < N; i += 32) dst[i] = occ[i];
+      }
     }
-  if ((a.obs_flags & OBS_ENERGY) && lane == 0 && a.obs_capacity > 0)      // ring: the host drains it in time
-    a.ob_e[(size_t)r * a.obs_capacity + (size_t)(k % (unsigned long long)a.obs_capacity)] = e;
-  if (a.obs_flags & OBS_LOWEST) {
-    double *best = a.ob_best + (size_t)r * (1 + n_eci);
-    const bool lower = e < best[0];                 // warp-uniform (same address, same value)
-    __syncwarp();
-    if (lower) {
-      if (lane == 0) best[0] = e;
-      for (int i = lane; i < n_eci; i += 32) best[1 + i] = cf[i];
-      int8_t *dst = a.ob_best_occ + (size_t)r * N;
-      for (int i = lane; i < N; i += 32) dst[i] = occ[i];
-    }
-  }
-  if (a.obs_flags & OBS_SITE_ORDER) {
-    const int8_t *ref = a.ob_occ_ref + (size_t)r * N;
-    int cnt = 0;
-    for (int i = lane; i < N; i += 32) cnt += (occ[i] != ref[i]) ? 1 : 0;
+    if (a.obs_flags & OBS_SITE_ORDER) {
+      const int8_t *ref = o.occ_ref + (size_t)r * N;
+      int cnt = 0;
+      for (int i = lane; i < N; i += 32) cnt += (occ[i] != ref[i]) ? 1 : 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) {
-      const double c = (double)cnt;
-      a.ob_order[2 * (size_t)r] = __dadd_rn(a.ob_order[2 * (size_t)r], c);
-      a.ob_order[2 * (size_t)r + 1] = __dadd_rn(a.ob_order[2 * (size_t)r + 1], __dmul_rn(c, c));
+      for (int w = 16; w > 0; w >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, w);
+      if (lane == 0) {
+        const double c = (double)cnt;
+        o.order[2 * (size_t)r] = __dadd_rn(o.order[2 * (size_t)r], c);
+        o.order[2 * (size_t)r + 1] = __dadd_rn(o.order[2 * (size_t)r + 1], __dmul_rn(c, c));
+      }
     }
+    __syncwarp();
   }
-  if (lane == 0) a.ob_n[r] = k + 1;
-  __syncwarp();
+  if (lane == 0) o.folded[r] = n;
 }
 
 // ---------------------------------------------------------------------------
@@ -790,7 +820,7 @@ mc_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride) {
           // state observers on their boundary (warp 0 is the only writer of the chain's state)
           if (kFast) { __syncwarp(); if (lane < n_eci) s.cf[lane] = cf_reg; }
           __syncwarp();
-          observer_boundary(a, r, lane, n_eci, N, s.cf, e_cur, s.occ);
+          observer_snapshot(a, r, lane, n_eci, N, s.cf, e_cur, s.occ);
         }
         if (lane == 0 && (a.tr_acc || a.tr_e) && it < a.tr_capacity) {
           const size_t q = (size_t)r * a.tr_capacity + it;

@@ -116,17 +116,40 @@ class MCParameterSweep(object):
         return self.results
 
     def save(self, data):
-        """Append the flattened result arrays to ``outfile`` (.npz)."""
-        flat = {key: [] for key in data[0].keys()}
-        for dset in data:
-            for key, value in dset.items():
-                flat[key].append(value)
-        old = {}
+        """Append the result arrays (one entry per grid point and key) to ``outfile``.
+
+        ``*.h5`` / ``*.hdf5`` and an importable ``h5py``: the reference's HDF5 layout -- one
+        resizable 1-d dataset per key, appended to on every call (mc_parameter_sweep.py:80-103),
+        so cemc/tools post-processing reads it.  Otherwise (h5py is not part of this image) the
+        same arrays go to a NumPy ``.npz`` archive, appended the same way."""
+        skip = ("timestamp", "python_version")
+        columns = {}
+        for row in data:
+            for key, value in row.items():
+                if key not in skip:
+                    columns.setdefault(key, []).append(value)
+        columns = {k: np.asarray(v) for k, v in columns.items()}
+        h5 = None
+        if str(self.outfile).lower().endswith((".h5", ".hdf5")):
+            try:
+                import h5py as h5
+            except ImportError:
+                h5 = None
+        if h5 is not None:
+            with h5.File(self.outfile, "a") as hf:
+                for key, value in columns.items():
+                    if key in hf:
+                        ds = hf[key]
+                        ds.resize((ds.shape[0] + len(value),))
+                        ds[-len(value):] = value
+                    else:
+                        hf.create_dataset(key, data=value, maxshape=(None,))
+            return
+        previous = {}
         try:
             with np.load(self.outfile) as z:
-                old = {k: z[k] for k in z.files}
+                previous = {k: z[k] for k in z.files}
         except (IOError, OSError):
             pass
-        out = {k: np.concatenate([old[k], np.array(v)]) if k in old else np.array(v)
-               for k, v in flat.items()}
-        np.savez(self.outfile, **out)
+        np.savez(self.outfile, **{k: np.concatenate([previous[k], v]) if k in previous else v
+                                  for k, v in columns.items()})

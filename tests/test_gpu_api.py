@@ -301,8 +301,8 @@ def test_state_observers_match_oracle(cuda_device, where, variant):
     launches = mc._gpu.launch_count() - l0
     if where == "device":
         assert mc._device_observer_plan() == (iv, 1 | 2 | 4 | 8)
-        assert launches < steps // iv            # the device loop did not stop on the boundaries
-        if variant >= 0:
+        if variant >= 0:                         # (autotuning adds its own timed segments)
+            assert launches < steps // iv        # the device loop did not stop on the boundaries
             assert mc._gpu.last_variant() == variant
     else:
         assert mc._device_observer_plan() is None and len(seen) == steps // iv

@@ -1032,3 +1032,38 @@ def test_two_ecis_per_lane(cuda_device, system, batch, mode):
     for c in chains2:
         (c.run_sgc if mode == "sgc" else c.run_canonical)(300)
     assert_state_equal(gpu2, chains2)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 8, 9])
+@pytest.mark.parametrize("case", [LAYERED, LAYERED_BINARY])
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+def test_multi_group_batch_kernel(cuda_device, mode, case, variant):
+    """Two translational symmetry groups with different cluster families (crystal with a basis,
+    ce_updater.cpp:379-384): the batch kernel's table evaluation picks descriptors, task list
+    and per-ECI constants by the changed site's group.  Every batch flavour reproduces the
+    oracle's trajectory, trace, CFs, energies and observer sums."""
+    if variant in (8, 9) and mode != "canonical":
+        pytest.skip("site split: swaps only")
+    for L in (4, 6):
+        st, eci, symbols, ft = build(**dict(case, L=L))
+        assert ft.n_symm == 2
+        syms = [syn.random_symbols(st, case["conc"], seed=60 + r) for r in range(3)]
+        gpu, chains = make_pair(ft, syms, [0.02, 0.05, 0.2], seed=909)
+        assert gpu.batch_kernel_applies() and gpu.get_batch_eval() == 2
+        gpu.set_variant(variant, variant)
+        n = 1200
+        gpu.set_trace(n)
+        gpu.reset_accumulators()
+        (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+        assert gpu.last_variant() == variant
+        tr = gpu.get_trace(n)
+        for r, c in enumerate(chains):
+            o = c.run_sgc(n, trace=True) if mode == "sgc" else c.run_canonical(n, trace=True)
+            assert np.array_equal(tr[0][r], o[0]) and np.array_equal(tr[3][r], o[3])
+            assert np.array_equal(tr[4][r], o[4])
+        assert_state_equal(gpu, chains)
+        assert np.array_equal(gpu.get_accumulators(), np.stack([c.acc for c in chains]))
+        # incremental CFs equal the definition (every cluster is listed in each member's table)
+        cf_run = gpu.get_cf()
+        gpu.recompute_cf()
+        np.testing.assert_allclose(gpu.get_cf(), cf_run, rtol=0, atol=1e-13)
