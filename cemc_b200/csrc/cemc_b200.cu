@@ -70,6 +70,8 @@ struct cemc_handle {
   int32_t *tr_sites = nullptr; int8_t *tr_news = nullptr; double *tr_u = nullptr;
   uint8_t *tr_acc = nullptr; double *tr_e = nullptr;
   double *cf_partial = nullptr;         // [R][n_jobs]
+  double *cf_slots = nullptr;           // [R][n_jobs][cf_n_slots] (table-based recompute)
+  int cf_n_slots = 0;
   int32_t *pt_scratch = nullptr; int pt_scratch_n = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // cemc_timer_start / _stop
   cudaEvent_t tv0 = nullptr, tv1 = nullptr;     // the autotuner's own pair
@@ -77,6 +79,7 @@ struct cemc_handle {
   // returns, the copy itself is stream-ordered (no host synchronisation per setter)
   struct Staging { void *host = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; };
   Staging stg_occ, stg_eci, stg_kT, stg_cf, stg_ref;
+  Staging stg_out;                     // getters: device -> pinned (one synchronisation) -> caller's buffer
   // host copies needed by the API
   std::vector<int32_t> symm_of_site;
   std::vector<int8_t> allowed;
@@ -270,6 +273,101 @@ __global__ void cf_partial_kernel(DeviceTables t, const int8_t *occ, double *par
   if (threadIdx.x == 0) partial[(size_t)r * n_jobs + job] = red[0];
 }
 
+// Brute-force CF partial sums with the product tables of the batch kernel (TabTables): per tile
+// of CF_TILE sites, (1) two threads per site pack the occupations of every sub-cluster of the
+// site into table offsets (the codes are shared by all decorations of a family), (2) one thread
+// per (task, site subset) adds table entries.  ~6x fewer instructions than one product per
+// (site, task, sub-cluster, factor) and no dependent global gathers in the inner loop: the
+// occupations of the replica and the tables sit in shared memory.  Deterministic: every (chunk,
+// group, task) partial sum has its own slot; cf_final_kernel adds the slots in a fixed order.
+#define CF_TILE 128
+__global__ void __launch_bounds__(256)
+cf_tab_kernel(DeviceTables t, TabTables tb, const int8_t *occ_all, double *partial, int n_jobs,
+              int n_slots, int chunks, int tasks_pad, int occ_in_smem) {
+  extern __shared__ __align__(16) unsigned char cf_smem[];
+  const int r = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int N = t.N, K = t.K, n_sub = tb.n_sub, stride = tb.n_rounds * 32;
+  double *tab_s = reinterpret_cast<double *>(cf_smem);
+  unsigned short *codes = reinterpret_cast<unsigned short *>(tab_s + tb.n_tab);     // [CF_TILE][n_sub]
+  int8_t *occ_s = reinterpret_cast<int8_t *>(codes + (size_t)CF_TILE * n_sub);
+  const int8_t *g_occ = occ_all + (size_t)r * N;
+  for (int i = tid; i < tb.n_tab; i += 256) tab_s[i] = tb.tab[i];
+  if (occ_in_smem) for (int i = tid; i < N; i += 256) occ_s[i] = g_occ[i];
+  const int8_t *o = occ_in_smem ? occ_s : g_occ;
+  __syncthreads();
+  const int per = (N + chunks - 1) / chunks, a_begin = chunk * per, a_end = min(N, a_begin + per);
+  const int groups = 256 / tasks_pad, my_task = tid % tasks_pad, my_grp = tid / tasks_pad;
+  int task_group = 0;                                   // symmetry group my task belongs to
+  int4 tt = make_int4(0, 0, 0, 0);
+  if (my_task < t.n_tasks_total) {
+    while (my_task >= t.task_base[task_group + 1]) task_group++;
+    tt = tb.task[my_task];
+  }
+  double acc = 0.0;
+  for (int a0 = a_begin; a0 < a_end; a0 += CF_TILE) {
+    // (1) codes: thread pair (2 s, 2 s + 1) shares site a0 + s, each takes every other sub-cluster
+    {
+      const int sl = tid >> 1, a = a0 + sl;
+      if (a < a_end) {
+        const int g = t.symm_of_site[a];
+        const int me = o[a];
+        const int32_t *row = t.trans + (size_t)a * K;
+        for (int q = tid & 1; q < n_sub; q += 2) {
+          unsigned short w = 0;
+          if (g >= 0) {
+            const uint2 d = tb.desc[g * stride + q];
+            if (d.y == 0u) w = (unsigned short)(d.x & 0xffffu);                  // padding: the zero row
+            else {
+              const uint32_t rest = (uint32_t)o[__ldg(row + (d.x & 0xffu))] * (d.y & 0xffu) +
+                                    (uint32_t)o[__ldg(row + ((d.x >> 8) & 0xffu))] * ((d.y >> 8) & 0xffu) +
+                                    (uint32_t)o[__ldg(row + ((d.x >> 16) & 0xffu))] * ((d.y >> 16) & 0xffu);
+              w = (unsigned short)(((rest + (uint32_t)me * (d.y >> 24)) * (d.x >> 24)) << 3);
+            }
+          }
+          codes[sl * n_sub + q] = w;
+        }
+      }
+    }
+    __syncthreads();
+    // (2) sums: my task over the sites of my group of threads
+    if (my_task < t.n_tasks_total) {
+      const char *tbl = reinterpret_cast<const char *>(tab_s) + tt.x;
+      const int n_here = min(CF_TILE, a_end - a0);
+      for (int sl = my_grp; sl < n_here; sl += groups) {
+        if (t.symm_of_site[a0 + sl] != task_group) continue;
+        const unsigned short *cp = codes + sl * n_sub + tt.y;
+        double sp = 0.0;
+        for (int m = 0; m < tt.z; m++) sp += *reinterpret_cast<const double *>(tbl + cp[m]);
+        acc += sp;
+      }
+    }
+    __syncthreads();
+  }
+  if (my_task < t.n_tasks_total)
+    partial[((size_t)r * n_jobs + my_task) * n_slots + chunk * groups + my_grp] = acc;
+  // singlet jobs: sum of the basis function over the active sites of this chunk
+  __shared__ double red[256];
+  for (int d = 0; d < t.D; d++) {
+    double sv = 0.0;
+    for (int a = a_begin + tid; a < a_end; a += 256)
+      if (t.symm_of_site[a] >= 0) sv += t.bf[d * t.S + o[a]];
+    red[tid] = sv;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) { if (tid < w) red[tid] += red[tid + w]; __syncthreads(); }
+    if (tid < groups) partial[((size_t)r * n_jobs + t.n_tasks_total + d) * n_slots + chunk * groups + tid] = tid == 0 ? red[0] : 0.0;
+    __syncthreads();
+  }
+}
+
+// out[q] = sum of the n_slots partial sums of (replica, job) q, in ascending slot order
+__global__ void cf_slot_sum_kernel(const double *slots, double *out, int n, int n_slots) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  double v = 0.0;
+  for (int k = 0; k < n_slots; k++) v += slots[(size_t)q * n_slots + k];
+  out[q] = v;
+}
+
 __global__ void cf_final_kernel(DeviceTables t, const double *partial, int n_jobs, double *cf) {
   const int r = blockIdx.x;
   for (int i = threadIdx.x; i < t.n_eci; i += blockDim.x) {
@@ -451,6 +549,41 @@ static int check_status(cemc_handle *h) {
     }
   }
   return 0;
+}
+
+static int status_error(cemc_handle *h, const int32_t *stt) {
+  for (int r = 0; r < h->R; r++) {
+    if (stt[r]) {
+      CU(cudaMemsetAsync(h->st.status, 0, sizeof(int32_t) * h->R, h->stream));
+      char buf[160];
+      const char *why = stt[r] == 1 ? "Attempting to move a background atom!"
+                        : stt[r] == 2 ? "There is only one element in the given atoms object!"
+                                      : "proposal out of range";
+      snprintf(buf, sizeof buf, "replica %d: %s", r, why);
+      return fail(buf, 10 + stt[r]);
+    }
+  }
+  return 0;
+}
+
+// Getter: device -> pinned staging buffer (a pageable destination would make the driver stage the
+// copy itself, several times slower), the kernels' status words ride along, ONE stream
+// synchronisation, then a host copy into the caller's buffer.
+static int d2h_staged(cemc_handle *h, void *dst, const void *src, size_t bytes, bool with_status) {
+  cemc_handle::Staging &st = h->stg_out;
+  const size_t sbytes = sizeof(int32_t) * (size_t)h->R, need = ((bytes + 15) / 16) * 16 + sbytes;
+  if (st.cap < need) {
+    if (st.host) { CU(cudaFreeHost(st.host)); st.host = nullptr; st.cap = 0; }
+    CU(cudaMallocHost(&st.host, need));
+    st.cap = need;
+  }
+  char *pin = static_cast<char *>(st.host);
+  int32_t *pstat = reinterpret_cast<int32_t *>(pin + ((bytes + 15) / 16) * 16);
+  CU(cudaMemcpyAsync(pin, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (with_status) CU(cudaMemcpyAsync(pstat, h->st.status, sbytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  memcpy(dst, pin, bytes);
+  return with_status ? status_error(h, pstat) : 0;
 }
 
 extern "C" {
@@ -857,11 +990,11 @@ int cemc_destroy(cemc_handle *h) {
   void *extra[] = {h->d_sites, h->d_news, h->d_u, h->d_acc, h->d_e, h->tr_sites, h->tr_news,
                    h->tr_u, h->tr_acc, h->tr_e, h->pt_scratch, h->ob_n, h->ob_folded, h->ob_snap_cf,
                    h->ob_snap_e, h->ob_snap_occ, h->ob_cf_sum, h->ob_cf_sq,
-                   h->ob_best, h->ob_e, h->ob_order, h->ob_best_occ, h->ob_occ_ref};
+                   h->ob_best, h->ob_e, h->ob_order, h->ob_best_occ, h->ob_occ_ref, h->cf_slots};
   for (void *p : extra) if (p) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
-  for (cemc_handle::Staging *st : {&h->stg_occ, &h->stg_eci, &h->stg_kT, &h->stg_cf, &h->stg_ref}) {
+  for (cemc_handle::Staging *st : {&h->stg_occ, &h->stg_eci, &h->stg_kT, &h->stg_cf, &h->stg_ref, &h->stg_out}) {
     if (st->ev) { cudaEventSynchronize(st->ev); cudaEventDestroy(st->ev); }
     if (st->host) cudaFreeHost(st->host);
   }
@@ -949,9 +1082,7 @@ int cemc_set_occupancy(cemc_handle *h, const int8_t *occ) {
 int cemc_get_occupancy(cemc_handle *h, int8_t *occ) {
   if (!h || !occ) return fail("null argument");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(occ, h->st.occ, (size_t)h->R * h->t.N, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return 0;
+  return d2h_staged(h, occ, h->st.occ, (size_t)h->R * h->t.N, false);
 }
 
 int cemc_set_cf(cemc_handle *h, const double *cf) {
@@ -965,18 +1096,49 @@ int cemc_set_cf(cemc_handle *h, const double *cf) {
 int cemc_get_cf(cemc_handle *h, double *cf) {
   if (!h || !cf) return fail("null argument");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(cf, h->st.cf, sizeof(double) * h->R * h->t.n_eci, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return 0;
+  return d2h_staged(h, cf, h->st.cf, sizeof(double) * h->R * h->t.n_eci, false);
 }
 
 int cemc_recompute_cf(cemc_handle *h) {
   if (!h) return fail("null handle");
   CU(cudaSetDevice(h->device));
-  dim3 grid(h->n_jobs, h->R);
-  cf_partial_kernel<<<grid, 256, 0, h->stream>>>(h->t, h->st.occ, h->cf_partial, h->n_jobs);
+  bool done = false;
+  if (h->tab_ok && h->t.n_tasks_total <= 256 && !h->force_generic) {
+    // product tables available: codes per sub-cluster + table sums (cf_tab_kernel)
+    int tasks_pad = 1;
+    while (tasks_pad < h->t.n_tasks_total) tasks_pad *= 2;
+    const int groups = 256 / tasks_pad;
+    int chunks = std::max(1, std::min(16, 2 * h->n_sms / std::max(1, h->R)));
+    chunks = std::min(chunks, (h->t.N + CF_TILE - 1) / CF_TILE);
+    const int n_slots = chunks * groups;
+    size_t sm = (size_t)h->tab.n_tab * sizeof(double) + (size_t)CF_TILE * h->tab.n_sub * sizeof(unsigned short);
+    const int occ_in_smem = (sm + (size_t)h->t.N + 16 <= (size_t)h->max_smem_optin) ? 1 : 0;
+    if (occ_in_smem) sm += (size_t)h->t.N;
+    sm = (sm + 15) / 16 * 16;
+    if (sm <= (size_t)h->max_smem_optin) {
+      if (h->cf_n_slots < n_slots) {
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->cf_slots) cudaFree(h->cf_slots);
+        h->cf_slots = nullptr; h->cf_n_slots = 0;
+        CU(cudaMalloc((void **)&h->cf_slots, sizeof(double) * (size_t)h->R * h->n_jobs * n_slots));
+        h->cf_n_slots = n_slots;
+      }
+      CU(cudaFuncSetAttribute(cf_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      cf_tab_kernel<<<dim3(chunks, h->R), 256, sm, h->stream>>>(h->t, h->tab, h->st.occ, h->cf_slots, h->n_jobs,
+                                                                n_slots, chunks, tasks_pad, occ_in_smem);
+      const int nq = h->R * h->n_jobs;
+      cf_slot_sum_kernel<<<(nq + 127) / 128, 128, 0, h->stream>>>(h->cf_slots, h->cf_partial, nq, n_slots);
+      h->launches += 2;
+      done = true;
+    }
+  }
+  if (!done) {
+    dim3 grid(h->n_jobs, h->R);
+    cf_partial_kernel<<<grid, 256, 0, h->stream>>>(h->t, h->st.occ, h->cf_partial, h->n_jobs);
+    h->launches++;
+  }
   cf_final_kernel<<<h->R, 64, 0, h->stream>>>(h->t, h->cf_partial, h->n_jobs, h->st.cf);
-  h->launches += 2;
+  h->launches++;
   CU(cudaGetLastError());
   drop_trials(h);
   return refresh_energy(h);
@@ -1017,9 +1179,7 @@ int cemc_get_ecis(cemc_handle *h, double *eci) {
 int cemc_get_energy(cemc_handle *h, double *energy) {
   if (!h || !energy) return fail("null argument");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(energy, h->st.e_cur, sizeof(double) * h->R, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return check_status(h);
+  return d2h_staged(h, energy, h->st.e_cur, sizeof(double) * h->R, true);
 }
 
 int cemc_set_kT(cemc_handle *h, const double *kT) {
@@ -1868,9 +2028,7 @@ int cemc_reset_accumulators(cemc_handle *h, const double *ref) {
 int cemc_get_accumulators(cemc_handle *h, double *acc) {
   if (!h || !acc) return fail("null argument");
   CU(cudaSetDevice(h->device));
-  CU(cudaMemcpyAsync(acc, h->st.acc, sizeof(double) * h->R * h->acc_stride, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return check_status(h);
+  return d2h_staged(h, acc, h->st.acc, sizeof(double) * h->R * h->acc_stride, true);
 }
 
 // ---- device-side state observers ---------------------------------------------------

@@ -1067,3 +1067,28 @@ def test_multi_group_batch_kernel(cuda_device, mode, case, variant):
         cf_run = gpu.get_cf()
         gpu.recompute_cf()
         np.testing.assert_allclose(gpu.get_cf(), cf_run, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("case", [BINARY, TERNARY, LAYERED, LAYERED_BINARY,
+                                  dict(L=5, species=["Al", "Mg", "Si"], families=["nn", "2nn", "3nn", "tri", "iso", "tet"],
+                                       conc={"Al": 0.5, "Mg": 0.25, "Si": 0.25})])
+def test_recompute_cf_table_kernel(cuda_device, case):
+    """cemc_recompute_cf with the product tables (codes per sub-cluster + table sums) against the
+    oracle's brute-force definition and against the item-by-item kernel (generic path)."""
+    st, eci, symbols, ft = build(**case)
+    R = 5
+    syms = [syn.random_symbols(st, case["conc"], seed=20 + r) for r in range(R)]
+    occ = np.stack([ft.occupancy(s) for s in syms])
+    want = np.stack([OracleChain(ft, occ[r]).cf for r in range(R)])
+    out = []
+    for generic in (False, True):
+        gpu = BatchedCEUpdater(ft, R)
+        gpu.set_generic_path(generic)
+        gpu.set_occupancy(occ)
+        gpu.recompute_cf()
+        cf = gpu.get_cf()
+        np.testing.assert_allclose(cf, want, rtol=0, atol=2e-14)
+        gpu.recompute_cf()
+        assert np.array_equal(gpu.get_cf(), cf)          # reproducible bits
+        out.append(cf)
+    np.testing.assert_allclose(out[0], out[1], rtol=0, atol=2e-14)
