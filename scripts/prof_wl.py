@@ -6,7 +6,7 @@ from cemc_b200 import workloads as wl
 
 which, variant = sys.argv[1].upper(), int(sys.argv[2])
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 4000
-w = wl.WORKLOADS[which]()
+w = wl.c4_parallel_tempering(R=64, n_total=64) if which == "C4" else wl.WORKLOADS[which]()
 gpu = wl.make_updater(w)
 gpu.set_variant(variant, variant)
 run = gpu.run_sgc if w.mode == "sgc" else gpu.run_canonical
