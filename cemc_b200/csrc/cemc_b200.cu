@@ -901,7 +901,7 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
     std::vector<float> tb_tab32(tb_tab.begin(), tb_tab.end());      // each entry rounded once
     if ((rc = dupload(h, &h->tab.tab32, tb_tab32))) return rc;
   }
-#ifdef CEMC_PHASE_TIMING
+#if defined(CEMC_PHASE_TIMING) || defined(CEMC_WARP_TIMING)
   if ((rc = dalloc(h, &h->d_phase, (size_t)n_replicas * 24))) return rc;
 #endif
   if (t.n_active != N) { if ((rc = dupload(h, &t.active, active))) return rc; }
@@ -1200,7 +1200,7 @@ int cemc_get_kT(cemc_handle *h, double *kT) {
 
 int cemc_debug_phase_cycles(cemc_handle *h, uint64_t *out8) {
   if (!h || !out8) return fail("null argument");
-#ifdef CEMC_PHASE_TIMING
+#if defined(CEMC_PHASE_TIMING) || defined(CEMC_WARP_TIMING)
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpy(out8, h->d_phase, (size_t)h->R * 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost));

@@ -85,10 +85,12 @@ struct BatchSmem {
   int32_t *prop;            // [B][8] decoded proposal
   int32_t *cmask;           // [B] bit k: move b reads a site that move k changes
   int32_t *cmask2;          // site split: the same for the second changed site (written by CTA 1)
+  int2 *scr;                // [2][BT] {conflict mask, screen verdict (1 accept, 2 inconclusive)} of every move of the batch
+  int4 *rec;                // [2][2][BT] site split: {conflict mask, -, dE} of changed site 0 / 1 (summed by the deciding warps)
   int32_t *ctl;             // control words
   int32_t *list;
   int8_t *occ;
-  uint64_t *mbar;           // [0] TMA staging copies; async cluster protocol: [1] evaluations complete (CTA 0), [2] decision arrived (CTA 1)
+  uint64_t *mbar;           // [0] TMA staging copies; async cluster protocol: [1], [2] results of a batch complete (even / odd batches), [3] exact decision arrived (CTA 1)
 };
 
 // B = moves evaluated by this CTA, BT = moves per batch over the whole cluster
@@ -123,7 +125,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   o = align_up(o, 16);                     // code words are read four at a time
   CEMC_TAKE(codes, uint32_t, tb ? B * nj * tb->n_sub : 0);
   CEMC_TAKE(sq, double, 2 * BT * 2 * 32 * E);  // double buffered: the bookkeeper reads batch k during batch k+1
-  CEMC_TAKE(pub, double, 32 * E + 2);
+  CEMC_TAKE(pub, double, 2 * (32 * E + 2));   // double buffered (batch parity)
   CEMC_TAKE(qtab, double, spin_wq * 64);      // spin evaluation: quotient table [new species][count][ECI lane]
   CEMC_TAKE(dEa, double, BT);
   CEMC_TAKE(dEb, double, BT);
@@ -137,6 +139,8 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(prop, int32_t, 2 * BT * 8);
   CEMC_TAKE(cmask, int32_t, BT);
   CEMC_TAKE(cmask2, int32_t, BT);
+  CEMC_TAKE(scr, int2, 2 * BT);
+  CEMC_TAKE(rec, int4, 2 * 2 * BT);
   o = align_up(o, 8);
   CEMC_TAKE(ctl, int32_t, 8);
   CEMC_TAKE(mbar, uint64_t, 4);
@@ -248,47 +252,89 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   } else {
     occ_of[0] = s.occ; list_of[0] = s.list; prop_of[0] = s.prop; ctl_of[0] = s.ctl;
   }
-  // ---- async cluster protocol (C = 2, state in shared memory): CTA 1 sends its evaluation
-  // results to CTA 0 with st.async (the bytes complete CTA 0's mbarrier E), CTA 0's warp 0 waits
-  // for (local arrivals, remote bytes), decides, commits its own copy of the state and sends the
-  // 8-byte decision (moves decided, accept mask) to CTA 1 (completes CTA 1's mbarrier D); CTA 1
-  // applies the commits to its own copy from its own proposal ring.  No barrier.cluster (with
-  // its MEMBAR.ALL.GPU / L1 invalidation) inside the batch loop.
+  // ---- async cluster protocol (C = 2, state in shared memory).  Both CTAs keep a copy of the
+  // chain's state and BOTH decide: every evaluation warp writes the screen record of its move
+  // into its own CTA's shared memory and sends it to the other CTA with st.async (SASS STAS),
+  // whose bytes complete the destination's mbarrier; every warp of either CTA waits for (local
+  // arrivals, remote bytes) of the batch, derives the same decision record with ballots and
+  // applies the accepted changes to its CTA's copy itself (identical values to identical
+  // addresses).  No barrier.cluster (with its MEMBAR.ALL.GPU / L1 invalidation), no block
+  // barrier, no decision round trip inside the batch loop.  CTA 1 additionally sends the
+  // per-ECI quotients to CTA 0, whose observer warp keeps the books; the rare inconclusive
+  // screen is settled by CTA 0 (it has the published CF vector) and mailed to CTA 1.
+  // Everything is double buffered by the batch parity -- two mbarriers as well, so that bytes
+  // of batch k + 1 can never land in the phase of batch k --, and the observer warps send a
+  // token per batch so that no CTA runs more than one batch ahead of ANY warp of the other.
 #ifdef CEMC_SYNC_CLUSTER   // debugging aid: barrier.cluster everywhere (compute-sanitizer's racecheck does not
   constexpr bool kAsync = false;   // model mbarrier transaction counts / st.async as synchronisation)
 #else
   constexpr bool kAsync = (C == 2) && kStateSmem;
 #endif
   const bool remote = kAsync && crank == 1;
-  constexpr uint32_t kTxPerMove = kSplit ? (256u + 8u + 4u) : (32u + 512u + 8u + 4u);
-  uint32_t rE = 0, r_sq = 0, r_dE = 0, r_cm = 0, r_prop = 0, rD = 0, r_ctl = 0, phE = 0, phD = 0;
+  // One CTA per chain: ONE barrier per batch.  Every evaluation warp screens its own move and
+  // publishes {conflict mask, verdict}; after the barrier EVERY warp derives the same decision
+  // record from those words (ballots, no loop) and applies the accepted changes itself -- the
+  // warps store identical values to identical addresses, and each sees its own stores -- so
+  // nobody waits for a deciding warp.  Everything a late warp still reads of batch k while an
+  // early one writes batch k + 1 is double buffered by the batch parity.
+  constexpr bool kRed = (C == 1);
+  constexpr bool kAll = kRed || kAsync;          // every warp decides
+  // bytes one evaluation warp sends to the other CTA per batch: its screen record and its proposal
+  // (site split: a 16-byte partial record; both CTAs derive every proposal themselves); CTA 1 also
+  // sends the quotients of its changed site(s)
+  constexpr uint32_t kTxRec = kSplit ? 16u : (8u + 32u);
+  constexpr uint32_t kTxSq = kSplit ? 256u : 512u;
+  uint32_t r_S0 = 0, r_S1 = 0, r_sq = 0, r_scr = 0, r_rec = 0, r_prop = 0, r_X = 0, r_ctl = 0, r_tok = 0, phX = 0;
   if (kAsync) {
-    rE = mapa_u32(smem_u32(s.mbar + 1), 0);
+    const uint32_t other = (uint32_t)(crank ^ 1);
+    r_S0 = mapa_u32(smem_u32(s.mbar + 1), other);
+    r_S1 = mapa_u32(smem_u32(s.mbar + 2), other);
     r_sq = mapa_u32(smem_u32(s.sq), 0);
-    r_dE = mapa_u32(smem_u32(kSplit ? s.dEb : s.dEa), 0);
-    r_cm = mapa_u32(smem_u32(kSplit ? s.cmask2 : s.cmask), 0);
-    r_prop = mapa_u32(smem_u32(s.prop), 0);
-    rD = mapa_u32(smem_u32(s.mbar + 2), 1);
+    r_scr = mapa_u32(smem_u32(s.scr), other);
+    r_rec = mapa_u32(smem_u32(s.rec), other);
+    r_prop = mapa_u32(smem_u32(s.prop), other);
+    r_X = mapa_u32(smem_u32(s.mbar + 3), 1);
     r_ctl = mapa_u32(smem_u32(s.ctl), 1);
+    r_tok = mapa_u32(smem_u32(s.ctl + 4), other);
   }
-  // results of one evaluated move -> CTA 0 (b = move of the batch, pp = batch parity)
+  // results of one evaluated move (b = move of the batch, pp = batch parity)
   auto put_sq = [&](int pp, int b, int half, double q, int e = 0) {   // per-ECI quotient, (lane, e) = ECI e * 32 + lane
     const int idx = pp * (BT * 2 * LW) + b * 2 * LW + half * LW + e * 32 + lane;
-    if (remote) st_async_f64(r_sq + (uint32_t)idx * 8u, q, rE); else s0.sq[idx] = q;
+    if (remote) st_async_f64(r_sq + (uint32_t)idx * 8u, q, pp ? r_S1 : r_S0);
+    else if (kAsync) s.sq[idx] = q;
+    else s0.sq[idx] = q;
   };
-  auto put_de = [&](int b, double de) {                            // lane 0
-    if (remote) st_async_f64(r_dE + (uint32_t)b * 8u, de, rE);
-    else (kSplit && crank ? s0.dEb : s0.dEa)[b] = de;
+  auto put_de = [&](int b, double de) {                            // lane 0 (one deciding warp only)
+    (kSplit && crank ? s0.dEb : s0.dEa)[b] = de;
   };
-  auto put_cm = [&](int b, uint32_t m) {                           // lane 0
-    if (remote) st_async_b32(r_cm + (uint32_t)b * 4u, m, rE);
-    else (kSplit && crank ? s0.cmask2 : s0.cmask)[b] = (int32_t)m;
+  auto put_cm = [&](int b, uint32_t m) {                           // lane 0 (one deciding warp only)
+    (kSplit && crank ? s0.cmask2 : s0.cmask)[b] = (int32_t)m;
   };
-  auto put_prop = [&](int pp, int b, int4 p0, int4 p1) {           // lane 0; site split: CTA 0 writes its own
-    if (kSplit && crank) return;
+  auto put_prop = [&](int pp, int b, int4 p0, int4 p1) {           // lane 0
     const int idx = pp * (BT * 8) + b * 8;
-    if (remote) { st_async_v4b32(r_prop + (uint32_t)idx * 4u, p0, rE); st_async_v4b32(r_prop + (uint32_t)idx * 4u + 16u, p1, rE); }
-    else { *reinterpret_cast<int4 *>(s0.prop + idx) = p0; *reinterpret_cast<int4 *>(s0.prop + idx + 4) = p1; }
+    if (kAsync) {                                                  // own copy; the other CTA's unless it derives the proposal itself
+      *reinterpret_cast<int4 *>(s.prop + idx) = p0; *reinterpret_cast<int4 *>(s.prop + idx + 4) = p1;
+      if (!kSplit) {
+        const uint32_t rS = pp ? r_S1 : r_S0;
+        st_async_v4b32(r_prop + (uint32_t)idx * 4u, p0, rS); st_async_v4b32(r_prop + (uint32_t)idx * 4u + 16u, p1, rS);
+      }
+      return;
+    }
+    if (kSplit && crank) return;                                   // site split: CTA 0 writes its own
+    *reinterpret_cast<int4 *>(s0.prop + idx) = p0; *reinterpret_cast<int4 *>(s0.prop + idx + 4) = p1;
+  };
+  // every-warp-decides flavours: the screen record of move b (lane 0)
+  auto put_scr = [&](int pp, int b, uint32_t m, int verdict, double dE) {
+    if (kSplit) {                                                  // partial record of this CTA's changed site
+      const int idx = (pp * 2 + crank) * BT + b;
+      const int4 v = make_int4((int)m, 0, __double2loint(dE), __double2hiint(dE));
+      s.rec[idx] = v;
+      st_async_v4b32(r_rec + (uint32_t)idx * 16u, v, pp ? r_S1 : r_S0);
+    } else {
+      const int idx = pp * BT + b;
+      s.scr[idx] = make_int2((int)m, verdict);
+      if (kAsync) st_async_v2b32(r_scr + (uint32_t)idx * 8u, m, (uint32_t)verdict, pp ? r_S1 : r_S0);
+    }
   };
 
   // ---- stage: the TMA engine copies the read-only tables -- and the replica's occupations /
@@ -299,7 +345,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   const bool list_tma = kStateSmem && kCanon && tma_aligned(g_list, (size_t)N * 4);
   if (tid == 0) {
     mbar_init(s.mbar, 1);
-    if (kAsync) { mbar_init(s.mbar + 1, B + 1); mbar_init(s.mbar + 2, 1); }   // E: CTA 0's warps; D: CTA 1's poster
+    if (kAsync) { mbar_init(s.mbar + 1, B + 1); mbar_init(s.mbar + 2, B + 1); mbar_init(s.mbar + 3, 1); }   // every warp of the CTA; the mailbox poster
   }
   __syncthreads();
   if (tid == 0) {
@@ -577,7 +623,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           }
         }
       }
-      if (accmask) { cf_reg[e] = c; s.pub[e * 32 + lane] = c; }
+      if (accmask) cf_reg[e] = c;
+      if (kAll) s.pub[(pp ^ 1) * (LW + 2) + e * 32 + lane] = c;      // read by the decisions of the batch after pp
+      else if (accmask) s.pub[e * 32 + lane] = c;
     }
     __syncwarp();
     CEMC_OTICK(16);
@@ -610,8 +658,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     if (accmask) {
       const int last = 31 - __clz(accmask);
       e_cur = __shfl_sync(0xffffffffu, E_l, last);
-      if (lane == 0) s.pub[LW] = e_cur;
+      if (!kAll && lane == 0) s.pub[LW] = e_cur;
     }
+    if (kAll && lane == 0) s.pub[(pp ^ 1) * (LW + 2) + LW] = e_cur;
     if (lane < nd) s.obE[lane] = E_after;
     if (tracing && lane < nd && base + lane < a.tr_capacity) {
       const int4 pa = *reinterpret_cast<const int4 *>(s.prop + pp * (BT * 8) + lane * 8);
@@ -634,29 +683,29 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     }
     if (!observe) return;
     if (ref_is_one) {            // Averager reference value 1: value / ref is the value itself
-      int b = 0;
-      for (; b + 3 < nd; b += 4) {
-        double Eb[4], cb[4];
+      // groups of GO moves: loads and squares of the whole group up front (entries >= nd are
+      // in bounds and ignored), then six interleaved DADD chains, the only serial part
+      constexpr int GO = (BT % 5 == 0) ? 5 : (BT % 7 == 0) ? 7 : 3;
+      aE0 = __dadd_rn(aE0, (double)nd);          // a count: nd additions of 1.0 give the same (exact) bits
+#pragma unroll 1
+      for (int b0 = 0; b0 < nd; b0 += GO) {
+        double Eb[GO], cb[GO], e2[GO], c2[GO], ce[GO];
 #pragma unroll
-        for (int x = 0; x < 4; x++) { Eb[x] = s.obE[b + x]; cb[x] = s.Ch[(b + x) * LW + lane]; }
+        for (int x = 0; x < GO; x++) { Eb[x] = s.obE[b0 + x]; cb[x] = s.Ch[(b0 + x) * LW + lane]; }
 #pragma unroll
-        for (int x = 0; x < 4; x++) {
-          aE0 = __dadd_rn(aE0, 1.0);
-          aE1 = __dadd_rn(aE1, Eb[x]);
-          aE2 = __dadd_rn(aE2, __dmul_rn(Eb[x], Eb[x]));
-          aS0 = __dadd_rn(aS0, cb[x]);
-          aS1 = __dadd_rn(aS1, __dmul_rn(cb[x], cb[x]));
-          aS2 = __dadd_rn(aS2, __dmul_rn(cb[x], Eb[x]));
+        for (int x = 0; x < GO; x++) {
+          e2[x] = __dmul_rn(Eb[x], Eb[x]); c2[x] = __dmul_rn(cb[x], cb[x]); ce[x] = __dmul_rn(cb[x], Eb[x]);
         }
-      }
-      for (; b < nd; b++) {
-        const double Eb = s.obE[b], cb = s.Ch[b * LW + lane];
-        aE0 = __dadd_rn(aE0, 1.0);
-        aE1 = __dadd_rn(aE1, Eb);
-        aE2 = __dadd_rn(aE2, __dmul_rn(Eb, Eb));
-        aS0 = __dadd_rn(aS0, cb);
-        aS1 = __dadd_rn(aS1, __dmul_rn(cb, cb));
-        aS2 = __dadd_rn(aS2, __dmul_rn(cb, Eb));
+#pragma unroll
+        for (int x = 0; x < GO; x++) {
+          if (b0 + x < nd) {
+            aE1 = __dadd_rn(aE1, Eb[x]);
+            aE2 = __dadd_rn(aE2, e2[x]);
+            aS0 = __dadd_rn(aS0, cb[x]);
+            aS1 = __dadd_rn(aS1, c2[x]);
+            aS2 = __dadd_rn(aS2, ce[x]);
+          }
+        }
       }
     } else {
       for (int b = 0; b < nd; b++) {
@@ -677,19 +726,29 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   if (is_obs) { produce32(0); produce32(32); produce32(64); }
   if (is_obs && crank == 0) {
 #pragma unroll
-    for (int e = 0; e < E; e++) s.pub[e * 32 + lane] = cf_reg[e];
-    if (lane == 0) s.pub[LW] = e_cur;
+    for (int e = 0; e < E; e++) { s.pub[e * 32 + lane] = cf_reg[e]; s.pub[(LW + 2) + e * 32 + lane] = cf_reg[e]; }
+    if (lane == 0) { s.pub[LW] = e_cur; s.pub[(LW + 2) + LW] = e_cur; }
   }
   fill_end = 96;
   csync();
 
   long long sdone = 0;                 // moves decided so far
+  int kb = 0;                          // batches done (par = kb & 1; phase of this parity's mbarrier = (kb >> 1) & 1)
+#ifdef CEMC_WARP_TIMING
+  long long wtW = 0, wtB = 0, wtD = 0;  // per warp: work before the barrier, barrier wait, decision (scripts/warp_timing.py)
+#endif
 
   while (sdone < a.n_steps) {
     int nb = (int)((a.n_steps - sdone) < BT ? (a.n_steps - sdone) : BT);
-    if (to_ob < nb) nb = to_ob;
-    if (remote && tid == 0) mbar_expect_tx(s.mbar + 2, 8u);          // this batch's decision record
+    {
+      int tb = to_ob;
+      if (kAll && is_obs && crank == 0 && (mflags & 4)) { tb -= bk_nd; if (tb <= 0) tb += (int)a.obs_interval; }   // its copy lags one batch
+      if (tb < nb) nb = tb;
+    }
     CEMC_TICK(0);
+#ifdef CEMC_WARP_TIMING
+    const long long wt0 = clock64();
+#endif
 
 #ifdef CEMC_PHASE_TIMING
     const long long tob0 = clock64();
@@ -728,32 +787,53 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     auto conflict_mask = [&](int b, const int (&gsx)[2], int sk0, int sk1, const int (&gsy)[2]) -> uint32_t {
       uint32_t m = 0;
       if (b <= KP) {
-        for (int k = 0; k < b; k++) {
-          const int a0 = __shfl_sync(0xffffffffu, sk0, k);
-          bool hit = (gsx[0] == a0);
-          if (NJE == 2) hit |= (gsx[1] == a0);
-          if (kWide) { hit |= (gsy[0] == a0); if (NJE == 2) hit |= (gsy[1] == a0); }
-          if (kCanon) {
-            const int a1 = __shfl_sync(0xffffffffu, sk1, k);
-            hit |= (gsx[0] == a1);
-            if (NJE == 2) hit |= (gsx[1] == a1);
-            if (kWide) { hit |= (gsy[0] == a1); if (NJE == 2) hit |= (gsy[1] == a1); }
+        // eight earlier moves at a time, their shuffles / votes independent of each other (lanes
+        // >= b of sk0 / sk1 hold -2, which matches no site: no bound check inside a group)
+        for (int k0 = 0; k0 < b; k0 += 8) {
+#pragma unroll
+          for (int x = 0; x < 8; x++) {
+            const int k = (k0 + x) & 31;
+            const int a0 = __shfl_sync(0xffffffffu, sk0, k);
+            bool hit = (gsx[0] == a0);
+            if (NJE == 2) hit |= (gsx[1] == a0);
+            if (kWide) { hit |= (gsy[0] == a0); if (NJE == 2) hit |= (gsy[1] == a0); }
+            if (kCanon) {
+              const int a1 = __shfl_sync(0xffffffffu, sk1, k);
+              hit |= (gsx[0] == a1);
+              if (NJE == 2) hit |= (gsx[1] == a1);
+              if (kWide) { hit |= (gsy[0] == a1); if (NJE == 2) hit |= (gsy[1] == a1); }
+            }
+            if (__any_sync(0xffffffffu, hit)) m |= 1u << k;
           }
-          if (__any_sync(0xffffffffu, hit)) m |= 1u << k;
         }
       } else {
+        // eight gathered sites at a time (lanes past the last column hold -1, which is no site)
         bool hit = false;
 #pragma unroll
         for (int j = 0; j < NJE; j++)
-          for (int q = 0; q < KP; q++) {
-            const int g = __shfl_sync(0xffffffffu, (kWide && q >= 32) ? gsy[j] : gsx[j], q & 31);
-            hit |= (g == sk0) | (kCanon & (g == sk1));
+          for (int q0 = 0; q0 < KP; q0 += 8) {
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+              const int q = q0 + x;
+              const int g = __shfl_sync(0xffffffffu, (kWide && q >= 32) ? gsy[j] : gsx[j], q & 31);
+              hit |= (g == sk0) | (kCanon & (g == sk1));
+            }
           }
         m = __ballot_sync(0xffffffffu, hit) & (b >= 32 ? 0xffffffffu : ((1u << b) - 1u));
       }
       return m;
     };
 
+    // every warp decides: the evaluating warp screens its own move (the expression of the deciding warp below,
+    // on the same operands): 1 = accept, 2 = inconclusive, 0 = reject
+    auto screen = [&](int b, double dE) -> int {
+      const uint4 rec1 = s.ring[(int)((sdone + b) & 127) * 2 + 1];
+      const double L = __hiloint2double((int)rec1.w, (int)rec1.z);
+      const double band = a.screen_slack * (4e-7 * (kT + fabs(L)) + 1e-9 * fabs(dE)) + etol;
+      const bool acc = dE < L - band;
+      const bool bdr = !acc && !(dE > L + band);
+      return (acc ? 1 : 0) | (bdr ? 2 : 0);
+    };
     if constexpr (kSpin) {
       // ---- spin evaluation (cemc_spin_kernel.cuh), the M moves of this warp side by side
       // (independent instruction streams: the warp has few siblings on its scheduler, so
@@ -847,9 +927,14 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
           for (int mi = 0; mi < M; mi++) de[mi] += __shfl_xor_sync(0xffffffffu, de[mi], o);
+        int verdict[M];
 #pragma unroll
-        for (int mi = 0; mi < M; mi++)
-          if (lane == 0) put_de(warp + mi * BW, de[mi] * dN);
+        for (int mi = 0; mi < M; mi++) {
+          de[mi] *= dN;
+          verdict[mi] = 0;
+          if (kAll) { if (!kSplit) verdict[mi] = screen(warp + mi * BW, de[mi]); }
+          else if (lane == 0) put_de(warp + mi * BW, de[mi]);
+        }
         CEMC_TICK(12);
         int sk0, sk1;
         changed_sites(warp + (M - 1) * BW, sk0, sk1);
@@ -857,7 +942,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int mi = 0; mi < M; mi++) {
           const int b = warp + mi * BW;
           const uint32_t m = conflict_mask(b, gs[mi], sk0, sk1, gs2[mi]);
-          if (lane == 0) put_cm(b, m);
+          if (lane == 0) { if (kAll) put_scr(par, b, m, verdict[mi], de[mi]); else put_cm(b, m); }
         }
         CEMC_TICK(13);
       }
@@ -867,6 +952,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       const int b = warp + mi * BW;             // warp w evaluates moves w, w + BW, ...
       if (is_obs || (b >= nb && !kAsync)) break;   // async protocol: fixed byte count per batch, evaluate anyway
       int gsx[2] = {-1, -1};      // this lane's gathered sites (conflict check): columns 0..31 (and the site itself)
+      int verdict = 0;
+      double dEs = 0.0;           // screen value N sum_i eci_i dcf_i of this warp's changed site(s)
       int gsy[2] = {-1, -1};      // kWide: columns 32..K-1 and the site itself
       const uint4 rec0 = s.ring[(int)((sdone + b) & 127) * 2];
       int site0, site1 = -1, new0, new1 = 0, old0, old1 = 0, slot0 = -1, slot1 = -1;
@@ -1088,7 +1175,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
-          if (lane == 0) put_de(b, de * dN);
+          dEs = de * dN;
+          if (kAll) { if (!kSplit) verdict = screen(b, dEs); }
+          else if (lane == 0) put_de(b, dEs);
         }
       } else {
       // P1: gather
@@ -1222,7 +1311,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
-        if (lane == 0) put_de(b, de * dN);
+        dEs = de * dN;
+        if (kAll) { if (!kSplit) verdict = screen(b, dEs); }
+        else if (lane == 0) put_de(b, dEs);
       }
       }
       CEMC_TICK(12);
@@ -1230,27 +1321,37 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         int sk0, sk1;
         changed_sites(b, sk0, sk1);
         const uint32_t m = conflict_mask(b, gsx, sk0, sk1, gsy);
-        if (lane == 0) put_cm(b, m);
+        if (lane == 0) { if (kAll) put_scr(par, b, m, verdict, dEs); else put_cm(b, m); }
       }
       CEMC_TICK(13);
       if (M > 1) __syncwarp();                  // the warp's scratch is reused by its next move
     }
     }
+#ifdef CEMC_WARP_TIMING
+    const long long wt1 = clock64();
+#endif
     if (kAsync) {
-      // CTA 0: every warp arrives on E (the deciding warp also posts CTA 1's byte count) and
-      // only the deciding warp waits; CTA 1 has sent its results and goes on to wait for D
+      // every warp arrives on this batch's mbarrier of its CTA (warp 0 also posts the byte count the
+      // other CTA sends) and waits for the phase: local records written, remote records landed
       __syncwarp();
-      if (crank == 0) {
-        if (lane == 0) { if (is_decider) mbar_expect_tx(s.mbar + 1, (uint32_t)B * kTxPerMove); else mbar_arrive(s.mbar + 1); }
-        if (is_decider) mbar_wait(s.mbar + 1, phE);
-        phE ^= 1u;
+      uint64_t *S = s.mbar + 1 + par;
+      if (lane == 0) {
+        // observer warps: the token says this warp is done with the buffers of the previous batch
+        // (its payload depends on what the warp read from them)
+        if (is_obs) st_async_v2b32(r_tok, (uint32_t)bk_nd, (uint32_t)__double2loint(e_cur), par ? r_S1 : r_S0);
+        if (lwarp == 0) mbar_expect_tx(S, (uint32_t)B * (kTxRec + (crank == 0 ? kTxSq : 0u)) + 8u);
+        else mbar_arrive(S);
       }
+      mbar_wait(S, (uint32_t)(kb >> 1) & 1u);
     } else csync();
 #ifdef CEMC_PHASE_TIMING
     if (*reinterpret_cast<volatile int32_t *>(s.ctl + 7) == 0x7fffffff) tlast = 0;   // wait for the barrier release
     if (is_obs && crank == 0 && lane == 0) { tph[14] += (unsigned long long)(tob1 - tob0); tph[15] += (unsigned long long)(clock64() - tob1); }
 #endif
     CEMC_TICK(1);
+#ifdef CEMC_WARP_TIMING
+    const long long wt2 = clock64();
+#endif
 
     // ---- D: warp 0 decides the moves strictly in order ---------------------------------
     // The Metropolis outcome of a move depends on the chain state only through
@@ -1261,27 +1362,59 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     // dot, observer sums) of the decided moves follows, lane-parallel over moves
     // where the reference's operation order allows.  A move whose screen is
     // inconclusive (|dE - L| inside the band) is decided with the exact expression.
-    if (is_decider) {
-      const uint4 rec1 = s.ring[(int)((sdone + (lane < nb ? lane : 0)) & 127) * 2 + 1];
-      const double u_l = __hiloint2double((int)rec1.y, (int)rec1.x);
-      const double L_l = __hiloint2double((int)rec1.w, (int)rec1.z);
-      const double dE_l = kSplit ? s.dEa[lane < nb ? lane : 0] + s.dEb[lane < nb ? lane : 0] : s.dEa[lane < nb ? lane : 0];
-      const double band = a.screen_slack * (4e-7 * (kT + fabs(L_l)) + 1e-9 * fabs(dE_l)) + etol;
-      const bool t_acc = lane < nb && (dE_l < L_l - band);
-      const bool t_bdr = lane < nb && !t_acc && !(dE_l > L_l + band);
+    int2 ct_red = make_int2(0, 0);       // every warp decides: this warp's copy of the decision record
+    if (kAll || is_decider) {
+      bool t_acc, t_bdr;
+      uint32_t cm_l;
+      double u_l = 0.0;
+      if (kAll && !kSplit) {
+        const int2 sc = lane < nb ? s.scr[par * BT + lane] : make_int2(0, 0);
+        t_acc = (sc.y & 1) != 0; t_bdr = (sc.y & 2) != 0;
+        cm_l = (uint32_t)sc.x;
+      } else if (kAll) {                   // site split: the two CTAs' partial records of every move
+        const int l0 = lane < nb ? lane : 0;
+        const int4 ra = s.rec[(par * 2) * BT + l0], rb = s.rec[(par * 2 + 1) * BT + l0];
+        const uint4 rec1 = s.ring[(int)((sdone + l0) & 127) * 2 + 1];
+        const double L_l = __hiloint2double((int)rec1.w, (int)rec1.z);
+        const double dE_l = __hiloint2double(ra.w, ra.z) + __hiloint2double(rb.w, rb.z);
+        const double band = a.screen_slack * (4e-7 * (kT + fabs(L_l)) + 1e-9 * fabs(dE_l)) + etol;
+        t_acc = lane < nb && (dE_l < L_l - band);
+        t_bdr = lane < nb && !t_acc && !(dE_l > L_l + band);
+        cm_l = lane < nb ? (uint32_t)(ra.x | rb.x) : 0u;
+      } else {
+        const uint4 rec1 = s.ring[(int)((sdone + (lane < nb ? lane : 0)) & 127) * 2 + 1];
+        u_l = __hiloint2double((int)rec1.y, (int)rec1.x);
+        const double L_l = __hiloint2double((int)rec1.w, (int)rec1.z);
+        const double dE_l = kSplit ? s.dEa[lane < nb ? lane : 0] + s.dEb[lane < nb ? lane : 0] : s.dEa[lane < nb ? lane : 0];
+        const double band = a.screen_slack * (4e-7 * (kT + fabs(L_l)) + 1e-9 * fabs(dE_l)) + etol;
+        t_acc = lane < nb && (dE_l < L_l - band);
+        t_bdr = lane < nb && !t_acc && !(dE_l > L_l + band);
+        cm_l = lane < nb ? (uint32_t)(kSplit ? (s.cmask[lane] | s.cmask2[lane]) : s.cmask[lane]) : 0u;
+      }
       const uint32_t tmask = __ballot_sync(0xffffffffu, t_acc);
       const uint32_t bmask = __ballot_sync(0xffffffffu, t_bdr);
-      const uint32_t cm_l = lane < nb ? (uint32_t)(kSplit ? (s.cmask[lane] | s.cmask2[lane]) : s.cmask[lane]) : 0u;
       uint32_t tm = tmask;
-      if (bmask & 1u) {
+      if ((bmask & 1u) && kAsync && crank == 1) {
+        // move 0 is inconclusive: CTA 0 settles it (it has the published CF vector) and mails the
+        // outcome; bmask is the same in both CTAs, so both take this path in the same batches
+        if (tid == 0) mbar_expect_tx(s.mbar + 3, 8u);
+        mbar_wait(s.mbar + 3, phX);
+        phX ^= 1u;
+        if (*reinterpret_cast<volatile int32_t *>(s.ctl)) tm |= 1u; else tm &= ~1u;
+      } else if (bmask & 1u) {
         // move 0 is inconclusive: exact path (rare) -- ordered dot (named_array.cpp:27-31)
         // and the reference expression (montecarlo.py:951-956) on the current state, which
         // the bookkeeper published after the previous batch
-        const double e_old = s.pub[LW];
+        const double *pubr = s.pub + (kAll ? par * (LW + 2) : 0);
+        if (kAll) {
+          const uint4 rec1 = s.ring[(int)(sdone & 127) * 2 + 1];
+          u_l = __hiloint2double((int)rec1.y, (int)rec1.x);
+        }
+        const double e_old = pubr[LW];
         double p[E];
 #pragma unroll
         for (int e = 0; e < E; e++) {
-          double cn = s.pub[e * 32 + lane];
+          double cn = pubr[e * 32 + lane];
           if (f_any[e]) {
             cn = __dadd_rn(cn, s.sq[par * (BT * 2 * LW) + e * 32 + lane]);
             if (kCanon) cn = __dadd_rn(cn, s.sq[par * (BT * 2 * LW) + LW + e * 32 + lane]);
@@ -1294,7 +1427,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           for (int i = 0; i < 32 && e * 32 + i < n_eci4; i++) e_new = __dadd_rn(e_new, __shfl_sync(0xffffffffu, p[e], i));
         e_new = __dmul_rn(e_new, dN);
         const double ub = __shfl_sync(0xffffffffu, u_l, 0);
-        if (metropolis(e_new, e_old, ub, kT, rkT)) tm |= 1u; else tm &= ~1u;
+        const bool acc0 = metropolis(e_new, e_old, ub, kT, rkT);
+        if (acc0) tm |= 1u; else tm &= ~1u;
+        if (kAsync && is_decider && lane == 0) st_async_v2b32(r_ctl, acc0 ? 1u : 0u, 0u, r_X);
       }
       // In-order semantics without a loop: all moves before the first invalid one are
       // decided by their screen bit, so move b is invalid iff one of the moves it
@@ -1305,7 +1440,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       const uint32_t stops = __ballot_sync(0xffffffffu, stop_here);
       const int ndone = stops ? (__ffs(stops) - 1) : nb;
       const uint32_t accmask = tm & (ndone >= 32 ? 0xffffffffu : ((1u << ndone) - 1u));
-      n_acc += __popc(accmask);
+      if (is_decider) n_acc += __popc(accmask);
       const bool my_acc = lane < ndone && ((accmask >> lane) & 1u);
       // commits of the decided moves: lane b applies move b (accepted moves of one
       // batch never share a site, so the order among them is irrelevant)
@@ -1313,88 +1448,64 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         if (my_acc) {
           const int4 pa = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8);
           const int4 pb = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8 + 4);
+          if (kAsync) {                         // this CTA's copy (every warp, identical values)
+            s.occ[pa.x] = (int8_t)pa.z;
+            if (kCanon) {                      // swap_move_index_tracker.py:39-59
+              s.occ[pa.y] = (int8_t)pa.w;
+              if (pb.z >= 0) { s.list[pb.z] = pa.y; s.list[pb.w] = pa.x; }           // replay: no list slots
+            }
+          } else {
 #pragma unroll
-          for (int q = 0; q < ((kStateSmem && !kAsync) ? C : 1); q++) {       // every CTA's copy of the state (async: CTA 1 commits its own)
+          for (int q = 0; q < (kStateSmem ? C : 1); q++) {       // every CTA's copy of the state
             occ_of[q][pa.x] = (int8_t)pa.z;
             if (kCanon) {                      // swap_move_index_tracker.py:39-59
               occ_of[q][pa.y] = (int8_t)pa.w;
               if (pb.z >= 0) { list_of[q][pb.z] = pa.y; list_of[q][pb.w] = pa.x; }   // replay: no list slots
             }
           }
-          if (kCanon && pb.z >= 0) { g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z); }
+          }
+          if (kCanon && pb.z >= 0 && is_decider) { g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z); }
         }
       }
       if (!kStateSmem) { if (C > 1) __threadfence(); else __threadfence_block(); }
-      if (kAsync) {
-        if (lane == 0) {
-          *reinterpret_cast<int2 *>(s.ctl) = make_int2(ndone, (int)accmask);
-          st_async_v2b32(r_ctl, (uint32_t)ndone, accmask, rD);      // completes CTA 1's mbarrier D
-        }
+      if (kAll) {
+        __syncwarp();                    // this warp's lanes see each other's commits
+        ct_red = make_int2(ndone, (int)accmask);
       } else if (lane < C) {
         int32_t *cp = ctl_of[0];
 #pragma unroll
         for (int q = 1; q < C; q++) if (lane == q) cp = ctl_of[q];
         *reinterpret_cast<int2 *>(cp) = make_int2(ndone, (int)accmask);
       }
-      CEMC_TICK(3);
+      if (is_decider) CEMC_TICK(3);
 #ifdef CEMC_PHASE_TIMING
       if (tid == 0) { tph[8] += 1; tph[9] += ndone; tph[10] += __popc(accmask); tph[11] += (stops ? 1 : 0); }
 #endif
     }
-    int2 ct_early = make_int2(0, 0);
-    if (kAsync) {
-      if (crank == 1) {
-        mbar_wait(s.mbar + 2, phD);                 // the decision record has landed in s.ctl
-        phD ^= 1u;
-        // every warp of CTA 1 (also the observer warp, which sends nothing to CTA 0) takes its copy
-        // BEFORE the block barrier: the next decision can only be sent after all evaluation warps
-        // passed that barrier, so it can never overwrite a record somebody still has to read
-        ct_early = *reinterpret_cast<const int2 *>(s.ctl);
-        if (lwarp == 0) {
-          // CTA 1 applies the accepted moves to its own copy of the state, re-deriving each
-          // move from its own proposal ring (accepted moves of a batch touch disjoint sites)
-          const int2 ct = *reinterpret_cast<const int2 *>(s.ctl);
-          if (lane < ct.x && ((ct.y >> lane) & 1)) {
-            const uint4 rk = s.ring[(int)((sdone + lane) & 127) * 2];
-            if (replay) {
-              s.occ[rk.x] = (int8_t)rk.z;
-              if (kCanon) s.occ[rk.y] = (int8_t)rk.w;
-            } else if (!kCanon) {
-              const int site = t.active ? t.active[rk.x] : (int)rk.x;
-              const int old = s.occ[site];
-              int nw;
-              if (t.allowed_identity) { nw = (int)__umulhi(rk.y, (uint32_t)(S - 1)); nw += (nw >= old); }
-              else {
-                const int p = t.allowed_pos[old];
-                int rr;
-                if (p >= 0) { rr = (int)__umulhi(rk.y, (uint32_t)(n_allowed - 1)); rr += (rr >= p); }
-                else rr = (int)__umulhi(rk.y, (uint32_t)n_allowed);
-                nw = t.allowed[rr];
-              }
-              s.occ[site] = (int8_t)nw;
-            } else {                                  // swap_move_index_tracker.py:39-59
-              const int sl0 = (int)rk.x, sl1 = (int)rk.y;
-              const int st0 = s.list[sl0], st1 = s.list[sl1];
-              s.occ[st0] = (int8_t)rk.z; s.occ[st1] = (int8_t)rk.w;
-              s.list[sl0] = st1; s.list[sl1] = st0;
-            }
-          }
-        }
-      }
-      __syncthreads();
-    } else csync();
+    if (!kAll) csync();
 #ifdef CEMC_PHASE_TIMING
     if (*reinterpret_cast<volatile int32_t *>(s.ctl + 7) == 0x7fffffff) tlast = 0;
 #endif
     {   // rewritten only after the next barrier: no second barrier needed
-      const int2 ct = (kAsync && crank == 1) ? ct_early : *reinterpret_cast<const int2 *>(s.ctl);
+      const int2 ct = kAll ? ct_red : *reinterpret_cast<const int2 *>(s.ctl);
       bk_nd = ct.x; bk_am = (uint32_t)ct.y; bk_base = sdone;
       sdone += ct.x;
-      if ((mflags & 4) && !is_obs) { to_ob -= ct.x; if (to_ob <= 0) to_ob += (int)a.obs_interval; }
+      if ((mflags & 4) && !(is_obs && crank == 0)) { to_ob -= ct.x; if (to_ob <= 0) to_ob += (int)a.obs_interval; }   // (the bookkeeper's copy lags, see bookkeep)
       par ^= 1;
+      kb++;
     }
     CEMC_TICK(4);
+#ifdef CEMC_WARP_TIMING
+    { const long long wt3 = clock64(); wtW += wt1 - wt0; wtB += wt2 - wt1; wtD += wt3 - wt2; }
+#endif
   }
+#ifdef CEMC_WARP_TIMING
+  if (lane == 0 && crank == 0 && lwarp < 8 && a.phase) {
+    a.phase[(size_t)r * 24 + lwarp * 3] = (unsigned long long)wtW;
+    a.phase[(size_t)r * 24 + lwarp * 3 + 1] = (unsigned long long)wtB;
+    a.phase[(size_t)r * 24 + lwarp * 3 + 2] = (unsigned long long)wtD;
+  }
+#endif
   if (is_obs && crank == 0 && bk_nd > 0) bookkeep(bk_nd, bk_am, bk_base, par ^ 1);
 
 #ifdef CEMC_PHASE_TIMING
