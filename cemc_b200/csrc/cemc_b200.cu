@@ -1572,14 +1572,25 @@ static int launch_variant_raw(cemc_handle *h, const RunArgs &a, int v);
 
 template <int MODE>
 static int launch_variant(cemc_handle *h, const RunArgs &a, int v) {
+  // the kernels count the moves of one launch in 32 bits
+  const long long kMaxLaunch = 1ll << 30;
   if (a.obs_interval <= 0) {
-    const int rc = launch_variant_raw<MODE>(h, a, v);
-    if (rc == 0) h->last_variant = v;
-    return rc;
+    if (a.n_steps > kMaxLaunch && (a.rp_sites || a.tr_acc || a.tr_e || a.tr_sites || a.tr_news || a.tr_u))
+      return fail("traced / replayed runs are limited to 2^30 moves per call");
+    long long done = 0;
+    while (done < a.n_steps) {
+      RunArgs part = a;
+      part.n_steps = std::min<long long>(a.n_steps - done, kMaxLaunch);
+      const int rc = launch_variant_raw<MODE>(h, part, v);
+      if (rc) return rc;
+      h->last_variant = v;
+      done += part.n_steps;
+    }
+    return 0;
   }
   // device observers: a launch must not cross more boundaries than the snapshot ring holds; after
   // every launch the (tiny) fold kernel turns the snapshots into the observers' sums, in order
-  const long long cap = (long long)h->obs_ring * a.obs_interval;
+  const long long cap = std::min<long long>((long long)h->obs_ring * a.obs_interval, kMaxLaunch);
   long long done = 0;
   while (done < a.n_steps) {
     RunArgs part = a;

@@ -86,12 +86,16 @@ struct BatchSmem {
   int32_t *cmask;           // [B] bit k: move b reads a site that move k changes
   int32_t *cmask2;          // site split: the same for the second changed site (written by CTA 1)
   int2 *scr;                // [2][BT] {conflict mask, screen verdict (1 accept, 2 inconclusive)} of every move of the batch
+  uint32_t *bmap;           // [B][ceil(N / 32)] per evaluation warp: the sites its move gathers (conflict masks), 0 words for large cells
   int4 *rec;                // [2][2][BT] site split: {conflict mask, -, dE} of changed site 0 / 1 (summed by the deciding warps)
   int32_t *ctl;             // control words
   int32_t *list;
   int8_t *occ;
   uint64_t *mbar;           // [0] TMA staging copies; async cluster protocol: [1], [2] results of a batch complete (even / odd batches), [3] exact decision arrived (CTA 1)
 };
+
+// words of one evaluation warp's site bitmap (conflict masks); 0 = cell too large, shuffle / vote scan instead
+__host__ __device__ inline int bmap_words(int N) { return N <= 16384 ? (N + 31) / 32 : 0; }
 
 // B = moves evaluated by this CTA, BT = moves per batch over the whole cluster
 // E = ECIs per lane (ECI i lives in lane i % 32, slot i / 32): rows of per-ECI data are 32 E wide
@@ -141,6 +145,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(cmask2, int32_t, BT);
   CEMC_TAKE(scr, int2, 2 * BT);
   CEMC_TAKE(rec, int4, 2 * 2 * BT);
+  CEMC_TAKE(bmap, uint32_t, B * bmap_words(t.N));
   o = align_up(o, 8);
   CEMC_TAKE(ctl, int32_t, 8);
   CEMC_TAKE(mbar, uint64_t, 4);
@@ -220,6 +225,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   auto csync = [&]() { if (C > 1) cg::this_cluster().sync(); else __syncthreads(); };
   const int N = t.N, K = t.K, KP = t.KP, S = t.S, D = t.D, VS = t.VS, n_eci = t.n_eci;
   const int RB = D * KP;
+  const int bmw = bmap_words(N);
   const int max_slots = t.max_slots, max_tasks = t.max_tasks;
   const int n_items = t.item_base[1] - t.item_base[0];
   const int n_tasks = t.task_base[1] - t.task_base[0];
@@ -268,7 +274,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #ifdef CEMC_SYNC_CLUSTER   // debugging aid: barrier.cluster everywhere (compute-sanitizer's racecheck does not
   constexpr bool kAsync = false;   // model mbarrier transaction counts / st.async as synchronisation)
 #else
-  constexpr bool kAsync = (C == 2) && kStateSmem;
+  constexpr bool kAsync = (C == 2);
 #endif
   const bool remote = kAsync && crank == 1;
   // One CTA per chain: ONE barrier per batch.  Every evaluation warp screens its own move and
@@ -363,6 +369,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     if (b_list) tma_bulk_g2s(s.list, g_list, b_list, s.mbar);
   }
   for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
+  for (int i = tid; i < B * bmw; i += nthr) s.bmap[i] = 0u;
   if (!kTab)
     for (int i = tid; i < B * NJ * VS; i += nthr) s.V[i] = 1.0;      // V[K] is the constant 1.0
   if (kStateSmem) {
@@ -434,7 +441,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   }
   int bk_nd = 0, par = 0;              // bookkeeper: decided moves of the previous batch; batch parity
   uint32_t bk_am = 0u;
-  long long bk_base = 0;
+  int bk_base = 0;
   double e_cur = st.e_cur[r];
   const double kT = st.kT[r];
   const double rkT = __ddiv_rn(1.0, kT);
@@ -530,7 +537,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 
   // ---- proposal ring: 128 records, produced 32 at a time by the observer warp of every
   // CTA while the evaluation warps work (montecarlo.py:890-908, sgc_montecarlo.py:62-76)
-  auto produce32 = [&](long long first) {
+  auto produce32 = [&](int first) {
     const unsigned long long stp = step0 + (unsigned long long)first + lane;
     uint32_t c0 = (uint32_t)stp, c1 = (uint32_t)(stp >> 32), c2 = rep_global, c3 = 0;
     philox4x32_10(c0, c1, c2, c3, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
@@ -586,7 +593,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // (:236-242, one lane per move), trace records, Averager / SGCObserver sums
   // (montecarlo.py:811-814, mc_observers.py:264-270).  The deciding warp only needs the CF
   // vector and the energy for an inconclusive screen; they are published in s.pub.
-  auto bookkeep = [&](int nd, uint32_t accmask, long long base, int pp) {
+  auto bookkeep = [&](int nd, uint32_t accmask, int base, int pp) {
 #ifdef CEMC_PHASE_TIMING
     long long tb0 = clock64();
 #define CEMC_OTICK(slot) do { const long long n_ = clock64(); if (lane == 0) tph[slot] += (unsigned long long)(n_ - tb0); tb0 = n_; } while (0)
@@ -722,7 +729,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     CEMC_OTICK(18);
   };
 
-  long long fill_end = 0;              // records of steps [sdone, fill_end) are in the ring
+  int fill_end = 0;                    // records of steps [sdone, fill_end) are in the ring
   if (is_obs) { produce32(0); produce32(32); produce32(64); }
   if (is_obs && crank == 0) {
 #pragma unroll
@@ -732,14 +739,16 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   fill_end = 96;
   csync();
 
-  long long sdone = 0;                 // moves decided so far
+  // 32-bit step counters inside a launch (the host splits runs into launches of at most 2^30 moves)
+  const int n_steps = (int)a.n_steps;
+  int sdone = 0;                       // moves decided so far
   int kb = 0;                          // batches done (par = kb & 1; phase of this parity's mbarrier = (kb >> 1) & 1)
 #ifdef CEMC_WARP_TIMING
   long long wtW = 0, wtB = 0, wtD = 0;  // per warp: work before the barrier, barrier wait, decision (scripts/warp_timing.py)
 #endif
 
-  while (sdone < a.n_steps) {
-    int nb = (int)((a.n_steps - sdone) < BT ? (a.n_steps - sdone) : BT);
+  while (sdone < n_steps) {
+    int nb = (n_steps - sdone) < BT ? (n_steps - sdone) : BT;
     {
       int tb = to_ob;
       if (kAll && is_obs && crank == 0 && (mflags & 4)) { tb -= bk_nd; if (tb <= 0) tb += (int)a.obs_interval; }   // its copy lags one batch
@@ -786,6 +795,31 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     // / vote sequences (MATCH.ANY over 32 distinct values costs ~400 cycles on sm_100).
     auto conflict_mask = [&](int b, const int (&gsx)[2], int sk0, int sk1, const int (&gsy)[2]) -> uint32_t {
       uint32_t m = 0;
+      if (b == 0) return 0u;
+      if (bmw > 0) {
+        // site bitmap of this warp: the gathering lanes set the bits of their sites, lane k tests
+        // the site(s) move k changes, one ballot, the gathering lanes clear their words again
+        uint32_t *bm = s.bmap + lwarp * bmw;
+#pragma unroll
+        for (int j = 0; j < NJE; j++) {
+          if (gsx[j] >= 0) atomicOr(bm + (gsx[j] >> 5), 1u << (gsx[j] & 31));
+          if (kWide && gsy[j] >= 0) atomicOr(bm + (gsy[j] >> 5), 1u << (gsy[j] & 31));
+        }
+        __syncwarp();
+        bool hit = false;
+        if (lane < b) {
+          hit = ((bm[sk0 >> 5] >> (sk0 & 31)) & 1u) != 0u;
+          if (kCanon) hit |= ((bm[sk1 >> 5] >> (sk1 & 31)) & 1u) != 0u;
+        }
+        m = __ballot_sync(0xffffffffu, hit);
+#pragma unroll
+        for (int j = 0; j < NJE; j++) {
+          if (gsx[j] >= 0) bm[gsx[j] >> 5] = 0u;
+          if (kWide && gsy[j] >= 0) bm[gsy[j] >> 5] = 0u;
+        }
+        __syncwarp();
+        return m;
+      }
       if (b <= KP) {
         // eight earlier moves at a time, their shuffles / votes independent of each other (lanes
         // >= b of sk0 / sk1 hold -2, which matches no site: no bound check inside a group)
@@ -1467,7 +1501,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           if (kCanon && pb.z >= 0 && is_decider) { g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z); }
         }
       }
-      if (!kStateSmem) { if (C > 1) __threadfence(); else __threadfence_block(); }
+      // global-memory state: one deciding warp -> its commits must be visible to the whole cluster; every warp
+      // decides -> a warp only ever reads what its own lanes wrote (the __syncwarp below orders them)
+      if (!kStateSmem) { if (C > 1 && !kAsync) __threadfence(); else __threadfence_block(); }
       if (kAll) {
         __syncwarp();                    // this warp's lanes see each other's commits
         ct_red = make_int2(ndone, (int)accmask);
