@@ -954,7 +954,7 @@ int cemc_create(const cemc_tables *tb, int n_replicas, int replica_offset, int d
   // ---- per-replica state ---------------------------------------------------
   const size_t R = (size_t)n_replicas;
   ReplicaState &st = h->st;
-  if ((rc = dalloc(h, &st.occ, R * N))) return rc;
+  if ((rc = dalloc(h, &st.occ, R * N + 32))) return rc;       // + padding: the kernels' TMA staging reads whole 16-byte blocks
   if ((rc = dalloc(h, &st.cf, R * n_eci))) return rc;
   if ((rc = dalloc(h, &st.eci, R * n_eci))) return rc;
   if ((rc = dalloc(h, &st.e_cur, R))) return rc;

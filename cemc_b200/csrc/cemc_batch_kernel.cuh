@@ -151,7 +151,7 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(mbar, uint64_t, 4);
   if (state_in_smem) {
     if (canonical) CEMC_TAKE16(list, int32_t, t.N);
-    CEMC_TAKE16(occ, int8_t, t.N);
+    CEMC_TAKE16(occ, int8_t, t.N + 32);      // + the misalignment of the replica's row in global memory (TMA staging)
   }
 #undef CEMC_TAKE16
 #undef CEMC_TAKE
@@ -235,7 +235,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   int32_t *g_loc = st.loc + (size_t)r * N;
   BatchSmem s;
   batch_smem_layout<B, BT, E>(&s, smem_raw, t, kCanon, kStateSmem, kTab ? &tb : nullptr, kTab32, kSpin ? sp.wq : 0);
-  if (!kStateSmem) { s.occ = g_occ; s.list = g_list; }
+  // (the shared-memory occupations start at the row's offset inside its first 16-byte block: TMA staging below)
+  const uint32_t occ_mis = kStateSmem ? (uint32_t)(reinterpret_cast<uintptr_t>(g_occ) & 15u) : 0u;
+  if (!kStateSmem) { s.occ = g_occ; s.list = g_list; } else s.occ += occ_mis;
   // CTA 0's copies of the arrays the deciding warp reads (DSMEM when C > 1)
   BatchSmem s0 = s;
   int8_t *occ_of[C];
@@ -343,11 +345,12 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     }
   };
 
-  // ---- stage: the TMA engine copies the read-only tables -- and the replica's occupations /
-  // site lists when their global addresses are 16-byte aligned -- into shared memory
-  // (cp.async.bulk -> mbarrier transaction bytes); the threads only fill what has no
-  // global image (V) or is misaligned
-  const bool occ_tma = kStateSmem && tma_aligned(g_occ, (size_t)N);
+  // ---- stage: the TMA engine copies the read-only tables and the replica's occupations / site
+  // lists into shared memory (cp.async.bulk -> mbarrier transaction bytes); the threads only
+  // fill what has no global image (V).  A replica's occupation row starts anywhere (N bytes per
+  // replica): the copy covers the 16-byte blocks around it and the shared-memory array starts at
+  // the same offset inside its first block (the occupation buffer is padded by 16 bytes).
+  const bool occ_tma = kStateSmem;
   const bool list_tma = kStateSmem && kCanon && tma_aligned(g_list, (size_t)N * 4);
   if (tid == 0) {
     mbar_init(s.mbar, 1);
@@ -359,13 +362,13 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     const uint32_t b_ttask = kTab ? (uint32_t)t.n_tasks_total * 16u : 0u;
     const uint32_t b_items = kTab ? 0u : (uint32_t)t.n_items_total * 16u;
     const uint32_t b_tsum = kTab ? 0u : (uint32_t)align_up((size_t)t.n_tasks_total * 8, 16);
-    const uint32_t b_occ = occ_tma ? (uint32_t)N : 0u, b_list = list_tma ? (uint32_t)N * 4u : 0u;
+    const uint32_t b_occ = occ_tma ? (uint32_t)align_up((size_t)N + occ_mis, 16) : 0u, b_list = list_tma ? (uint32_t)N * 4u : 0u;
     mbar_expect_tx(s.mbar, b_tab + b_ttask + b_items + b_tsum + b_occ + b_list);
     if (b_tab) tma_bulk_g2s(s.tab, kTab32 ? (const void *)tb.tab32 : (const void *)tb.tab, b_tab, s.mbar);
     if (b_ttask) tma_bulk_g2s(s.ttask, tb.task, b_ttask, s.mbar);
     if (b_items) tma_bulk_g2s(s.items, t.items4, b_items, s.mbar);
     if (b_tsum) tma_bulk_g2s(s.task_sum, t.task_sum, b_tsum, s.mbar);
-    if (b_occ) tma_bulk_g2s(s.occ, g_occ, b_occ, s.mbar);
+    if (b_occ) tma_bulk_g2s(s.occ - occ_mis, g_occ - occ_mis, b_occ, s.mbar);
     if (b_list) tma_bulk_g2s(s.list, g_list, b_list, s.mbar);
   }
   for (int i = tid; i < D * S; i += nthr) s.bf[i] = t.bf[i];
@@ -1107,14 +1110,14 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
             TR spO[NJE], spN[NJE];
 #pragma unroll
             for (int j = 0; j < NJE; j++) { spO[j] = (TR)0; spN[j] = (TR)0; }
+            uint4 w[NJE][2];                            // code words of the group being summed / the next one
+#pragma unroll
+            for (int j = 0; j < NJE; j++) {
+              w[j][0] = *reinterpret_cast<const uint4 *>(cp + j * n_sub);
+              w[j][1] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + 4);
+            }
 #pragma unroll 1
             for (int m = 0; m < tt.z; m += 8) {         // M is padded to a multiple of 8 with zero entries
-              uint4 w[NJE][2];
-#pragma unroll
-              for (int j = 0; j < NJE; j++) {
-                w[j][0] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m);
-                w[j][1] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m + 4);
-              }
               TR vo[NJE][8], vn[NJE][8];
 #pragma unroll
               for (int j = 0; j < NJE; j++)
@@ -1125,6 +1128,13 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                   vo[j][4 * h + 2] = TV(w[j][h].z & 0xffffu); vn[j][4 * h + 2] = TV(w[j][h].z >> 16);
                   vo[j][4 * h + 3] = TV(w[j][h].w & 0xffffu); vn[j][4 * h + 3] = TV(w[j][h].w >> 16);
                 }
+              if (m + 8 < tt.z) {                       // the next group's code words, while this group's sums run
+#pragma unroll
+                for (int j = 0; j < NJE; j++) {
+                  w[j][0] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m + 8);
+                  w[j][1] = *reinterpret_cast<const uint4 *>(cp + j * n_sub + m + 12);
+                }
+              }
 #pragma unroll
               for (int x = 0; x < 8; x++)
 #pragma unroll
@@ -1190,9 +1200,21 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
               for (int je = 0; je < NJE; je++)
                 num[je] = __dsub_rn(s.bf[f_d[e] * S + news[jb + je]], s.bf[f_d[e] * S + olds[jb + je]]);
             } else if (f_kind[e] == 2) {
-              for (int q = 0; q < f_nd[e]; q++) {             // :397
+              // sum over the decorations in the stored order (:397), four loads in flight at a time
+              for (int q0 = 0; q0 < f_nd[e]; q0 += 4) {
+                double v[NJE][4];
 #pragma unroll
-                for (int je = 0; je < NJE; je++) num[je] = __dadd_rn(num[je], db[je * max_tasks + f_t0[e] + q]);
+                for (int x = 0; x < 4; x++) {
+                  const int q = (q0 + x < f_nd[e]) ? q0 + x : q0;          // (clamped: a valid address)
+#pragma unroll
+                  for (int je = 0; je < NJE; je++) v[je][x] = db[je * max_tasks + f_t0[e] + q];
+                }
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+                  if (q0 + x < f_nd[e]) {
+#pragma unroll
+                    for (int je = 0; je < NJE; je++) num[je] = __dadd_rn(num[je], v[je][x]);
+                  }
               }
 #pragma unroll
               for (int je = 0; je < NJE; je++) num[je] = __dmul_rn(num[je], f_scale[e]);   // :400
