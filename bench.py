@@ -401,7 +401,8 @@ def gpu_arm(args):
                 "parallelism": "replicas sharded over %d GPU(s), no data-path collective (the pt block "
                                "is the workload with one)" % world,
                 "kernel_variant": "%d (0 spin, 1-4 batch (16,2)/(16,1)/(8,1)/(4,1), 5 one move at a "
-                                  "time, 8 batch (16,2) site split; autotuned unless --variant)" % variant,
+                                  "time, 6 batch (8,1) two moves per warp, 8/9 batch (16,2)/(8,2) site split; "
+                                  "autotuned unless --variant)" % variant,
             },
             "roofline": roof,
             "roofline_issue": issue,

@@ -1618,7 +1618,8 @@ static int launch_variant_raw(cemc_handle *h, const RunArgs &a, int v) {
     case 2: return launch_batch<MODE>(h, a, 16, 1);
     case 3: return launch_batch<MODE>(h, a, 8, 1);
     case 4: return launch_batch<MODE>(h, a, 4, 1);
-    case 6: case 7: return -1;      // retired (two moves per evaluation warp: never the fastest)
+    case 6: return launch_batch<MODE>(h, a, 8, 1, 2);      // (8,1) with two moves per evaluation warp (spin evaluation)
+    case 7: return -1;              // retired ((16,1) with two moves per warp: never the fastest)
     case 8: return (MODE == MODE_CANONICAL && (2 * h->R <= h->n_sms || h->cluster == 2))
                        ? launch_batch<MODE>(h, a, 16, 2, 1, 1) : -1;
     case 9: return (MODE == MODE_CANONICAL && (2 * h->R <= h->n_sms || h->cluster == 2))

@@ -61,6 +61,7 @@ static int batch_launch_b(const BatchLaunch &L) {
   if (!in_smem) sm = batch_smem_layout<B, B * C * M>(nullptr, nullptr, L.t, MODE == MODE_CANONICAL, false, tb, f32, wq);
   if (sm > (size_t)L.max_smem_optin) return -1;
   if constexpr (M > 1) {            // two moves per warp: shared-memory state only
+    if (in_smem && !L.extras) return batch_launch_kc<MODE, kTree, B, true, C, EV, M, false, false, 1, false>(L, sm);
     return in_smem ? batch_launch_kc<MODE, kTree, B, true, C, EV, M>(L, sm) : -1;
   } else {
     if (in_smem && !L.extras && B >= 7) return batch_launch_kc<MODE, kTree, B, true, C, EV, M, false, false, 1, false>(L, sm);
@@ -133,7 +134,16 @@ static int batch_launch_bc(const BatchLaunch &L) {
   }
   // L.B counts the warps of a CTA: B - 1 evaluation warps (moves per batch) + the observer
   // warp; power-of-two CTAs get the full register budget (512 threads x 128 registers)
-  if (L.M != 1) return -1;      // two moves per evaluation warp: measured slower on every workload (round 1), retired
+  if (L.M == 2) {
+    // two moves per evaluation warp, their instruction streams interleaved (14-move batches at 8 warps; spin
+    // evaluation only).  Slower than one move per warp in round 1; since every warp decides and the conflict
+    // masks cost the same for any batch length it wins on config 2 (173 -> 157 ns/move; M = 3: 190, M = 4: 238)
+    if constexpr (EV == EV_SPIN) {
+      if (L.B == 8 && L.C == 1) return batch_launch_b<MODE, kTree, 7, 1, EV, 2>(L);
+    }
+    return -1;
+  }
+  if (L.M != 1) return -1;
   if (L.B == 16 && L.C == 2) return batch_launch_b<MODE, kTree, 15, 2, EV>(L);
   if (L.B == 16 && L.C == 1) return batch_launch_b<MODE, kTree, 15, 1, EV>(L);
   if (L.B == 8 && L.C == 1) return batch_launch_b<MODE, kTree, 7, 1, EV>(L);

@@ -43,8 +43,9 @@ def assert_state_equal(gpu, chains):
 
 # kernel variants the recorded trajectories are put through: 0 spin kernel (warp per replica),
 # 1 / 2 / 3 / 4 batch kernel (16 warps, cluster of 2) / (16,1) / (8,1) / (4,1), 5 generic
-# one-move-at-a-time kernel, 8 / 9 batch kernel (16,2) / (8,2) with site split (swaps)
-REPLAY_VARIANTS = [0, 1, 2, 3, 4, 5, 8, 9]
+# one-move-at-a-time kernel, 6 batch kernel (8,1) with two moves per evaluation warp (binary +-1
+# basis), 8 / 9 batch kernel (16,2) / (8,2) with site split (swaps)
+REPLAY_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 8, 9]
 
 
 def _pin_replay_variant(gpu, variant, mode):
@@ -54,6 +55,8 @@ def _pin_replay_variant(gpu, variant, mode):
         pytest.skip("several symmetry groups: this build runs them on the generic kernel")
     if variant == 0 and (ev != 1 or gpu.tables.n_symm > 1):
         pytest.skip("spin kernel: binary +-1 basis only")
+    if variant == 6 and (ev != 1 or gpu.tables.K > 31):
+        pytest.skip("two moves per warp: spin evaluation, K <= 31 only")
     if variant in (8, 9) and mode != "canonical":
         pytest.skip("site split: swaps only")
     gpu.set_variant(variant, variant)
@@ -697,6 +700,35 @@ def test_batch_kernel_spin_evaluation(cuda_device, batch, cluster, mode):
         accs = gpu.get_accumulators()
         for r, c in enumerate(chains):
             assert np.array_equal(accs[r], c.acc)
+
+
+@pytest.mark.parametrize("mode", ["sgc", "canonical"])
+def test_two_moves_per_warp(cuda_device, mode):
+    """Kernel variant 6: (8,1) batch kernel with TWO moves per evaluation warp (14-move batches,
+    the two spin evaluations interleaved).  Oracle trajectory, trace, state and observer sums,
+    also on the 27-site cell (batches collide constantly) and with forced exact decisions."""
+    cases = [(BINARY, 3), (dict(BINARY, L=3), 2),
+             (dict(BINARY, L=5, families=["nn", "2nn", "tri"]), 2)]
+    for case, R in cases:
+        st, eci, symbols, ft = build(**case)
+        kTs = np.linspace(0.02, 0.2, R)
+        for slack in (1.0, 1e30):
+            gpu, chains = make_pair(ft, [symbols] * R, kTs, seed=91)
+            gpu.set_variant(6, 6)
+            gpu.set_screen_slack(slack)
+            n = 1500 if slack == 1.0 else 300
+            gpu.set_trace(n)
+            gpu.reset_accumulators()
+            (gpu.run_sgc if mode == "sgc" else gpu.run_canonical)(n)
+            assert gpu.last_variant() == 6
+            tr = gpu.get_trace(n)
+            for r, c in enumerate(chains):
+                o = c.run_sgc(n, trace=True) if mode == "sgc" else c.run_canonical(n, trace=True)
+                assert np.array_equal(tr[0][r], o[0]) and np.array_equal(tr[3][r], o[3])
+                assert np.array_equal(tr[4][r], o[4])
+            assert_state_equal(gpu, chains)
+            assert np.array_equal(gpu.get_accumulators(), np.stack([c.acc for c in chains]))
+            gpu.close()
 
 
 @pytest.mark.parametrize("order", ["reference", "tree"])
