@@ -1,3 +1,3 @@
-timeout 900 compute-sanitizer --tool racecheck --print-limit 60 python scripts/sanitize_target.py 2 3 4 6 > gpurun_out/r02_san_racecheck_c1.log 2>&1
-tail -2 gpurun_out/r02_san_racecheck_c1.log
-grep -o "in cemc_[a-z_]*.cuh:[0-9]*" gpurun_out/r02_san_racecheck_c1.log | sort | uniq -c | sort -rn | head
+python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench.err
+python bench.py > gpurun_out/r02_bench.json 2>> gpurun_out/r02_bench.err
+tail -c 400 gpurun_out/r02_bench.json; tail -n 3 gpurun_out/r02_bench.err
