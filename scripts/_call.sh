@@ -1,3 +1,2 @@
-python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench.err
-python bench.py > gpurun_out/r02_bench.json 2>> gpurun_out/r02_bench.err
-tail -c 400 gpurun_out/r02_bench.json; tail -n 3 gpurun_out/r02_bench.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err
+tail -c 300 gpurun_out/r02_bench_n2.json; tail -n 3 gpurun_out/r02_bench_n2.err
