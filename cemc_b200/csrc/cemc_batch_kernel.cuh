@@ -7,14 +7,18 @@
 //
 //   * B warps of a CTA evaluate the CF increments of the next B trial moves
 //     concurrently, one WARP per move, all against the current state (phases
-//     P0-P2b of cemc_kernels.cuh plus the per-ECI quotients; warp-level syncs only);
-//   * warp 0 then decides the moves IN ORDER (per-ECI normalisation, ordered
-//     energy dot product, Metropolis test, commit).  A move whose inputs were
-//     touched by an earlier accepted move of the same batch -- one of its
-//     gathered sites (or, for swaps, one of its list slots) changed -- is not
-//     decided: the batch ends there and the next batch re-evaluates it from the
-//     committed state.  The Philox stream is keyed by the step index, so the
-//     restart changes nothing.
+//     P0-P2b of cemc_kernels.cuh plus the per-ECI quotients; warp-level syncs only), screen
+//     their move's Metropolis test and note which earlier moves of the batch would invalidate
+//     the evaluation (conflict mask from a per-warp site bitmap);
+//   * after ONE barrier EVERY warp decides the moves IN ORDER from those records (three
+//     ballots, no loop) and applies the accepted changes itself -- all warps store identical
+//     values to identical addresses, so nobody waits for a deciding warp.  A move whose
+//     inputs were touched by an earlier accepted move of the same batch -- one of its
+//     gathered sites (or, for swaps, one of its list slots) changed -- is not decided: the
+//     batch ends there and the next batch re-evaluates it from the committed state.  The
+//     Philox stream is keyed by the step index, so the restart changes nothing;
+//   * the observer warp does the exact bookkeeping of a decided batch (CF vector, ordered
+//     energy dot products, observer sums) while the evaluation warps work on the next one.
 //
 // EV_TAB32 (opt-in fp32 variant, cemc_set_precision): the tables and the sums over the
 // sub-clusters are single precision (half the shared-memory traffic, FADD instead of DADD
@@ -23,13 +27,13 @@
 //
 // Results are bit-identical to the one-move-at-a-time kernels (tested): the
 // arithmetic of each phase is the same code path, operation for operation.
+//
 // CTA clusters (template parameter C = 2): the two CTAs of a thread-block cluster work on ONE
 // chain: twice the evaluation throughput for one chain, the exact sequential Markov chain is
-// kept.  Each CTA evaluates B moves of the batch (2 B <= 32 moves per batch), CTA 0's warp 0
-// decides.  With the state in shared memory the CTAs talk through an async DSMEM protocol
-// (st.async + mbarrier transaction bytes, see kAsync below) and each commits its own copy of
-// the occupations; with the state in global memory (supercells that do not fit) the results
-// are written straight into CTA 0's shared memory and barrier.cluster replaces __syncthreads.
+// kept.  Each CTA evaluates B moves of the batch (2 B <= 32 moves per batch) and BOTH decide:
+// the CTAs exchange their records over an async DSMEM protocol (st.async + mbarrier
+// transaction bytes, see kAsync below) and each commits its own copy of the occupations (or,
+// for supercells that do not fit, the same global-memory copy).
 //
 // Template parameters of batch_kernel:
 //   MODE        MODE_SGC (one-site flips) | MODE_CANONICAL (swaps: two changed sites per move)
@@ -39,12 +43,15 @@
 //   kStateSmem  occupations and site lists in shared memory (else global memory)
 //   C           CTAs per chain (1 | 2)
 //   EV          EV_PRODUCT | EV_SPIN | EV_TAB | EV_TAB32: how one move is evaluated
-//   M           moves per evaluation warp and batch (1 | 2)
+//   M           moves per evaluation warp and batch (1 | 2; 2 = interleaved spin evaluations, variant 6)
 //   kSplit      site split (swaps, C = 2): both CTAs evaluate the same moves, one changed site each
-//   kWide       spin evaluation with 32..63 translation columns (two per lane)
+//   kWide       spin / table evaluation with 32..63 translation columns (two per lane)
+//   E           ECIs per lane (1 | 2: up to 64 ECIs)
+//   kX          replay / lattice arithmetic / observer boundaries compiled in
 //
-// Used when the CF vector fits one warp (<= 32 ECIs), one symmetry group and K <= 31
-// translation columns (<= 63 for the spin evaluation); everything else runs mc_kernel.
+// Used when the CF vector fits one warp (<= 32 E ECIs) and K <= 31 translation columns (<= 63
+// for the spin and table evaluations); several symmetry groups: table evaluation only;
+// everything else runs mc_kernel.
 #pragma once
 #include <cooperative_groups.h>
 #include <type_traits>
@@ -76,19 +83,17 @@ struct TabTables {
 enum BatchEval : int { EV_PRODUCT = 0, EV_SPIN = 1, EV_TAB = 2, EV_TAB32 = 3 };
 
 struct BatchSmem {
-  double *V, *PO, *PN, *diff, *sq, *bf, *dEa, *dEb, *Pm, *Ch, *obE, *tab, *pub, *qtab;
+  double *V, *PO, *PN, *diff, *sq, *bf, *Pm, *Ch, *obE, *tab, *pub, *qtab;
   uint4 *items;
   int2 *task_sum;
   int4 *ttask;
   uint32_t *codes;          // [B][NJ][n_sub] old code*8 | new code*8 << 16
   uint4 *ring;              // [32][2]: proposal; uniform + Metropolis threshold
   int32_t *prop;            // [B][8] decoded proposal
-  int32_t *cmask;           // [B] bit k: move b reads a site that move k changes
-  int32_t *cmask2;          // site split: the same for the second changed site (written by CTA 1)
-  int2 *scr;                // [2][BT] {conflict mask, screen verdict (1 accept, 2 inconclusive)} of every move of the batch
+  int2 *scr;                // [2][BT] {conflict mask (bit k: move b reads a site move k changes), screen verdict (1 accept, 2 inconclusive)}
   uint32_t *bmap;           // [B][ceil(N / 32)] per evaluation warp: the sites its move gathers (conflict masks), 0 words for large cells
   int4 *rec;                // [2][2][BT] site split: {conflict mask, -, dE} of changed site 0 / 1 (summed by the deciding warps)
-  int32_t *ctl;             // control words
+  int32_t *ctl;             // cluster protocol: [0..1] mailbox of the exact decision (CTA 1), [4..5] landing pad of the other CTA's token
   int32_t *list;
   int8_t *occ;
   uint64_t *mbar;           // [0] TMA staging copies; async cluster protocol: [1], [2] results of a batch complete (even / odd batches), [3] exact decision arrived (CTA 1)
@@ -131,8 +136,6 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE(sq, double, 2 * BT * 2 * 32 * E);  // double buffered: the bookkeeper reads batch k during batch k+1
   CEMC_TAKE(pub, double, 2 * (32 * E + 2));   // double buffered (batch parity)
   CEMC_TAKE(qtab, double, spin_wq * 64);      // spin evaluation: quotient table [new species][count][ECI lane]
-  CEMC_TAKE(dEa, double, BT);
-  CEMC_TAKE(dEb, double, BT);
   CEMC_TAKE(Pm, double, BT * (32 * E + 1));
   CEMC_TAKE(Ch, double, BT * 32 * E);
   CEMC_TAKE(obE, double, BT);
@@ -141,8 +144,6 @@ __host__ __device__ inline size_t batch_smem_layout(BatchSmem *s, unsigned char 
   CEMC_TAKE16(task_sum, int2, tb ? 0 : t.n_tasks_total);
   CEMC_TAKE(ring, uint4, 128 * 2);
   CEMC_TAKE(prop, int32_t, 2 * BT * 8);
-  CEMC_TAKE(cmask, int32_t, BT);
-  CEMC_TAKE(cmask2, int32_t, BT);
   CEMC_TAKE(scr, int2, 2 * BT);
   CEMC_TAKE(rec, int4, 2 * 2 * BT);
   CEMC_TAKE(bmap, uint32_t, B * bmap_words(t.N));
@@ -238,29 +239,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // (the shared-memory occupations start at the row's offset inside its first 16-byte block: TMA staging below)
   const uint32_t occ_mis = kStateSmem ? (uint32_t)(reinterpret_cast<uintptr_t>(g_occ) & 15u) : 0u;
   if (!kStateSmem) { s.occ = g_occ; s.list = g_list; } else s.occ += occ_mis;
-  // CTA 0's copies of the arrays the deciding warp reads (DSMEM when C > 1)
-  BatchSmem s0 = s;
-  int8_t *occ_of[C];
-  int32_t *list_of[C], *prop_of[C], *ctl_of[C];
-  if (C > 1) {
-    cg::cluster_group cl = cg::this_cluster();
-    s0.prop = cl.map_shared_rank(s.prop, 0);
-    s0.sq = cl.map_shared_rank(s.sq, 0);
-    s0.dEa = cl.map_shared_rank(s.dEa, 0);
-    s0.cmask = cl.map_shared_rank(s.cmask, 0);
-    s0.dEb = cl.map_shared_rank(s.dEb, 0);
-    s0.cmask2 = cl.map_shared_rank(s.cmask2, 0);
-#pragma unroll
-    for (int q = 0; q < C; q++) {
-      occ_of[q] = kStateSmem ? cl.map_shared_rank(s.occ, q) : g_occ;
-      list_of[q] = (kStateSmem && kCanon) ? cl.map_shared_rank(s.list, q) : g_list;
-      prop_of[q] = cl.map_shared_rank(s.prop, q);
-      ctl_of[q] = cl.map_shared_rank(s.ctl, q);
-    }
-  } else {
-    occ_of[0] = s.occ; list_of[0] = s.list; prop_of[0] = s.prop; ctl_of[0] = s.ctl;
-  }
-  // ---- async cluster protocol (C = 2, state in shared memory).  Both CTAs keep a copy of the
+  // ---- async cluster protocol (C = 2).  Both CTAs keep a copy of the
   // chain's state and BOTH decide: every evaluation warp writes the screen record of its move
   // into its own CTA's shared memory and sends it to the other CTA with st.async (SASS STAS),
   // whose bytes complete the destination's mbarrier; every warp of either CTA waits for (local
@@ -273,11 +252,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // Everything is double buffered by the batch parity -- two mbarriers as well, so that bytes
   // of batch k + 1 can never land in the phase of batch k --, and the observer warps send a
   // token per batch so that no CTA runs more than one batch ahead of ANY warp of the other.
-#ifdef CEMC_SYNC_CLUSTER   // debugging aid: barrier.cluster everywhere (compute-sanitizer's racecheck does not
-  constexpr bool kAsync = false;   // model mbarrier transaction counts / st.async as synchronisation)
-#else
   constexpr bool kAsync = (C == 2);
-#endif
   const bool remote = kAsync && crank == 1;
   // One CTA per chain: ONE barrier per batch.  Every evaluation warp screens its own move and
   // publishes {conflict mask, verdict}; after the barrier EVERY warp derives the same decision
@@ -285,8 +260,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // warps store identical values to identical addresses, and each sees its own stores -- so
   // nobody waits for a deciding warp.  Everything a late warp still reads of batch k while an
   // early one writes batch k + 1 is double buffered by the batch parity.
-  constexpr bool kRed = (C == 1);
-  constexpr bool kAll = kRed || kAsync;          // every warp decides
+  static_assert(C == 1 || C == 2, "one CTA or a cluster of two per chain");
   // bytes one evaluation warp sends to the other CTA per batch: its screen record and its proposal
   // (site split: a 16-byte partial record; both CTAs derive every proposal themselves); CTA 1 also
   // sends the quotients of its changed site(s)
@@ -309,14 +283,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   auto put_sq = [&](int pp, int b, int half, double q, int e = 0) {   // per-ECI quotient, (lane, e) = ECI e * 32 + lane
     const int idx = pp * (BT * 2 * LW) + b * 2 * LW + half * LW + e * 32 + lane;
     if (remote) st_async_f64(r_sq + (uint32_t)idx * 8u, q, pp ? r_S1 : r_S0);
-    else if (kAsync) s.sq[idx] = q;
-    else s0.sq[idx] = q;
-  };
-  auto put_de = [&](int b, double de) {                            // lane 0 (one deciding warp only)
-    (kSplit && crank ? s0.dEb : s0.dEa)[b] = de;
-  };
-  auto put_cm = [&](int b, uint32_t m) {                           // lane 0 (one deciding warp only)
-    (kSplit && crank ? s0.cmask2 : s0.cmask)[b] = (int32_t)m;
+    else s.sq[idx] = q;
   };
   auto put_prop = [&](int pp, int b, int4 p0, int4 p1) {           // lane 0
     const int idx = pp * (BT * 8) + b * 8;
@@ -328,10 +295,9 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       }
       return;
     }
-    if (kSplit && crank) return;                                   // site split: CTA 0 writes its own
-    *reinterpret_cast<int4 *>(s0.prop + idx) = p0; *reinterpret_cast<int4 *>(s0.prop + idx + 4) = p1;
+    *reinterpret_cast<int4 *>(s.prop + idx) = p0; *reinterpret_cast<int4 *>(s.prop + idx + 4) = p1;
   };
-  // every-warp-decides flavours: the screen record of move b (lane 0)
+  // the screen record of move b (lane 0)
   auto put_scr = [&](int pp, int b, uint32_t m, int verdict, double dE) {
     if (kSplit) {                                                  // partial record of this CTA's changed site
       const int idx = (pp * 2 + crank) * BT + b;
@@ -634,8 +600,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         }
       }
       if (accmask) cf_reg[e] = c;
-      if (kAll) s.pub[(pp ^ 1) * (LW + 2) + e * 32 + lane] = c;      // read by the decisions of the batch after pp
-      else if (accmask) s.pub[e * 32 + lane] = c;
+      s.pub[(pp ^ 1) * (LW + 2) + e * 32 + lane] = c;                // read by the decisions of the batch after pp
     }
     __syncwarp();
     CEMC_OTICK(16);
@@ -668,9 +633,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     if (accmask) {
       const int last = 31 - __clz(accmask);
       e_cur = __shfl_sync(0xffffffffu, E_l, last);
-      if (!kAll && lane == 0) s.pub[LW] = e_cur;
     }
-    if (kAll && lane == 0) s.pub[(pp ^ 1) * (LW + 2) + LW] = e_cur;
+    if (lane == 0) s.pub[(pp ^ 1) * (LW + 2) + LW] = e_cur;
     if (lane < nd) s.obE[lane] = E_after;
     if (tracing && lane < nd && base + lane < a.tr_capacity) {
       const int4 pa = *reinterpret_cast<const int4 *>(s.prop + pp * (BT * 8) + lane * 8);
@@ -754,7 +718,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     int nb = (n_steps - sdone) < BT ? (n_steps - sdone) : BT;
     {
       int tb = to_ob;
-      if (kAll && is_obs && crank == 0 && (mflags & 4)) { tb -= bk_nd; if (tb <= 0) tb += (int)a.obs_interval; }   // its copy lags one batch
+      if (is_obs && crank == 0 && (mflags & 4)) { tb -= bk_nd; if (tb <= 0) tb += (int)a.obs_interval; }   // its copy lags one batch
       if (tb < nb) nb = tb;
     }
     CEMC_TICK(0);
@@ -969,8 +933,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int mi = 0; mi < M; mi++) {
           de[mi] *= dN;
           verdict[mi] = 0;
-          if (kAll) { if (!kSplit) verdict[mi] = screen(warp + mi * BW, de[mi]); }
-          else if (lane == 0) put_de(warp + mi * BW, de[mi]);
+          if (!kSplit) verdict[mi] = screen(warp + mi * BW, de[mi]);
         }
         CEMC_TICK(12);
         int sk0, sk1;
@@ -979,7 +942,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int mi = 0; mi < M; mi++) {
           const int b = warp + mi * BW;
           const uint32_t m = conflict_mask(b, gs[mi], sk0, sk1, gs2[mi]);
-          if (lane == 0) { if (kAll) put_scr(par, b, m, verdict[mi], de[mi]); else put_cm(b, m); }
+          if (lane == 0) put_scr(par, b, m, verdict[mi], de[mi]);
         }
         CEMC_TICK(13);
       }
@@ -1232,8 +1195,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
           dEs = de * dN;
-          if (kAll) { if (!kSplit) verdict = screen(b, dEs); }
-          else if (lane == 0) put_de(b, dEs);
+          if (!kSplit) verdict = screen(b, dEs);
         }
       } else {
       // P1: gather
@@ -1368,8 +1330,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
         dEs = de * dN;
-        if (kAll) { if (!kSplit) verdict = screen(b, dEs); }
-        else if (lane == 0) put_de(b, dEs);
+        if (!kSplit) verdict = screen(b, dEs);
       }
       }
       CEMC_TICK(12);
@@ -1377,7 +1338,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         int sk0, sk1;
         changed_sites(b, sk0, sk1);
         const uint32_t m = conflict_mask(b, gsx, sk0, sk1, gsy);
-        if (lane == 0) { if (kAll) put_scr(par, b, m, verdict, dEs); else put_cm(b, m); }
+        if (lane == 0) put_scr(par, b, m, verdict, dEs);
       }
       CEMC_TICK(13);
       if (M > 1) __syncwarp();                  // the warp's scratch is reused by its next move
@@ -1409,25 +1370,31 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     const long long wt2 = clock64();
 #endif
 
-    // ---- D: warp 0 decides the moves strictly in order ---------------------------------
+    // ---- D: EVERY warp decides the moves strictly in order -----------------------------
     // The Metropolis outcome of a move depends on the chain state only through
     // E_new - E_cur = N sum_i eci_i dcf_i (+ rounding), i.e. on the move alone, as long
-    // as none of its inputs was changed by an earlier accepted move.  So: (1) every
-    // lane screens one move against its threshold -kT ln u; (2) a scalar pass applies
-    // the conflict masks in order; (3) the exact bookkeeping (CF vector, ordered energy
-    // dot, observer sums) of the decided moves follows, lane-parallel over moves
-    // where the reference's operation order allows.  A move whose screen is
-    // inconclusive (|dE - L| inside the band) is decided with the exact expression.
-    int2 ct_red = make_int2(0, 0);       // every warp decides: this warp's copy of the decision record
-    if (kAll || is_decider) {
+    // as none of its inputs was changed by an earlier accepted move.  So: (1) the evaluating
+    // warp has screened its move against its threshold -kT ln u; (2) a loop-free pass (lane =
+    // move, three ballots) applies the conflict masks in order; (3) the warp applies the
+    // accepted changes to its CTA's copy of the state.  A move whose screen is inconclusive
+    // (|dE - L| inside the band) is decided with the exact expression.  The exact bookkeeping
+    // (CF vector, ordered energy dot, observer sums) follows in the observer warp of CTA 0.
+    int2 ct_red = make_int2(0, 0);       // this warp's copy of the decision record {moves decided, accept mask}
+    {
       bool t_acc, t_bdr;
       uint32_t cm_l;
       double u_l = 0.0;
-      if (kAll && !kSplit) {
+      // the proposal lane b would commit (loaded up front: its latency overlaps the ballots)
+      int4 pa = make_int4(0, 0, 0, 0), pb = pa;
+      if (lane < nb) {
+        pa = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8);
+        pb = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8 + 4);
+      }
+      if (!kSplit) {
         const int2 sc = lane < nb ? s.scr[par * BT + lane] : make_int2(0, 0);
         t_acc = (sc.y & 1) != 0; t_bdr = (sc.y & 2) != 0;
         cm_l = (uint32_t)sc.x;
-      } else if (kAll) {                   // site split: the two CTAs' partial records of every move
+      } else {                             // site split: the two CTAs' partial records of every move
         const int l0 = lane < nb ? lane : 0;
         const int4 ra = s.rec[(par * 2) * BT + l0], rb = s.rec[(par * 2 + 1) * BT + l0];
         const uint4 rec1 = s.ring[(int)((sdone + l0) & 127) * 2 + 1];
@@ -1437,15 +1404,6 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         t_acc = lane < nb && (dE_l < L_l - band);
         t_bdr = lane < nb && !t_acc && !(dE_l > L_l + band);
         cm_l = lane < nb ? (uint32_t)(ra.x | rb.x) : 0u;
-      } else {
-        const uint4 rec1 = s.ring[(int)((sdone + (lane < nb ? lane : 0)) & 127) * 2 + 1];
-        u_l = __hiloint2double((int)rec1.y, (int)rec1.x);
-        const double L_l = __hiloint2double((int)rec1.w, (int)rec1.z);
-        const double dE_l = kSplit ? s.dEa[lane < nb ? lane : 0] + s.dEb[lane < nb ? lane : 0] : s.dEa[lane < nb ? lane : 0];
-        const double band = a.screen_slack * (4e-7 * (kT + fabs(L_l)) + 1e-9 * fabs(dE_l)) + etol;
-        t_acc = lane < nb && (dE_l < L_l - band);
-        t_bdr = lane < nb && !t_acc && !(dE_l > L_l + band);
-        cm_l = lane < nb ? (uint32_t)(kSplit ? (s.cmask[lane] | s.cmask2[lane]) : s.cmask[lane]) : 0u;
       }
       const uint32_t tmask = __ballot_sync(0xffffffffu, t_acc);
       const uint32_t bmask = __ballot_sync(0xffffffffu, t_bdr);
@@ -1461,8 +1419,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         // move 0 is inconclusive: exact path (rare) -- ordered dot (named_array.cpp:27-31)
         // and the reference expression (montecarlo.py:951-956) on the current state, which
         // the bookkeeper published after the previous batch
-        const double *pubr = s.pub + (kAll ? par * (LW + 2) : 0);
-        if (kAll) {
+        const double *pubr = s.pub + par * (LW + 2);
+        {
           const uint4 rec1 = s.ring[(int)(sdone & 127) * 2 + 1];
           u_l = __hiloint2double((int)rec1.y, (int)rec1.x);
         }
@@ -1502,50 +1460,30 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       // batch never share a site, so the order among them is irrelevant)
       if (lane < ndone) {
         if (my_acc) {
-          const int4 pa = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8);
-          const int4 pb = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8 + 4);
-          if (kAsync) {                         // this CTA's copy (every warp, identical values)
-            s.occ[pa.x] = (int8_t)pa.z;
-            if (kCanon) {                      // swap_move_index_tracker.py:39-59
-              s.occ[pa.y] = (int8_t)pa.w;
-              if (pb.z >= 0) { s.list[pb.z] = pa.y; s.list[pb.w] = pa.x; }           // replay: no list slots
-            }
-          } else {
-#pragma unroll
-          for (int q = 0; q < (kStateSmem ? C : 1); q++) {       // every CTA's copy of the state
-            occ_of[q][pa.x] = (int8_t)pa.z;
-            if (kCanon) {                      // swap_move_index_tracker.py:39-59
-              occ_of[q][pa.y] = (int8_t)pa.w;
-              if (pb.z >= 0) { list_of[q][pb.z] = pa.y; list_of[q][pb.w] = pa.x; }   // replay: no list slots
-            }
-          }
+          // this CTA's copy of the state: every warp stores the same values to the same addresses
+          s.occ[pa.x] = (int8_t)pa.z;
+          if (kCanon) {                        // swap_move_index_tracker.py:39-59
+            s.occ[pa.y] = (int8_t)pa.w;
+            if (pb.z >= 0) { s.list[pb.z] = pa.y; s.list[pb.w] = pa.x; }             // replay: no list slots
           }
           if (kCanon && pb.z >= 0 && is_decider) { g_loc[pa.y] = pb.z - offs_of(offs, pa.w); g_loc[pa.x] = pb.w - offs_of(offs, pa.z); }
         }
       }
-      // global-memory state: one deciding warp -> its commits must be visible to the whole cluster; every warp
-      // decides -> a warp only ever reads what its own lanes wrote (the __syncwarp below orders them)
-      if (!kStateSmem) { if (C > 1 && !kAsync) __threadfence(); else __threadfence_block(); }
-      if (kAll) {
-        __syncwarp();                    // this warp's lanes see each other's commits
-        ct_red = make_int2(ndone, (int)accmask);
-      } else if (lane < C) {
-        int32_t *cp = ctl_of[0];
-#pragma unroll
-        for (int q = 1; q < C; q++) if (lane == q) cp = ctl_of[q];
-        *reinterpret_cast<int2 *>(cp) = make_int2(ndone, (int)accmask);
-      }
+      // global-memory state: a warp only ever reads what its own lanes wrote (every warp commits every
+      // accepted change itself; the __syncwarp below orders the lanes), so a block-level fence will do
+      if (!kStateSmem) __threadfence_block();
+      __syncwarp();                      // this warp's lanes see each other's commits
+      ct_red = make_int2(ndone, (int)accmask);
       if (is_decider) CEMC_TICK(3);
 #ifdef CEMC_PHASE_TIMING
       if (tid == 0) { tph[8] += 1; tph[9] += ndone; tph[10] += __popc(accmask); tph[11] += (stops ? 1 : 0); }
 #endif
     }
-    if (!kAll) csync();
 #ifdef CEMC_PHASE_TIMING
     if (*reinterpret_cast<volatile int32_t *>(s.ctl + 7) == 0x7fffffff) tlast = 0;
 #endif
-    {   // rewritten only after the next barrier: no second barrier needed
-      const int2 ct = kAll ? ct_red : *reinterpret_cast<const int2 *>(s.ctl);
+    {
+      const int2 ct = ct_red;
       bk_nd = ct.x; bk_am = (uint32_t)ct.y; bk_base = sdone;
       sdone += ct.x;
       if ((mflags & 4) && !(is_obs && crank == 0)) { to_ob -= ct.x; if (to_ob <= 0) to_ob += (int)a.obs_interval; }   // (the bookkeeper's copy lags, see bookkeep)

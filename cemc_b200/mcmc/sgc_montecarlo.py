@@ -104,38 +104,37 @@ class SGCMonteCarlo(mc.Montecarlo):
 
     @chemical_potential.setter
     def chemical_potential(self, chem_pot):
-        eci = self.atoms.get_calculator().eci
-        if any([k not in eci.keys() for k in chem_pot.keys()]):
+        calc = self.atoms.get_calculator()
+        untracked = [name for name in chem_pot if name not in calc.eci]
+        if untracked:
             raise InvalidChemicalPotentialError(
                 "A chemical potential that is currently not tracked is added. "
                 "Make sure that all the following keys are in the ECI before "
                 "the ECI are passed to the calculator: {} (if not add them "
                 "with a zero value)".format(list(chem_pot.keys())))
         self._chemical_potential = chem_pot
-        if self.chem_pot_in_ecis:
-            self._reset_eci_to_original(self.atoms.get_calculator().eci)
-        self._include_chemical_potential_in_ecis(chem_pot, self.atoms.get_calculator().eci)
+        self.reset_ecis()                       # take a previous potential out first
+        self._include_chemical_potential_in_ecis(chem_pot, calc.eci)
 
-    def _include_chemical_potential_in_ecis(self, chem_potential, eci):
-        self.chem_pots = []
-        self.chem_pot_names = []
-        keys = sorted(chem_potential.keys())
-        for key in keys:
-            self.chem_pots.append(chem_potential[key])
-            self.chem_pot_names.append(key)
-            eci[key] = eci.get(key, 0.0) - chem_potential[key]
-        self.atoms.get_calculator().update_ecis(eci)
-        self.chem_pot_in_ecis = True
-        self.current_energy = self.atoms.get_calculator().get_energy()
+    def _shift_singlet_ecis(self, eci, sign):
+        """eci[name] += sign * mu[name] for the potentials on record, then push the ECIs to the
+        device and refresh the energy (the SGC energy is E - sum mu_i n_i, sgc_montecarlo.py:239-261)."""
+        for name, mu in zip(self.chem_pot_names, self.chem_pots):
+            eci[name] = eci.get(name, 0.0) + sign * mu
+        calc = self.atoms.get_calculator()
+        calc.update_ecis(eci)
+        self.current_energy = calc.get_energy()
         return eci
 
+    def _include_chemical_potential_in_ecis(self, chem_potential, eci):
+        self.chem_pot_names = sorted(chem_potential)
+        self.chem_pots = [chem_potential[name] for name in self.chem_pot_names]
+        self.chem_pot_in_ecis = True
+        return self._shift_singlet_ecis(eci, -1.0)
+
     def _reset_eci_to_original(self, eci_with_chem_pot):
-        for name, val in zip(self.chem_pot_names, self.chem_pots):
-            eci_with_chem_pot[name] += val
-        self.atoms.get_calculator().update_ecis(eci_with_chem_pot)
         self.chem_pot_in_ecis = False
-        self.current_energy = self.atoms.get_calculator().get_energy()
-        return eci_with_chem_pot
+        return self._shift_singlet_ecis(eci_with_chem_pot, +1.0)
 
     def reset_ecis(self):
         if self.chem_pot_in_ecis:

@@ -133,8 +133,10 @@ int cemc_set_generic_path(cemc_handle *h, int on);
 int cemc_set_batch(cemc_handle *h, int b);
 /* All kernel variants (spin / batch (B,C) / one move at a time) give the same
  * trajectory bit for bit; on long runs the fastest one is measured on segments
- * of the run itself.  cemc_get_variant: 0 spin, 1..4 batch (16,2) (16,1) (8,1)
- * (4,1), 5 mc_kernel, -1 not tuned yet.                                        */
+ * of the run itself.  cemc_get_variant: 0 spin, 1..4 batch (warps, CTAs per chain)
+ * (16,2) (16,1) (8,1) (4,1), 5 mc_kernel, 6 batch (8,1) with two moves per warp
+ * (binary +-1 basis), 8 / 9 batch (16,2) / (8,2) with site split (swaps),
+ * -1 not tuned yet.                                                            */
 int cemc_set_autotune(cemc_handle *h, int on);
 int cemc_get_variant(cemc_handle *h, int *sgc, int *canonical);
 /* variant of the most recent Metropolis launch (run_sgc / run_canonical / replay), -1 = none */

@@ -43,3 +43,30 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0
     assert out.stdout.strip() == ""
+
+
+def test_profiler_figures_only_from_this_build(tmp_path, monkeypatch):
+    """roofline.traffic / roofline_issue come from profiles/traffic.json only when it was captured on
+    this build (kernel source hash); a stale file must yield null with the reason, never canned
+    counters, and the issue-slot roofline must follow from its inputs."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from cemc_b200 import _lib
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    clocks = {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 3}
+    # stale capture
+    (prof / "traffic.json").write_text(json.dumps({"kernel_source_sha": "0" * 16,
+                                                    "C2": {"dram_bytes_per_launch": 1, "warp_instructions_per_move": 300.0}}))
+    roof, issue = bench.rooflines("C2", 258, 5120000, 3.2e-3, 1.6e9, clocks)
+    assert roof["traffic"] is None and issue is None and "another build" in roof["traffic_source"]
+    assert abs(roof["achieved"] - 258 * 5120000 / 3.2e-3 / 1e9) < 1e-9 and roof["frac"] == roof["achieved"] / roof["peak"]
+    # capture of this build
+    (prof / "traffic.json").write_text(json.dumps({"kernel_source_sha": _lib.source_hash(),
+                                                    "C2": {"dram_bytes_per_launch": 453888, "warp_instructions_per_move": 289.2,
+                                                           "issue_slots_busy_pct": 51.0, "source": "x"}}))
+    roof, issue = bench.rooflines("C2", 258, 5120000, 3.2e-3, 1.6e9, clocks)
+    assert roof["traffic"] == 453888
+    assert issue["bound"] == "issue" and issue["peak"] == 148 * 4 * 1965.0e6
+    assert abs(issue["frac"] - 289.2 * 1.6e9 / (148 * 4 * 1965.0e6)) < 1e-12

@@ -890,7 +890,7 @@ def test_fp32_variant(cuda_device, variant):
         gpu.set_precision(32)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 8])
+@pytest.mark.parametrize("variant", [1, 2, 8, 9])
 def test_full_size_cluster_stress(cuda_device, variant):
     """BASELINE config 3 size (fcc 20^3 ternary, 8000 sites), 12 replicas over the whole
     temperature range, 30 000 SGC + 30 000 canonical moves: the CTA-cluster kernels with the
@@ -924,6 +924,43 @@ def test_full_size_cluster_stress(cuda_device, variant):
     for r, c in enumerate(chains):
         assert np.array_equal(accs[r], c.acc)
         assert steps[r] == 2 * n and n_acc[r] == c.n_accepted.value
+
+
+@pytest.mark.parametrize("variant", [3, 6])
+def test_full_size_bench_workload_stress(cuda_device, variant):
+    """BASELINE config 2 (the bench workload: fcc 10^3 Al-Mg, replicas across the whole mu x T grid
+    from its coldest to its hottest corner), 12 replicas x 250 000 SGC moves in two launches through
+    the bench kernels -- the (8,1) batch kernel where every warp decides (variant 3) and its
+    two-moves-per-warp form (6, the tuner's pick): occupations / CFs / energies / observer sums /
+    counters equal the oracle's.  (Some corners of the grid end up single-element, so no swaps here.)"""
+    from cemc_b200 import workloads as wl
+    w = wl.c2_almg_sgc_sweep()
+    R, n, n2 = 12, 200000, 50000
+    pick = np.linspace(0, w.R - 1, R).astype(int)
+    ft = w.tables
+    chains = [OracleChain(ft, w.occ[q], kT=w.kT[q], seed=777, replica=r, eci=w.eci_matrix[q])
+              for r, q in enumerate(pick)]
+    gpu = BatchedCEUpdater(ft, R)
+    gpu.set_occupancy(w.occ[pick])
+    gpu.set_cf(np.stack([c.cf for c in chains]))
+    gpu.set_ecis(w.eci_matrix[pick])
+    gpu.set_kT(w.kT[pick])
+    gpu.seed(777)
+    gpu.set_variant(variant, variant)
+    gpu.reset_accumulators()
+    gpu.run_sgc(n)
+    assert gpu.last_variant() == variant
+    gpu.run_sgc(n2)
+    gpu.synchronize()
+    for c in chains:
+        c.run_sgc(n)
+        c.run_sgc(n2)
+    assert_state_equal(gpu, chains)
+    accs = gpu.get_accumulators()
+    steps, n_acc = gpu.get_counters()
+    for r, c in enumerate(chains):
+        assert np.array_equal(accs[r], c.acc)
+        assert steps[r] == n + n2 and n_acc[r] == c.n_accepted.value
 
 
 def test_replica_order_is_invisible(cuda_device):
