@@ -265,7 +265,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // (site split: a 16-byte partial record; both CTAs derive every proposal themselves); CTA 1 also
   // sends the quotients of its changed site(s)
   constexpr uint32_t kTxRec = kSplit ? 16u : (8u + 32u);
-  constexpr uint32_t kTxSq = kSplit ? 256u : 512u;
+  constexpr uint32_t kTxSq = (kSplit || !kCanon) ? 256u : 512u;        // one 256-byte quotient row per changed site
   uint32_t r_S0 = 0, r_S1 = 0, r_sq = 0, r_scr = 0, r_rec = 0, r_prop = 0, r_X = 0, r_ctl = 0, r_tok = 0, phX = 0;
   if (kAsync) {
     const uint32_t other = (uint32_t)(crank ^ 1);
@@ -295,7 +295,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       }
       return;
     }
-    *reinterpret_cast<int4 *>(s.prop + idx) = p0; *reinterpret_cast<int4 *>(s.prop + idx + 4) = p1;
+    *reinterpret_cast<int4 *>(s.prop + idx) = p0;
+    if (kCanon) *reinterpret_cast<int4 *>(s.prop + idx + 4) = p1;    // old species / list slots: swaps only
   };
   // the screen record of move b (lane 0)
   auto put_scr = [&](int pp, int b, uint32_t m, int verdict, double dE) {
@@ -421,6 +422,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   unsigned long long n_acc = 0;
   const uint32_t rep_global = a.replica_offset + (uint32_t)r * a.replica_stride;
   const int n_eci4 = pin_reg((n_eci + 3) & ~3);
+  const bool few_eci = (E == 1) && n_eci <= 8;
   const int observe = pin_reg(a.observe);
   const bool tracing = (a.tr_acc != nullptr) || (a.tr_e != nullptr);
   const int n_allowed = t.n_allowed;
@@ -457,6 +459,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
     etol = 1e-13 * dN * sa * 16.0 * a.screen_slack;
   }
+  const double c_rel = 1e-9 * a.screen_slack;          // relative part of the screen's band
 
   // kSpin: this lane's sub-clusters (decoded once) and its ECI's ballot masks
   int sca[4], scb[4], scc[4];
@@ -543,14 +546,19 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       rec0 = make_uint4((uint32_t)slot0, (uint32_t)slot1, (uint32_t)sb, (uint32_t)sa);
       u = u53(d0, d1);
     }
-    // Metropolis threshold: u <= exp(-dE/kT)  <=>  dE <= -kT ln u.  Screen only, so a
+    // Metropolis threshold: u <= exp(-dE/kT)  <=>  dE <= -kT ln u =: L.  Screen only, so a
     // single-precision logarithm will do: |error| <= kT (6e-8 + 1.2e-7 |ln u|) is covered
-    // by the band of the screen, inconclusive moves take the exact expression.
+    // by the band of the screen, inconclusive moves take the exact expression.  The record holds
+    // the two thresholds of the screen with the move-independent part of the band folded in,
+    // L -+ (slack 4e-7 (kT + |L|) + etol), rounded outwards to fp32: a move is accepted when
+    // dE + c |dE| < L_lo, rejected when dE - c |dE| > L_hi (c = 1e-9 slack), inconclusive between.
     const double L = -kT * (double)logf((float)u);
+    const double bb = a.screen_slack * (4e-7 * (kT + fabs(L))) + etol;
+    const float L_lo = __double2float_rd(L - bb), L_hi = __double2float_ru(L + bb);
     const int slot = (int)((first + lane) & 127);
     s.ring[slot * 2] = rec0;
     s.ring[slot * 2 + 1] = make_uint4((uint32_t)__double2loint(u), (uint32_t)__double2hiint(u),
-                                      (uint32_t)__double2loint(L), (uint32_t)__double2hiint(L));
+                                      __float_as_uint(L_lo), __float_as_uint(L_hi));
   };
 #ifdef CEMC_PHASE_TIMING
   unsigned long long tph[24] = {0};
@@ -828,11 +836,10 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
     // every warp decides: the evaluating warp screens its own move (the expression of the deciding warp below,
     // on the same operands): 1 = accept, 2 = inconclusive, 0 = reject
     auto screen = [&](int b, double dE) -> int {
-      const uint4 rec1 = s.ring[(int)((sdone + b) & 127) * 2 + 1];
-      const double L = __hiloint2double((int)rec1.w, (int)rec1.z);
-      const double band = a.screen_slack * (4e-7 * (kT + fabs(L)) + 1e-9 * fabs(dE)) + etol;
-      const bool acc = dE < L - band;
-      const bool bdr = !acc && !(dE > L + band);
+      const float2 th = *reinterpret_cast<const float2 *>(&s.ring[(int)((sdone + b) & 127) * 2 + 1].z);
+      const double m = c_rel * fabs(dE);
+      const bool acc = dE + m < (double)th.x;
+      const bool bdr = !acc && !(dE - m > (double)th.y);
       return (acc ? 1 : 0) | (bdr ? 2 : 0);
     };
     if constexpr (kSpin) {
@@ -864,8 +871,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           } else if (!kCanon) {                   // sgc_montecarlo.py:69-75 (all species allowed)
             site[mi][0] = t.active ? t.active[rec0.x] : (int)rec0.x;
             oldv[mi][0] = s.occ[site[mi][0]];
-            int rr = (int)__umulhi(rec0.y, (uint32_t)(S - 1)); rr += (rr >= oldv[mi][0]);
-            newv[mi][0] = rr;
+            newv[mi][0] = 1 - oldv[mi][0];         // two species: "the other one" (sgc_montecarlo.py:70-75 draws nothing else)
           } else {
             slot0 = (int)rec0.x; slot1 = (int)rec0.y; newv[mi][0] = (int)rec0.z; newv[mi][1] = (int)rec0.w;
             site[mi][0] = s.list[slot0]; site[mi][1] = s.list[slot1];
@@ -910,7 +916,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                 }
               }
               qv[mi][je] = s.qtab[(newv[mi][j] * sp.wq + cnt) * 32 + lane];   // n dsigma (M - 2 cnt) / den, :393-402
-              if (newv[mi][j] == oldv[mi][j]) qv[mi][je] = 0.0;   // recorded no-op change (:315): the table assumes old != new
+              if (replay && newv[mi][j] == oldv[mi][j]) qv[mi][je] = 0.0;   // recorded no-op change (:315): the table assumes old != new
             }
           }
         }
@@ -918,16 +924,24 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         for (int mi = 0; mi < M; mi++) {
           const int b = warp + mi * BW;
           // this move's per-ECI quotients [2][32]
-          if (!kSplit) { put_sq(par, b, 0, qv[mi][0]); put_sq(par, b, 1, qv[mi][1]); }
+          if (!kSplit) { put_sq(par, b, 0, qv[mi][0]); if (kCanon) put_sq(par, b, 1, qv[mi][1]); }
           else put_sq(par, b, jb, qv[mi][0]);
         }
         double de[M];
 #pragma unroll
-        for (int mi = 0; mi < M; mi++) de[mi] = f_kind[0] > 0 ? eci_reg[0] * (qv[mi][0] + qv[mi][1]) : 0.0;   // screen only
+        for (int mi = 0; mi < M; mi++)           // screen only
+          de[mi] = f_kind[0] > 0 ? eci_reg[0] * (kCanon ? qv[mi][0] + qv[mi][1] : qv[mi][0]) : 0.0;
+        if (few_eci) {                          // ECIs in lanes 0..7 only: lanes 8.. hold +0.0, three rounds give the same bits
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+          for (int o = 4; o > 0; o >>= 1)
 #pragma unroll
-          for (int mi = 0; mi < M; mi++) de[mi] += __shfl_xor_sync(0xffffffffu, de[mi], o);
+            for (int mi = 0; mi < M; mi++) de[mi] += __shfl_xor_sync(0xffffffffu, de[mi], o);
+        } else {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int mi = 0; mi < M; mi++) de[mi] += __shfl_xor_sync(0xffffffffu, de[mi], o);
+        }
         int verdict[M];
 #pragma unroll
         for (int mi = 0; mi < M; mi++) {
@@ -1149,7 +1163,6 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                 put_sq(par, b, jb + je, qj, e);
                 qsum += qj;
               }
-              if (!kCanon) put_sq(par, b, 1, 0.0, e);
               de += eci_reg[e] * qsum;
             }
           } else
@@ -1189,7 +1202,6 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
               put_sq(par, b, jb + je, qj, e);
               qsum += qj;
             }
-            if (!kCanon) put_sq(par, b, 1, 0.0, e);
             if (f_kind[e] > 0) de += eci_reg[e] * qsum;
           }
 #pragma unroll
@@ -1324,7 +1336,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
           const double qa = exact_div(num0, f_den[e], f_rden[e]);               // :402
           const double qb = kCanon ? exact_div(num1, f_den[e], f_rden[e]) : 0.0;
           put_sq(par, b, 0, qa, e);
-          put_sq(par, b, 1, qb, e);
+          if (kCanon) put_sq(par, b, 1, qb, e);
           if (f_kind[e] > 0) de += eci_reg[e] * (qa + qb);
         }
 #pragma unroll
@@ -1388,7 +1400,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       int4 pa = make_int4(0, 0, 0, 0), pb = pa;
       if (lane < nb) {
         pa = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8);
-        pb = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8 + 4);
+        if (kCanon || kAsync) pb = *reinterpret_cast<const int4 *>(s.prop + par * (BT * 8) + lane * 8 + 4);
       }
       if (!kSplit) {
         const int2 sc = lane < nb ? s.scr[par * BT + lane] : make_int2(0, 0);
@@ -1397,12 +1409,11 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       } else {                             // site split: the two CTAs' partial records of every move
         const int l0 = lane < nb ? lane : 0;
         const int4 ra = s.rec[(par * 2) * BT + l0], rb = s.rec[(par * 2 + 1) * BT + l0];
-        const uint4 rec1 = s.ring[(int)((sdone + l0) & 127) * 2 + 1];
-        const double L_l = __hiloint2double((int)rec1.w, (int)rec1.z);
+        const float2 th = *reinterpret_cast<const float2 *>(&s.ring[(int)((sdone + l0) & 127) * 2 + 1].z);
         const double dE_l = __hiloint2double(ra.w, ra.z) + __hiloint2double(rb.w, rb.z);
-        const double band = a.screen_slack * (4e-7 * (kT + fabs(L_l)) + 1e-9 * fabs(dE_l)) + etol;
-        t_acc = lane < nb && (dE_l < L_l - band);
-        t_bdr = lane < nb && !t_acc && !(dE_l > L_l + band);
+        const double m_l = c_rel * fabs(dE_l);
+        t_acc = lane < nb && (dE_l + m_l < (double)th.x);
+        t_bdr = lane < nb && !t_acc && !(dE_l - m_l > (double)th.y);
         cm_l = lane < nb ? (uint32_t)(ra.x | rb.x) : 0u;
       }
       const uint32_t tmask = __ballot_sync(0xffffffffu, t_acc);
