@@ -1,3 +1,6 @@
-python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench.err
-python bench.py > gpurun_out/r02_bench.json 2>> gpurun_out/r02_bench.err
-tail -c 300 gpurun_out/r02_bench.json; tail -n 3 gpurun_out/r02_bench.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err
+tail -c 200 gpurun_out/r02_bench_n8.json; tail -n 2 gpurun_out/r02_bench_n8.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/r02_bench_n4.json 2> gpurun_out/r02_bench_n4.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err
+PT_L=12 PT_N=512 PT_STEPS=1728 PT_ROUNDS=6 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 scripts/pt_multi.py > gpurun_out/r02_pt_multi_n8.log 2>&1
+tail -n 1 gpurun_out/r02_pt_multi_n8.log
