@@ -203,3 +203,16 @@ def test_product_never_imports_oracle():
                     "import oracle" not in txt and "from oracle" not in txt
                 assert "from oracle" not in txt and "import oracle" not in txt
                 assert "ce_oracle" not in txt
+
+
+def test_ce_wrapper_pure_helpers():
+    """Host helpers of the CE wrapper that need no device: largest cluster size named in the ECIs
+    (ce_calculator.py:120-133) and the self-interaction check (:596-611)."""
+    from cemc_b200.ce_calculator import get_max_size_eci, _clusters_overlap
+    assert get_max_size_eci({"c0": 0.0, "c1_0": 0.1, "c2_d0000_0_00": 0.2, "c4_d0000_0_0000": 0.3}) == 4
+    assert get_max_size_eci({}) == 0
+    ok = [{"c2_a": {"ref_indx": 0, "indices": [[1], [2]]}, "c3_a": {"ref_indx": 0, "indices": [[1, 2], [3, 4]]}}]
+    assert not _clusters_overlap(ok)
+    own_site = [{"c2_a": {"ref_indx": 0, "indices": [[1], [0]]}}]                 # the reference site in its own sub-cluster
+    twice = [{"c3_a": {"ref_indx": 0, "indices": [[1, 2], [3, 3]]}}]              # the same site twice
+    assert _clusters_overlap(own_site) and _clusters_overlap(twice)
