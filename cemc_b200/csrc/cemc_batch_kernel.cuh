@@ -92,7 +92,7 @@ struct BatchSmem {
   int32_t *prop;            // [B][8] decoded proposal
   int2 *scr;                // [2][BT] {conflict mask (bit k: move b reads a site move k changes), screen verdict (1 accept, 2 inconclusive)}
   uint32_t *bmap;           // [B][ceil(N / 32)] per evaluation warp: the sites its move gathers (conflict masks), 0 words for large cells
-  int4 *rec;                // [2][2][BT] site split: {conflict mask, -, dE} of changed site 0 / 1 (summed by the deciding warps)
+  int4 *rec;                // [2][2][BT] site split: {conflict mask, -, dE} of changed site 0 / 1 (summed by every warp when it decides)
   int32_t *ctl;             // cluster protocol: [0..1] mailbox of the exact decision (CTA 1), [4..5] landing pad of the other CTA's token
   int32_t *list;
   int8_t *occ;
@@ -179,12 +179,12 @@ __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, 
 // The CTA has B evaluation warps plus one OBSERVER warp (CTA 0 only does work in
 // it): it folds the decided moves of batch k into the Averager / SGCObserver sums
 // while the evaluation warps are already busy with batch k+1, which takes the
-// per-move observer arithmetic off the deciding warp.
+// per-move observer arithmetic off the evaluation / decision path.
 // kSpin: binary +-1 basis -- the evaluation of a move is the XOR / ballot / popcount
 // scheme of cemc_spin_kernel.cuh instead of fp64 products (same quotients, bit for bit).
-// M: moves per evaluation warp and batch (one after the other): M = 2 doubles the batch at the
-// same number of warps / registers, so the per-batch costs (two barriers, the decision pass)
-// are shared by twice as many moves; the price is more speculation lost on hot chains.
+// M: moves per evaluation warp and batch (spin evaluation: interleaved instruction streams): M = 2
+// doubles the batch at the same number of warps, so the per-batch costs (the barrier, the decision
+// pass) are shared by twice as many moves; the price is more speculation lost on hot chains.
 // kSplit (canonical, C = 2): SITE SPLIT -- both CTAs of the cluster evaluate the SAME B moves of a
 // batch, CTA q the CF change of changed site q of every swap (update_cf is called once per changed
 // site, ce_updater.cpp:845-852, and the two calls only meet in the sum of their increments).  A
@@ -222,7 +222,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   const bool is_obs = (lwarp == B);              // the observer warp (works in CTA 0 only)
   const int warp = is_obs ? 1000 : (kSplit ? lwarp : crank * B + lwarp);   // move index of an evaluation warp
   const int jb = kSplit ? crank : 0;             // first changed site this warp evaluates
-  const bool is_decider = (warp == 0) && (!kSplit || crank == 0);
+  const bool is_decider = (warp == 0) && (!kSplit || crank == 0);   // the ONE warp that counts accepted moves, writes g_loc, mails exact decisions
   auto csync = [&]() { if (C > 1) cg::this_cluster().sync(); else __syncthreads(); };
   const int N = t.N, K = t.K, KP = t.KP, S = t.S, D = t.D, VS = t.VS, n_eci = t.n_eci;
   const int RB = D * KP;
@@ -568,7 +568,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
   // reference's order, off the critical path (it runs while the evaluation warps work on the
   // next batch): CF increments per accepted move (:404), ordered energy dot products
   // (:236-242, one lane per move), trace records, Averager / SGCObserver sums
-  // (montecarlo.py:811-814, mc_observers.py:264-270).  The deciding warp only needs the CF
+  // (montecarlo.py:811-814, mc_observers.py:264-270).  The deciding warps only need the CF
   // vector and the energy for an inconclusive screen; they are published in s.pub.
   auto bookkeep = [&](int nd, uint32_t accmask, int base, int pp) {
 #ifdef CEMC_PHASE_TIMING
@@ -833,8 +833,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
       return m;
     };
 
-    // every warp decides: the evaluating warp screens its own move (the expression of the deciding warp below,
-    // on the same operands): 1 = accept, 2 = inconclusive, 0 = reject
+    // the evaluating warp screens its own move against the two thresholds of its proposal record:
+    // 1 = accept, 2 = inconclusive, 0 = reject
     auto screen = [&](int b, double dE) -> int {
       const float2 th = *reinterpret_cast<const float2 *>(&s.ring[(int)((sdone + b) & 127) * 2 + 1].z);
       const double m = c_rel * fabs(dE);
@@ -877,7 +877,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
             site[mi][0] = s.list[slot0]; site[mi][1] = s.list[slot1];
             oldv[mi][0] = newv[mi][1]; oldv[mi][1] = newv[mi][0];
           }
-          if (lane == 0)                           // the deciding warp commits from this record
+          if (lane == 0)                           // every warp commits from this record
             put_prop(par, b, make_int4(site[mi][0], site[mi][1], newv[mi][0], newv[mi][1]),
                      make_int4(oldv[mi][0], oldv[mi][1], slot0, slot1));
         }
@@ -997,7 +997,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         old0 = new1; old1 = new0;
       }
       double *Vb = s.V + lwarp * NJ * VS;
-      if (lane == 0)                             // the deciding warp commits from this record
+      if (lane == 0)                             // every warp commits from this record
         put_prop(par, b, make_int4(site0, site1, new0, new1), make_int4(old0, old1, slot0, slot1));
       if (kTab) {
         CEMC_TICK(5);
