@@ -888,23 +888,26 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
             gs[mi][je] = -1; gs2[mi][je] = -1; qv[mi][je] = 0.0;
             if (je < NJE) {
               const int j = jb + je;
+              // (selects, not a run-time index: with the site split j is the CTA rank)
+              const int site_j = j ? site[mi][1] : site[mi][0];
+              const int newv_j = j ? newv[mi][1] : newv[mi][0], oldv_j = j ? oldv[mi][1] : oldv[mi][0];
               uint32_t v = 0;
               if (lane < K) {
-                const int nbs = neighbour(site[mi][j], lane, my_shift);
+                const int nbs = neighbour(site_j, lane, my_shift);
                 gs[mi][je] = nbs;
                 v = (uint32_t)s.occ[nbs];
                 if (j == 1 && nbs == site[mi][0]) v = (uint32_t)newv[mi][0];   // change 1 sees change 0 applied (:845-852)
-              } else if (lane == K) gs[mi][je] = site[mi][j];
+              } else if (lane == K) gs[mi][je] = site_j;
               typename std::conditional<kWide, unsigned long long, uint32_t>::type ob =
                   __ballot_sync(0xffffffffu, (v & 1u) != 0u);
               if (kWide) {                         // columns 32 .. K-1 and the site itself in the upper half
                 uint32_t v1 = 0;
                 if (lane + 32 < K) {
-                  const int nbs = neighbour(site[mi][j], lane + 32, my_shift2);
+                  const int nbs = neighbour(site_j, lane + 32, my_shift2);
                   gs2[mi][je] = nbs;
                   v1 = (uint32_t)s.occ[nbs];
                   if (j == 1 && nbs == site[mi][0]) v1 = (uint32_t)newv[mi][0];
-                } else if (lane + 32 == K) gs2[mi][je] = site[mi][j];
+                } else if (lane + 32 == K) gs2[mi][je] = site_j;
                 ob |= (unsigned long long)__ballot_sync(0xffffffffu, (v1 & 1u) != 0u) << 32;
               }
               int cnt = 0;
@@ -915,8 +918,8 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                   cnt += __popc(__ballot_sync(0xffffffffu, bit != 0u) & smask[q]);
                 }
               }
-              qv[mi][je] = s.qtab[(newv[mi][j] * sp.wq + cnt) * 32 + lane];   // n dsigma (M - 2 cnt) / den, :393-402
-              if (replay && newv[mi][j] == oldv[mi][j]) qv[mi][je] = 0.0;   // recorded no-op change (:315): the table assumes old != new
+              qv[mi][je] = s.qtab[(newv_j * sp.wq + cnt) * 32 + lane];   // n dsigma (M - 2 cnt) / den, :393-402
+              if (replay && newv_j == oldv_j) qv[mi][je] = 0.0;   // recorded no-op change (:315): the table assumes old != new
             }
           }
         }
@@ -1003,28 +1006,34 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
         CEMC_TICK(5);
         // ---- table evaluation: neighbour occupations stay in registers (lane c = column c),
         // sub-cluster codes by shuffles, sums over sub-clusters from the product tables
-        const int sites[2] = {site0, site1};
-        const int olds[2] = {old0, old1}, news[2] = {new0, new1};
+        // this warp's changed site(s), picked with selects: with the site split the index is the CTA
+        // rank, and a run-time index into a local array would put it into local memory
+        int sites[NJE], olds[NJE], news[NJE];
+#pragma unroll
+        for (int je = 0; je < NJE; je++) {
+          const bool second = kSplit ? (crank != 0) : (je != 0);
+          sites[je] = second ? site1 : site0; olds[je] = second ? old1 : old0; news[je] = second ? new1 : new0;
+        }
         uint32_t *cw = s.codes + lwarp * NJ * n_sub;
         int gsite[2] = {0, 0};                    // multi: symmetry group of the changed site(s)
 #pragma unroll
         for (int je = 0; je < NJE; je++) {
           const int j = jb + je;
-          if (multi) gsite[je] = __ldg(&t.symm_of_site[sites[j]]);
+          if (multi) gsite[je] = __ldg(&t.symm_of_site[sites[je]]);
           int v = 0, v2 = 0;
           if (lane < K) {
-            const int nbs = neighbour(sites[j], lane, my_shift);
+            const int nbs = neighbour(sites[je], lane, my_shift);
             gsx[je] = nbs;
             v = s.occ[nbs];
             if (j && nbs == site0) v = new0;      // change 1 sees change 0 applied (:845-852)
-          } else if (lane == K) gsx[je] = sites[j];
+          } else if (lane == K) gsx[je] = sites[je];
           if (kWide) {                            // 32 <= K <= 63: a second column per lane
             if (lane + 32 < K) {
-              const int nbs = neighbour(sites[j], lane + 32, my_shift2);
+              const int nbs = neighbour(sites[je], lane + 32, my_shift2);
               gsy[je] = nbs;
               v2 = s.occ[nbs];
               if (j && nbs == site0) v2 = new0;
-            } else if (lane + 32 == K) gsy[je] = sites[j];
+            } else if (lane + 32 == K) gsy[je] = sites[je];
           }
           auto occ_of_col = [&](uint32_t col) -> int {
             const int a1 = __shfl_sync(0xffffffffu, v, (int)(col & 31u));
@@ -1046,7 +1055,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
               const uint32_t rest = (uint32_t)va * (dy & 0xffu) + (uint32_t)vb * ((dy >> 8) & 0xffu) +
                                     (uint32_t)vc * ((dy >> 16) & 0xffu);
               const uint32_t wr = dy >> 24, nd = dx >> 24;            // nd: decorations per table row
-              const uint32_t cO = (rest + (uint32_t)olds[j] * wr) * nd, cN = (rest + (uint32_t)news[j] * wr) * nd;
+              const uint32_t cO = (rest + (uint32_t)olds[je] * wr) * nd, cN = (rest + (uint32_t)news[je] * wr) * nd;
               uint32_t word = (cO << TSH) | (cN << (16 + TSH));
               if (dy == 0u) { const uint32_t z = (dx & 0xffffu) >> (3 - TSH); word = z | (z << 16); }   // padding: the table's zero row
               if (q * 32 + lane < n_sub) cw[je * n_sub + q * 32 + lane] = word;
@@ -1153,7 +1162,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
                   const int4 f = __ldg(&t.fin_i[gsite[je] * n_eci + i]);
                   const double2 fd = __ldg(&t.fin_d[gsite[je] * n_eci + i]);
                   if (f.x == 1) {
-                    qj = __ddiv_rn(__dsub_rn(s.bf[f.y * S + news[jb + je]], s.bf[f.y * S + olds[jb + je]]), dN);
+                    qj = __ddiv_rn(__dsub_rn(s.bf[f.y * S + news[je]], s.bf[f.y * S + olds[je]]), dN);
                   } else if (f.x == 2) {
                     double num = 0.0;
                     for (int q = f.z; q < f.w; q++) num = __dadd_rn(num, db[je * max_tasks + q]);    // :397
@@ -1174,7 +1183,7 @@ batch_kernel(DeviceTables t, ReplicaState st, RunArgs a, int acc_stride, SpinTab
             if (f_kind[e] == 1) {                             // :366-371
 #pragma unroll
               for (int je = 0; je < NJE; je++)
-                num[je] = __dsub_rn(s.bf[f_d[e] * S + news[jb + je]], s.bf[f_d[e] * S + olds[jb + je]]);
+                num[je] = __dsub_rn(s.bf[f_d[e] * S + news[je]], s.bf[f_d[e] * S + olds[je]]);
             } else if (f_kind[e] == 2) {
               // sum over the decorations in the stored order (:397), four loads in flight at a time
               for (int q0 = 0; q0 < f_nd[e]; q0 += 4) {
